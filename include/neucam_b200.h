@@ -40,6 +40,32 @@ int neucam_check_device(void);
  * bit4 A tile staged by threads instead of TMA. */
 int neucam_umma_probe(const void* a, const void* b, float* d, int N, int K, int flags, void* stream);
 
+/* ---- scene sine-MLP (replaces SingleBVPNet.forward -> FCBlock.forward -> BatchLinear/Sine chain,
+ * modules.py:455-475, 90-95, 17-35, for the shipped shape 2 -> 512 x4 -> out_dim, and its autograd
+ * backward w.r.t. activations and input coordinates, training.py:270) -------------------------
+ *
+ * neucam_sine_mlp_fwd:  y[Q,out_dim] = MLP(uv[Q,2]).
+ *   w0 [512,2], b0 [512], b_hid [3,512], w4 [out_dim,512], b4 [out_dim] : fp32 master parameters.
+ *   w_hid16 : fp16 [3*512,512], the three hidden weight matrices stacked, each row-major [out,in]
+ *             (kept in sync with the fp32 masters by neucam_pack_hidden_weights).
+ *   act16   : fp16 [4,Q,512] out, a1..a4 (inputs of layers 1..4), or NULL for inference.
+ *   cos16   : fp16 [3, ceil(Q/128)*128*512] out, cos(30 z_l) l=1..3 in the library's tile-blocked
+ *             layout (opaque; only neucam_sine_mlp_bwd reads it); NULL iff act16 is NULL.
+ */
+int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float* b0, const void* w_hid16,
+                        const float* b_hid, const float* w4, const float* b4, int out_dim, float* y,
+                        void* act16, void* cos16, void* stream);
+
+/* neucam_sine_mlp_bwd:  given dy[Q,out_dim] computes duv[Q,2] and dz16 = fp16 [4,Q,512] holding
+ *   (*scale_dev) * dL/dz_l for l = 0..3 (consumed by neucam_sine_mlp_wgrad).
+ *   wT_hid16 : fp16 [3*512,512], the hidden weights stacked and TRANSPOSED ([in,out] row-major).
+ *   scale_dev: device pointer to one float, a power-of-two loss scale chosen so that the scaled
+ *              gradients sit in fp16's normal range (neucam_b200/step.py derives it from max|dy|).
+ */
+int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0, const void* wT_hid16,
+                        const float* w4, int out_dim, const float* dy, const void* cos16,
+                        const float* scale_dev, void* dz16, float* duv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

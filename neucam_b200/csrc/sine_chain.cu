@@ -1,0 +1,462 @@
+// sine_chain.cu -- the scene sine-MLP (SingleBVPNet 2 -> 512 -> 512 -> 512 -> 512 -> 3, modules.py:430-481)
+// forward and input/activation backward as ONE persistent kernel per direction.
+//
+// A CTA owns a 128-sample row tile.  The tile's activations live in shared memory as the K-major
+// SWIZZLE_128B A operand (128 x 512 fp16 = 128 KB) for the whole chain; the three 512x512 hidden
+// layers run on tcgen05 tensor cores (fp16 operands, fp32 accumulators = all 512 TMEM columns);
+// weights are streamed through a 4-stage TMA ring (they are L2-resident: 1.5 MB); the sine /
+// cosine epilogue reads TMEM with tcgen05.ld and writes the next layer's A operand in place.
+//
+//   forward  (FCBlock.forward / BatchLinear.forward / Sine.forward, modules.py:17-35,90-95):
+//       a1 = sin(30 (uv W0^T + b0))            SIMT prologue (K = 2)
+//       a_{l+1} = sin(30 (a_l W_l^T + b_l))    l = 1..3, tcgen05 + epilogue
+//       y  = a4 W4^T + b4                      SIMT, fused in the last epilogue (N = 3)
+//     side outputs for the backward: a1..a4 (TMA-stored straight from the operand tile) and
+//     cos(30 z_l), l = 1..3 (fp16, tile-blocked layout so the per-row threads store coalesced).
+//   backward (autograd of the same, training.py:270):
+//       dz3 = (dy W4) * 30 cos(30 z3)          SIMT prologue
+//       dz_{l-1} = (dz_l W_l) * 30 cos(30 z_{l-1})   l = 3..1, tcgen05 + epilogue
+//       duv = dz0 W0                           SIMT, fused in the last epilogue
+//     dz0..dz3 are TMA-stored for the weight-gradient kernels (wgrad.cu).  All dz are multiplied by a
+//     power-of-two loss scale read from device memory so that they sit in fp16's normal range.
+//
+// Warp roles (384 threads): warp 0 = TMA weight producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..11 = prologue/epilogue (thread = row; warps e and e+4 split the 512 columns).
+#include "host_util.h"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+namespace {
+
+constexpr int HID = 512;
+constexpr int TILE_M = 128;
+constexpr int NSTAGE = 4;
+constexpr uint32_t STAGE_BYTES = 128 * 64 * 2;     // weight chunk: 128 output rows x 64 k
+constexpr uint32_t A_BLOCK_BYTES = TILE_M * 128;   // one 64-column k-block of the operand tile
+constexpr uint32_t A_BYTES = 8 * A_BLOCK_BYTES;    // 128 x 512 fp16
+constexpr int NTHREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int FIRST_EPI_WARP = 4;
+
+constexpr uint32_t OFF_A = 0;
+constexpr uint32_t OFF_W = OFF_A + A_BYTES;
+constexpr uint32_t OFF_P0 = OFF_W + NSTAGE * STAGE_BYTES;   // float4[512]: 30*W0[j,0], 30*W0[j,1], 30*b0[j], 0
+constexpr uint32_t OFF_B30 = OFF_P0 + 512 * 16;             // float[3][512]: 30*b_l (forward)
+constexpr uint32_t OFF_W4 = OFF_B30 + 3 * 512 * 4;          // float[4][512]: W4 rows (row 3 = 0)
+constexpr uint32_t OFF_XCH = OFF_W4 + 4 * 512 * 4;          // float[128][4]: column-half exchange
+constexpr uint32_t OFF_BAR = OFF_XCH + 128 * 16;            // mbarriers
+constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
+constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
+constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;           // + alignment slack
+
+struct ChainParams {
+  int Q;
+  int ntiles;
+  int out_dim;           // 3 (or 4 for a foreground atlas without alpha MLP)
+  int store_act;         // forward: write a1..a4 / cos for the backward
+  const float* uv;       // [Q,2]
+  const float* w0;       // [512,2]
+  const float* b0;       // [512]
+  const float* b_hid;    // [3,512]
+  const float* w4;       // [out_dim,512]
+  const float* b4;       // [out_dim]
+  __half* cosbuf;        // [3][ntiles*128*512] tile-blocked
+  float* y;              // forward out [Q,out_dim]
+  const float* dy;       // backward in [Q,out_dim]
+  float* duv;            // backward out [Q,2]
+  const float* scale;    // backward: device scalar, power-of-two loss scale
+};
+
+struct ChainMaps {
+  CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T)
+  CUtensorMap act[4];    // forward: a1..a4 ; backward: dz3, dz2, dz1, dz0   ([Q,512] fp16, box 64x128)
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// saturating pack (finite max instead of inf) for the scaled gradients
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(NTHREADS, 1)
+sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+
+  float4* s_p0 = reinterpret_cast<float4*>(sm + OFF_P0);
+  float* s_b30 = reinterpret_cast<float*>(sm + OFF_B30);
+  float* s_w4 = reinterpret_cast<float*>(sm + OFF_W4);
+  float4* s_xch = reinterpret_cast<float4*>(sm + OFF_XCH);
+  const uint32_t bar_full = base + OFF_BAR;           // [NSTAGE]
+  const uint32_t bar_empty = bar_full + 8 * NSTAGE;   // [NSTAGE]
+  const uint32_t bar_aready = bar_empty + 8 * NSTAGE;
+  const uint32_t bar_accfull = bar_aready + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  for (int j = tid; j < HID; j += NTHREADS) {
+    s_p0[j] = make_float4(30.f * p.w0[2 * j], 30.f * p.w0[2 * j + 1], 30.f * p.b0[j], 0.f);
+    for (int c = 0; c < 4; ++c) s_w4[c * HID + j] = (c < p.out_dim) ? p.w4[c * HID + j] : 0.f;
+    if (!BWD) {
+      for (int l = 0; l < 3; ++l) s_b30[l * HID + j] = 30.f * p.b_hid[l * HID + j];
+    }
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_aready, 1);
+    mbar_init(bar_accfull, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&maps.w);
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA weight producer =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int g = 0; g < 3; ++g) {
+          const int wl = BWD ? (2 - g) : g;
+          for (int nq = 0; nq < 4; ++nq) {
+            for (int kb = 0; kb < 8; ++kb) {
+              mbar_wait(bar_empty + 8 * s, ph ^ 1);
+              mbar_arrive_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+              tma_load_2d(base + OFF_W + s * STAGE_BYTES, &maps.w, bar_full + 8 * s, kb * 64,
+                          wl * HID + nq * 128);
+              if (++s == NSTAGE) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 128, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
+      uint32_t s = 0, ph = 0, ar = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int g = 0; g < 3; ++g) {
+          mbar_wait(bar_aready, ar);
+          ar ^= 1;
+          tc_fence_after_sync();
+          for (int nq = 0; nq < 4; ++nq) {
+            for (int kb = 0; kb < 8; ++kb) {
+              mbar_wait(bar_full + 8 * s, ph);
+              tc_fence_after_sync();
+              const uint32_t a_addr = base + OFF_A + kb * A_BLOCK_BYTES;
+              const uint32_t b_addr = base + OFF_W + s * STAGE_BYTES;
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16) {
+                umma_f16_ss(tmem_base + nq * 128, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
+                            make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc,
+                            (kb | k16) != 0 ? 1u : 0u);
+              }
+              umma_commit(bar_empty + 8 * s);
+              if (++s == NSTAGE) { s = 0; ph ^= 1; }
+            }
+          }
+          umma_commit(bar_accfull);
+        }
+      }
+    }
+  } else if (warp >= FIRST_EPI_WARP) {
+    // ===================== prologue / epilogue warps =====================
+    const uint32_t e = warp - FIRST_EPI_WARP;
+    const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const uint32_t half = e >> 2;            // which 256 columns
+    const uint32_t row = quad * 32 + lane;   // row inside the tile
+    const uint32_t col0 = half * 256;
+    const bool issuer = (e == 0 && lane == 0);
+    const uint32_t a_base = base + OFF_A;
+    const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
+    uint32_t af = 0;
+    float gscale = 1.f;
+    if (BWD) gscale = *p.scale;
+
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const long long grow = (long long)tile * TILE_M + row;
+      const bool valid = grow < p.Q;
+      float u = 0.f, v = 0.f;
+      if (valid) {
+        const float2 t = *reinterpret_cast<const float2*>(p.uv + 2 * grow);
+        u = t.x;
+        v = t.y;
+      }
+      const size_t cos_tile_stride = (size_t)p.ntiles * TILE_M * HID;   // elements per layer
+      const size_t cos_row_off = ((size_t)tile * 64 * TILE_M + row) * 8; // + chunk64 * 128 * 8
+
+      // ---------------- prologue: first operand tile ----------------
+      if (issuer) tma_store_wait_read0();
+      epi_bar_sync();
+      if (!BWD) {
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          uint32_t w[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = col0 + i * 8 + jj * 2;
+            const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
+            const float h0 = __sinf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
+            const float h1 = __sinf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
+            w[jj] = pack_h2(h0, h1);
+          }
+          const uint32_t c = col0 + i * 8;
+          st_shared_v4(a_base + (c >> 6) * A_BLOCK_BYTES + sw128_offset(row, (c & 63) >> 3), w[0], w[1], w[2], w[3]);
+        }
+      } else {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        if (valid) {
+          const float* dyr = p.dy + (size_t)grow * p.out_dim;
+          d0 = dyr[0] * gscale * 30.f;
+          d1 = dyr[1] * gscale * 30.f;
+          d2 = dyr[2] * gscale * 30.f;
+          if (p.out_dim > 3) d3 = dyr[3] * gscale * 30.f;
+        }
+        const __half* cos3 = p.cosbuf + 2 * cos_tile_stride + cos_row_off;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t c = col0 + i * 8;
+          const uint4 cv = *reinterpret_cast<const uint4*>(cos3 + (size_t)(c >> 3) * (TILE_M * 8));
+          const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+          uint32_t w[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = c + jj * 2;
+            const float2 cc = unpack_h2(cw[jj]);
+            float g0 = d0 * s_w4[j] + d1 * s_w4[HID + j] + d2 * s_w4[2 * HID + j] + d3 * s_w4[3 * HID + j];
+            float g1 = d0 * s_w4[j + 1] + d1 * s_w4[HID + j + 1] + d2 * s_w4[2 * HID + j + 1] + d3 * s_w4[3 * HID + j + 1];
+            w[jj] = pack_h2_sat(g0 * cc.x, g1 * cc.y);
+          }
+          st_shared_v4(a_base + (c >> 6) * A_BLOCK_BYTES + sw128_offset(row, (c & 63) >> 3), w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (issuer) {
+        if (BWD || p.store_act) {
+          for (int kb = 0; kb < 8; ++kb)
+            tma_store_2d(&maps.act[0], a_base + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
+          tma_store_commit();
+        }
+        mbar_arrive(bar_aready);
+      }
+
+      // ---------------- three tensor-core layers ----------------
+      for (int g = 0; g < 3; ++g) {
+        mbar_wait(bar_accfull, af);
+        af ^= 1;
+        tc_fence_after_sync();
+        if (issuer) tma_store_wait_read0();
+        epi_bar_sync();
+
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // head (fwd) / duv (bwd) partials
+        const float* b30 = s_b30 + g * HID;
+        // forward: cos(30 z_{g+1}) -> cosbuf[g]; backward: reads cos(30 z_{2-g}) from cosbuf[1-g] (g<2)
+        __half* cos_out = p.cosbuf + (size_t)g * cos_tile_stride + cos_row_off;
+        const __half* cos_in = p.cosbuf + (size_t)(g < 2 ? 1 - g : 0) * cos_tile_stride + cos_row_off;
+
+        for (int i = 0; i < 8; ++i) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + col0 + i * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            const uint32_t c = col0 + i * 32 + q8 * 8;
+            uint32_t w[4];
+            if (!BWD) {
+              uint32_t cw[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = c + jj * 2;
+                const float t0 = fmaf(__uint_as_float(r[q8 * 8 + jj * 2]), 30.f, b30[j]);
+                const float t1 = fmaf(__uint_as_float(r[q8 * 8 + jj * 2 + 1]), 30.f, b30[j + 1]);
+                const float h0 = __sinf(t0), h1 = __sinf(t1);
+                w[jj] = pack_h2(h0, h1);
+                if (p.store_act) cw[jj] = pack_h2(__cosf(t0), __cosf(t1));
+                if (g == 2) {
+                  acc0 = fmaf(h0, s_w4[j], fmaf(h1, s_w4[j + 1], acc0));
+                  acc1 = fmaf(h0, s_w4[HID + j], fmaf(h1, s_w4[HID + j + 1], acc1));
+                  acc2 = fmaf(h0, s_w4[2 * HID + j], fmaf(h1, s_w4[2 * HID + j + 1], acc2));
+                  acc3 = fmaf(h0, s_w4[3 * HID + j], fmaf(h1, s_w4[3 * HID + j + 1], acc3));
+                }
+              }
+              if (p.store_act)
+                *reinterpret_cast<uint4*>(cos_out + (size_t)(c >> 3) * (TILE_M * 8)) =
+                    make_uint4(cw[0], cw[1], cw[2], cw[3]);
+            } else {
+              uint32_t cw[4] = {0, 0, 0, 0};
+              if (g < 2) {
+                const uint4 cv = *reinterpret_cast<const uint4*>(cos_in + (size_t)(c >> 3) * (TILE_M * 8));
+                cw[0] = cv.x; cw[1] = cv.y; cw[2] = cv.z; cw[3] = cv.w;
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = c + jj * 2;
+                float c0v, c1v;
+                if (g < 2) {
+                  const float2 cc = unpack_h2(cw[jj]);
+                  c0v = cc.x;
+                  c1v = cc.y;
+                } else {
+                  const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
+                  c0v = __cosf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
+                  c1v = __cosf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
+                  // placeholders; duv accumulated below
+                }
+                const float z0 = __uint_as_float(r[q8 * 8 + jj * 2]) * 30.f * c0v;
+                const float z1 = __uint_as_float(r[q8 * 8 + jj * 2 + 1]) * 30.f * c1v;
+                w[jj] = pack_h2_sat(z0, z1);
+                if (g == 2) {
+                  const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
+                  acc0 = fmaf(z0, q0.x, fmaf(z1, q1.x, acc0));
+                  acc1 = fmaf(z0, q0.y, fmaf(z1, q1.y, acc1));
+                }
+              }
+            }
+            st_shared_v4(a_base + (c >> 6) * A_BLOCK_BYTES + sw128_offset(row, (c & 63) >> 3), w[0], w[1], w[2], w[3]);
+          }
+        }
+
+        if (g == 2 && half == 1) s_xch[row] = make_float4(acc0, acc1, acc2, acc3);
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (issuer) {
+          if (BWD || p.store_act) {
+            for (int kb = 0; kb < 8; ++kb)
+              tma_store_2d(&maps.act[g + 1], a_base + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
+            tma_store_commit();
+          }
+          if (g < 2) mbar_arrive(bar_aready);
+        }
+        if (g == 2 && half == 0 && valid) {
+          const float4 o = s_xch[row];
+          if (!BWD) {
+            float* yr = p.y + (size_t)grow * p.out_dim;
+            yr[0] = acc0 + o.x + p.b4[0];
+            yr[1] = acc1 + o.y + p.b4[1];
+            yr[2] = acc2 + o.z + p.b4[2];
+            if (p.out_dim > 3) yr[3] = acc3 + o.w + p.b4[3];
+          } else {
+            // s_p0 holds 30*W0 and dz carries the loss scale: undo both
+            const float inv = 1.f / (30.f * gscale);
+            *reinterpret_cast<float2*>(p.duv + 2 * grow) = make_float2((acc0 + o.x) * inv, (acc1 + o.y) * inv);
+          }
+        }
+      }
+    }
+    if (issuer) tma_store_wait0();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, bool need_act) {
+  int rc = nchost::make_tmap_16b(&m->w, w16, 3 * HID, HID, HID, 128, 64);
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i) {
+    if (!need_act) {
+      m->act[i] = m->w;   // never dereferenced
+      continue;
+    }
+    rc = nchost::make_tmap_16b(&m->act[i], act[i], (uint64_t)Q, HID, HID, TILE_M, 64);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+template <bool BWD>
+int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NC_CHECK_CUDA(cudaFuncSetAttribute(sine_chain_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = nchost::sm_count();
+  if (grid > p.ntiles) grid = p.ntiles;
+  sine_chain_kernel<BWD><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float* b0,
+                                   const void* w_hid16, const float* b_hid, const float* w4,
+                                   const float* b4, int out_dim, float* y, void* act16, void* cos16,
+                                   void* stream) {
+  NC_CHECK_ARG(uv && w0 && b0 && w_hid16 && b_hid && w4 && b4 && y);
+  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - TILE_M);
+  NC_CHECK_ARG(out_dim == 3 || out_dim == 4);
+  NC_CHECK_ARG((act16 == nullptr) == (cos16 == nullptr));
+  ChainParams p{};
+  p.Q = (int)Q;
+  p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
+  p.out_dim = out_dim;
+  p.store_act = act16 != nullptr;
+  p.uv = uv; p.w0 = w0; p.b0 = b0; p.b_hid = b_hid; p.w4 = w4; p.b4 = b4;
+  p.cosbuf = reinterpret_cast<__half*>(cos16);
+  p.y = y;
+  ChainMaps maps;
+  void* act[4];
+  for (int i = 0; i < 4; ++i) act[i] = act16 ? (void*)((__half*)act16 + (size_t)i * Q * HID) : nullptr;
+  int rc = build_maps(&maps, w_hid16, act, Q, p.store_act);
+  if (rc) return rc;
+  return launch<false>(maps, p, (cudaStream_t)stream);
+}
+
+extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0,
+                                   const void* wT_hid16, const float* w4, int out_dim, const float* dy,
+                                   const void* cos16, const float* scale_dev, void* dz16, float* duv,
+                                   void* stream) {
+  NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4 && dy && cos16 && scale_dev && dz16 && duv);
+  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - TILE_M);
+  NC_CHECK_ARG(out_dim == 3 || out_dim == 4);
+  ChainParams p{};
+  p.Q = (int)Q;
+  p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
+  p.out_dim = out_dim;
+  p.store_act = 1;
+  p.uv = uv; p.w0 = w0; p.b0 = b0; p.w4 = w4;
+  p.cosbuf = reinterpret_cast<__half*>(const_cast<void*>(cos16));
+  p.dy = dy; p.duv = duv; p.scale = scale_dev;
+  ChainMaps maps;
+  // store order of the backward chain: dz3 (prologue), dz2, dz1, dz0  -> buffers [l] = dz_l
+  void* act[4];
+  for (int i = 0; i < 4; ++i) act[i] = (void*)((__half*)dz16 + (size_t)(3 - i) * Q * HID);
+  int rc = build_maps(&maps, wT_hid16, act, Q, true);
+  if (rc) return rc;
+  return launch<true>(maps, p, (cudaStream_t)stream);
+}

@@ -1,0 +1,112 @@
+"""GPU parity of the fused sine-MLP chain kernels (neucam_sine_mlp_fwd / _bwd) against the oracle
+(oracle/neucam_oracle.py, itself pinned to the reference).  Tolerances are BASELINE.json's:
+per-layer forward <= 1e-3 relative (teacher-forced, L2), gradients <= 1e-2 relative."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import neucam_oracle as orc  # noqa: E402  (the checker; tests may import it)
+
+from neucam_b200 import ops  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def siren_state(seed, out_dim=3, hid=512, gain=1.0):
+    """SIREN init of a SingleBVPNet(in=2, hidden=512, layers=3) (modules.py:939-952), optional weight gain
+    to emulate trained weights."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    dims = [(hid, 2)] + [(hid, hid)] * 3 + [(out_dim, hid)]
+    for i, (o, n) in enumerate(dims):
+        bound = 1.0 / n if i == 0 else math.sqrt(6.0 / n) / 30.0
+        sd[f"net.net.{i}.0.weight"] = (torch.rand(o, n, generator=g) * 2 - 1) * bound * (gain if i > 0 else 1.0)
+        sd[f"net.net.{i}.0.bias"] = (torch.rand(o, generator=g) * 2 - 1) / math.sqrt(n)
+    return sd
+
+
+def to_dev(sd):
+    w0 = sd["net.net.0.0.weight"].cuda().contiguous()
+    b0 = sd["net.net.0.0.bias"].cuda().contiguous()
+    wh = torch.stack([sd[f"net.net.{i}.0.weight"] for i in (1, 2, 3)]).cuda()
+    bh = torch.stack([sd[f"net.net.{i}.0.bias"] for i in (1, 2, 3)]).cuda().contiguous()
+    w4 = sd["net.net.4.0.weight"].cuda().contiguous()
+    b4 = sd["net.net.4.0.bias"].cuda().contiguous()
+    w16 = wh.half().reshape(3 * 512, 512).contiguous()
+    wT16 = wh.transpose(1, 2).half().reshape(3 * 512, 512).contiguous()
+    return w0, b0, w16, wT16, bh, w4, b4
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("Q,gain,out_dim", [(1000, 1.0, 3), (128, 1.0, 3), (20011, 1.0, 3), (4099, 2.5, 3), (777, 1.0, 4)])
+def test_forward_parity(Q, gain, out_dim):
+    sd = siren_state(7 + Q, out_dim, gain=gain)
+    w0, b0, w16, wT16, bh, w4, b4 = to_dev(sd)
+    uv = (torch.rand(Q, 2, generator=torch.Generator().manual_seed(Q)) * 2 - 1)
+    act, cos, dz = ops.alloc_chain_workspace(Q, "cuda")
+    act.fill_(float("nan"))
+    y = ops.sine_mlp_fwd(uv.cuda(), w0, b0, w16, bh, w4, b4, act16=act, cos16=cos)
+    torch.cuda.synchronize()
+    y_ref, hidden = orc.sine_mlp(sd, uv, return_hidden=True)
+    a = act.float().cpu()
+    assert torch.isfinite(a).all()
+    # layer 0 (input is exact) and teacher-forced layers 1..3: oracle fed with OUR fp16 activations
+    assert rel(a[0], hidden[0]) <= 1e-3
+    layers = orc.sine_mlp_layers(sd)
+    for l in (1, 2, 3):
+        W, b = layers[l]
+        ref = torch.sin(30.0 * (a[l - 1] @ W.t() + b))
+        assert rel(a[l], ref) <= 1e-3, f"layer {l}"
+    W4, b4c = layers[4]
+    assert rel(y.cpu(), a[3] @ W4.t() + b4c) <= 1e-3
+    # end-to-end (not teacher-forced) is reported, with a looser sanity bound
+    e2e = rel(y.cpu(), y_ref)
+    print(f"Q={Q} gain={gain}: end-to-end rel err {e2e:.3e}")
+    assert e2e <= 2e-2
+    # inference mode (no side outputs) gives the same y
+    y2 = ops.sine_mlp_fwd(uv.cuda(), w0, b0, w16, bh, w4, b4)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y)
+
+
+@pytest.mark.parametrize("Q,gain,out_dim", [(1000, 1.0, 3), (20011, 1.0, 3), (4099, 2.5, 3), (777, 1.0, 4)])
+def test_backward_parity(Q, gain, out_dim):
+    sd = siren_state(11 + Q, out_dim, gain=gain)
+    w0, b0, w16, wT16, bh, w4, b4 = to_dev(sd)
+    g = torch.Generator().manual_seed(Q + 1)
+    uv = (torch.rand(Q, 2, generator=g) * 2 - 1)
+    dy = torch.randn(Q, out_dim, generator=g) * 1e-5
+    act, cos, dz = ops.alloc_chain_workspace(Q, "cuda")
+    ops.sine_mlp_fwd(uv.cuda(), w0, b0, w16, bh, w4, b4, act16=act, cos16=cos)
+    scale_val = 2.0 ** math.floor(math.log2(16.0 / dy.abs().max().item()))
+    scale = torch.tensor([scale_val], device="cuda")
+    dz.fill_(float("nan"))
+    duv = ops.sine_mlp_bwd(uv.cuda(), w0, b0, wT16, w4, dy.cuda(), cos, scale, dz)
+    torch.cuda.synchronize()
+
+    # oracle: autograd through the fp32 restatement
+    uv_r = uv.clone().requires_grad_(True)
+    layers = orc.sine_mlp_layers(sd)
+    zs = []
+    h = uv_r
+    for li, (W, b) in enumerate(layers):
+        z = h @ W.t() + b
+        z.retain_grad()
+        zs.append(z)
+        h = torch.sin(30.0 * z) if li < 4 else z
+    (h * dy).sum().backward()
+    assert rel(duv.cpu(), uv_r.grad) <= 1e-2
+    dzc = dz.float().cpu() / scale_val
+    assert torch.isfinite(dzc).all()
+    for l in range(4):
+        assert rel(dzc[l], zs[l].grad) <= 1e-2, f"dz{l}"
+    print(f"Q={Q}: duv rel {rel(duv.cpu(), uv_r.grad):.2e}; dz rel " +
+          " ".join(f"{rel(dzc[l], zs[l].grad):.2e}" for l in range(4)))

@@ -50,10 +50,5 @@ def test_probe(N, K, flags, name):
     assert err <= 1e-4 * scale, f"{name}: max abs err {err} (scale {scale})"
 
 
-def test_probe_mixed_formats_report():
-    """fp16 x bf16 operand mixing inside kind::f16 -- recorded, used by DESIGN.md's precision plan."""
-    D, ref = _run(256, 128, 8)  # A fp16, B bf16
-    err = (D - ref).abs().max().item()
-    scale = ref.abs().max().item()
-    print(f"mixed fp16xbf16: max abs err {err:.3e} scale {scale:.3e}")
-    assert err <= 1e-4 * scale
+# NOTE (measured on B200, round 1): mixing operand formats inside kind::f16 (A fp16 x B bf16) raises
+# cudaErrorIllegalInstruction, so every GEMM in this library uses ONE 16-bit format for both operands.
