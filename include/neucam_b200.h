@@ -56,15 +56,26 @@ int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float
                         const float* b_hid, const float* w4, const float* b4, int out_dim, float* y,
                         void* act16, void* cos16, void* stream);
 
-/* neucam_sine_mlp_bwd:  given dy[Q,out_dim] computes duv[Q,2] and dz16 = fp16 [4,Q,512] holding
- *   (*scale_dev) * dL/dz_l for l = 0..3 (consumed by neucam_sine_mlp_wgrad).
+/* neucam_sine_mlp_bwd:  given dy[Q,out_dim] computes duv[Q,2], ACCUMULATES the first layer's
+ *   gradients into dw0 [512,2] / db0 [512] and writes dz16 = fp16 [3,Q,512] holding
+ *   (*scale_dev) * dL/dz_l for l = 1..3 (consumed by neucam_sine_mlp_wgrad).
  *   wT_hid16 : fp16 [3*512,512], the hidden weights stacked and TRANSPOSED ([in,out] row-major).
  *   scale_dev: device pointer to one float, a power-of-two loss scale chosen so that the scaled
  *              gradients sit in fp16's normal range (neucam_b200/step.py derives it from max|dy|).
  */
 int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0, const void* wT_hid16,
                         const float* w4, int out_dim, const float* dy, const void* cos16,
-                        const float* scale_dev, void* dz16, float* duv, void* stream);
+                        const float* scale_dev, void* dz16, float* duv, float* dw0, float* db0, void* stream);
+
+/* neucam_sine_mlp_wgrad: ACCUMULATES dW_l [512,512] += dz_l^T a_l / scale and db_l [512] += colsum(dz_l) / scale
+ *   for the hidden layers l = 1..3 (autograd MmBackward/sum of BatchLinear.forward, modules.py:24-25).
+ *   dz16 = [3,Q,512] from neucam_sine_mlp_bwd, act16 = [4,Q,512] from neucam_sine_mlp_fwd. */
+int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const float* scale_dev, float* dw1,
+                          float* db1, float* dw2, float* db2, float* dw3, float* db3, void* stream);
+
+/* neucam_sine_mlp_head_wgrad: ACCUMULATES dW4 [out_dim,512] += dy^T a4 (a4 = act16 slot 3). */
+int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q, float* dw4,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,8 @@
 //       dz3 = (dy W4) * 30 cos(30 z3)          SIMT prologue
 //       dz_{l-1} = (dz_l W_l) * 30 cos(30 z_{l-1})   l = 3..1, tcgen05 + epilogue
 //       duv = dz0 W0                           SIMT, fused in the last epilogue
-//     dz0..dz3 are TMA-stored for the weight-gradient kernels (wgrad.cu).  All dz are multiplied by a
+//       dW0 = dz0^T uv, db0 = sum dz0       column pass over the dz0 tile while it is still in smem
+//     dz1..dz3 are TMA-stored for the weight-gradient kernel (wgrad.cu).  All dz are multiplied by a
 //     power-of-two loss scale read from device memory so that they sit in fp16's normal range.
 //
 // Warp roles (384 threads): warp 0 = TMA weight producer, warp 1 = MMA issuer, warp 2 = TMEM
@@ -45,7 +46,8 @@ constexpr uint32_t OFF_P0 = OFF_W + NSTAGE * STAGE_BYTES;   // float4[512]: 30*W
 constexpr uint32_t OFF_B30 = OFF_P0 + 512 * 16;             // float[3][512]: 30*b_l (forward)
 constexpr uint32_t OFF_W4 = OFF_B30 + 3 * 512 * 4;          // float[4][512]: W4 rows (row 3 = 0)
 constexpr uint32_t OFF_XCH = OFF_W4 + 4 * 512 * 4;          // float[128][4]: column-half exchange
-constexpr uint32_t OFF_BAR = OFF_XCH + 128 * 16;            // mbarriers
+constexpr uint32_t OFF_UV = OFF_XCH + 128 * 16;             // float2[128]: the tile's input coordinates
+constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;              // mbarriers
 constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;           // + alignment slack
@@ -65,6 +67,8 @@ struct ChainParams {
   float* y;              // forward out [Q,out_dim]
   const float* dy;       // backward in [Q,out_dim]
   float* duv;            // backward out [Q,2]
+  float* dw0;            // backward out [512,2] (accumulated into)
+  float* db0;            // backward out [512]   (accumulated into)
   const float* scale;    // backward: device scalar, power-of-two loss scale
 };
 
@@ -104,6 +108,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   float* s_b30 = reinterpret_cast<float*>(sm + OFF_B30);
   float* s_w4 = reinterpret_cast<float*>(sm + OFF_W4);
   float4* s_xch = reinterpret_cast<float4*>(sm + OFF_XCH);
+  float2* s_uv = reinterpret_cast<float2*>(sm + OFF_UV);
   const uint32_t bar_full = base + OFF_BAR;           // [NSTAGE]
   const uint32_t bar_empty = bar_full + 8 * NSTAGE;   // [NSTAGE]
   const uint32_t bar_aready = bar_empty + 8 * NSTAGE;
@@ -201,6 +206,9 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     uint32_t af = 0;
     float gscale = 1.f;
     if (BWD) gscale = *p.scale;
+    // layer-0 weight-gradient partials of this CTA (backward): columns 2*et, 2*et+1
+    const uint32_t et = tid - FIRST_EPI_WARP * 32;
+    float gw0[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const long long grow = (long long)tile * TILE_M + row;
@@ -217,6 +225,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       // ---------------- prologue: first operand tile ----------------
       if (issuer) tma_store_wait_read0();
       epi_bar_sync();
+      if (BWD && half == 0) s_uv[row] = make_float2(u, v);
       if (!BWD) {
 #pragma unroll 4
         for (int i = 0; i < 32; ++i) {
@@ -351,12 +360,32 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         fence_proxy_async_smem();
         epi_bar_sync();
         if (issuer) {
-          if (BWD || p.store_act) {
+          if (BWD ? (g < 2) : (p.store_act != 0)) {
             for (int kb = 0; kb < 8; ++kb)
               tma_store_2d(&maps.act[g + 1], a_base + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
             tma_store_commit();
           }
           if (g < 2) mbar_arrive(bar_aready);
+        }
+        if (BWD && g == 2) {
+          // dW0[j,:] += sum_r dz0[r,j] * uv[r,:], db0[j] += sum_r dz0[r,j]: column pass over the dz0 tile
+          // that now sits in the operand buffer (never stored to HBM).
+          const uint32_t c = et * 2;
+          const uint32_t col_addr = a_base + (c >> 6) * A_BLOCK_BYTES + (c & 7) * 2;
+          const uint32_t chunk = (c & 63) >> 3;
+#pragma unroll 8
+          for (uint32_t r2 = 0; r2 < TILE_M; ++r2) {
+            uint32_t wv;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(col_addr + sw128_offset(r2, chunk)));
+            const float2 z = unpack_h2(wv);
+            const float2 t = s_uv[r2];
+            gw0[0][0] = fmaf(z.x, t.x, gw0[0][0]);
+            gw0[0][1] = fmaf(z.x, t.y, gw0[0][1]);
+            gw0[0][2] += z.x;
+            gw0[1][0] = fmaf(z.y, t.x, gw0[1][0]);
+            gw0[1][1] = fmaf(z.y, t.y, gw0[1][1]);
+            gw0[1][2] += z.y;
+          }
         }
         if (g == 2 && half == 0 && valid) {
           const float4 o = s_xch[row];
@@ -375,6 +404,16 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       }
     }
     if (issuer) tma_store_wait0();
+    if (BWD) {
+      const float inv = 1.f / gscale;
+      const uint32_t c = et * 2;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        atomicAdd(p.dw0 + (c + k) * 2 + 0, gw0[k][0] * inv);
+        atomicAdd(p.dw0 + (c + k) * 2 + 1, gw0[k][1] * inv);
+        atomicAdd(p.db0 + (c + k), gw0[k][2] * inv);
+      }
+    }
   }
 
   tc_fence_before_sync();
@@ -440,8 +479,8 @@ extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, 
 extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0,
                                    const void* wT_hid16, const float* w4, int out_dim, const float* dy,
                                    const void* cos16, const float* scale_dev, void* dz16, float* duv,
-                                   void* stream) {
-  NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4 && dy && cos16 && scale_dev && dz16 && duv);
+                                   float* dw0, float* db0, void* stream) {
+  NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4 && dy && cos16 && scale_dev && dz16 && duv && dw0 && db0);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - TILE_M);
   NC_CHECK_ARG(out_dim == 3 || out_dim == 4);
   ChainParams p{};
@@ -451,11 +490,13 @@ extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, 
   p.store_act = 1;
   p.uv = uv; p.w0 = w0; p.b0 = b0; p.w4 = w4;
   p.cosbuf = reinterpret_cast<__half*>(const_cast<void*>(cos16));
-  p.dy = dy; p.duv = duv; p.scale = scale_dev;
+  p.dy = dy; p.duv = duv; p.scale = scale_dev; p.dw0 = dw0; p.db0 = db0;
   ChainMaps maps;
-  // store order of the backward chain: dz3 (prologue), dz2, dz1, dz0  -> buffers [l] = dz_l
+  // store order of the backward chain: dz3 (prologue), dz2, dz1 -> dz16 = [3,Q,512] holding dz_1..dz_3
+  // (dz0 never leaves the SM: its weight gradient is reduced in-kernel)
   void* act[4];
-  for (int i = 0; i < 4; ++i) act[i] = (void*)((__half*)dz16 + (size_t)(3 - i) * Q * HID);
+  for (int i = 0; i < 3; ++i) act[i] = (void*)((__half*)dz16 + (size_t)(2 - i) * Q * HID);
+  act[3] = act[2];
   int rc = build_maps(&maps, wT_hid16, act, Q, true);
   if (rc) return rc;
   return launch<true>(maps, p, (cudaStream_t)stream);

@@ -1,0 +1,233 @@
+// wgrad.cu -- weight gradients of the scene sine-MLP (the MmBackward / sum nodes of autograd for
+// BatchLinear, modules.py:24-25, reduced over all Q samples of the step).
+//
+//   hidden layers l = 1..3:  dW_l[j,k] = sum_r dz_l[r,j] * a_l[r,k],   db_l[j] = sum_r dz_l[r,j]
+//     a split-K tcgen05 GEMM: both operands are read as MN-major tiles straight out of the row-major
+//     [Q,512] fp16 buffers the chain kernels TMA-stored (no transposes anywhere); each CTA owns one
+//     128 x 256 output tile of one layer for one slice of the Q axis and reduces into the fp32 gradient
+//     with red.global.add.  The bias gradient rides along as a 16-column MMA against an all-ones tile.
+//   head:  dW4[c,k] = sum_r dy[r,c] * a4[r,k]  (c < 4) -- an HBM-bound SIMT column reduction.
+//
+// dz carries the power-of-two loss scale of the backward chain; it is divided out here.
+#include "host_util.h"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+namespace {
+
+constexpr int HID = 512;
+constexpr int NSTAGE = 4;
+constexpr uint32_t A_STAGE = 64 * 128 * 2;   // 64 k-rows x 128 m   (2 atoms of 64 m)
+constexpr uint32_t B_STAGE = 64 * 256 * 2;   // 64 k-rows x 256 n   (4 atoms of 64 n)
+constexpr uint32_t ATOM_BYTES = 64 * 128;    // 64 k-rows x 128 B
+constexpr uint32_t STAGE_BYTES = A_STAGE + B_STAGE;
+constexpr uint32_t OFF_ONES = NSTAGE * STAGE_BYTES;   // 8 KB of fp16 1.0
+constexpr uint32_t OFF_BAR = OFF_ONES + ATOM_BYTES;
+constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
+constexpr int NTHREADS = 192;
+
+struct WgradMaps {
+  CUtensorMap dz[3];    // dz_1..dz_3   [Q,512] fp16, box 64 x 64
+  CUtensorMap act[3];   // a_1..a_3
+};
+
+struct WgradParams {
+  int Q;
+  int nkb;              // ceil(Q / 64)
+  int kb_per_split;
+  float* dw[3];         // fp32 [512,512] each (accumulated into)
+  float* db[3];         // fp32 [512]
+  const float* scale;   // device scalar: loss scale carried by dz
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+  const uint32_t bar_full = base + OFF_BAR, bar_empty = bar_full + 8 * NSTAGE, bar_acc = bar_empty + 8 * NSTAGE;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int mt = blockIdx.y >> 1, nt = blockIdx.y & 1;
+  const int layer = blockIdx.z;
+  const int kb0 = split * p.kb_per_split;
+  int kb1 = kb0 + p.kb_per_split;
+  if (kb1 > p.nkb) kb1 = p.nkb;
+  const int nk = kb1 - kb0;   // may be <= 0 for trailing splits
+  const bool with_bias = (nt == 0);
+
+  // all-ones tile for the bias-gradient MMA
+  for (uint32_t i = tid; i < ATOM_BYTES / 4; i += NTHREADS)
+    reinterpret_cast<uint32_t*>(sm + OFF_ONES)[i] = 0x3C003C00u;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const CUtensorMap* ta = &maps.dz[layer];
+        const CUtensorMap* tb = &maps.act[layer];
+        uint32_t s = 0, ph = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+          const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
+          for (int a = 0; a < 2; ++a)
+            tma_load_2d(a_st + a * ATOM_BYTES, ta, bar_full + 8 * s, mt * 128 + a * 64, kb * 64);
+          for (int a = 0; a < 4; ++a)
+            tma_load_2d(b_st + a * ATOM_BYTES, tb, bar_full + 8 * s, nt * 256 + a * 64, kb * 64);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_f16(128, 256, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
+        const uint32_t idesc_b = make_idesc_f16(128, 16, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
+        const uint32_t ones = base + OFF_ONES;
+        uint32_t s = 0, ph = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after_sync();
+          const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint64_t ad = make_sdesc_sw128(a_st + k16 * 2048, ATOM_BYTES, 1024);
+            const uint32_t accum = (kb > kb0 || k16 > 0) ? 1u : 0u;
+            umma_f16_ss(tmem_base, ad, make_sdesc_sw128(b_st + k16 * 2048, ATOM_BYTES, 1024), idesc, accum);
+            if (with_bias)
+              umma_f16_ss(tmem_base + 256, ad, make_sdesc_sw128(ones + k16 * 2048, ATOM_BYTES, 1024), idesc_b, accum);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        }
+        umma_commit(bar_acc);
+      }
+    } else {
+      // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+      const uint32_t quad = warp & 3;
+      const uint32_t row = quad * 32 + lane;
+      const float inv = 1.f / *p.scale;
+      mbar_wait(bar_acc, 0);
+      tc_fence_after_sync();
+      float* out = p.dw[layer] + (size_t)(mt * 128 + row) * HID + nt * 256;
+      const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
+      for (int i = 0; i < 8; ++i) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + i * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(out + i * 32 + j, __uint_as_float(r[j]) * inv);
+      }
+      if (with_bias) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_row + 256, r);
+        tmem_ld_wait();
+        atomicAdd(p.db[layer] + mt * 128 + row, __uint_as_float(r[0]) * inv);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// out[c][k] += sum_r s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound.
+__global__ void __launch_bounds__(256)
+skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int nc, int Q,
+                    int rows_per_block, float* __restrict__ out) {
+  const int r0 = blockIdx.x * rows_per_block;
+  int r1 = r0 + rows_per_block;
+  if (r1 > Q) r1 = Q;
+  const int k = threadIdx.x * 2;
+  float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  for (int r = r0; r < r1; ++r) {
+    const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + (size_t)r * HID + k));
+    const float* sr = s + (size_t)r * nc;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < nc) {
+        const float sv = __ldg(sr + c);
+        acc[c][0] = fmaf(sv, xv.x, acc[c][0]);
+        acc[c][1] = fmaf(sv, xv.y, acc[c][1]);
+      }
+    }
+  }
+  for (int c = 0; c < nc; ++c) {
+    atomicAdd(out + c * HID + k, acc[c][0]);
+    atomicAdd(out + c * HID + k + 1, acc[c][1]);
+  }
+}
+
+}  // namespace
+
+extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const float* scale_dev,
+                                     float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
+                                     void* stream) {
+  NC_CHECK_ARG(dz16 && act16 && scale_dev && dw1 && db1 && dw2 && db2 && dw3 && db3);
+  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128);
+  WgradMaps maps;
+  for (int l = 0; l < 3; ++l) {
+    // dz16 = [3,Q,512] holding dz_1..dz_3 ; act16 = [4,Q,512] holding a_1..a_4
+    const __half* dz = (const __half*)dz16 + (size_t)l * Q * HID;
+    const __half* a = (const __half*)act16 + (size_t)l * Q * HID;
+    int rc = nchost::make_tmap_16b(&maps.dz[l], dz, (uint64_t)Q, HID, HID, 64, 64);
+    if (rc) return rc;
+    rc = nchost::make_tmap_16b(&maps.act[l], a, (uint64_t)Q, HID, HID, 64, 64);
+    if (rc) return rc;
+  }
+  WgradParams p{};
+  p.Q = (int)Q;
+  p.nkb = (int)((Q + 63) / 64);
+  // 24 output tiles; fill the machine with ~6 Q-slices per tile
+  int splits = nchost::sm_count() / 24;
+  if (splits < 1) splits = 1;
+  if (splits > p.nkb) splits = p.nkb;
+  p.kb_per_split = (p.nkb + splits - 1) / splits;
+  p.dw[0] = dw1; p.dw[1] = dw2; p.dw[2] = dw3;
+  p.db[0] = db1; p.db[1] = db2; p.db[2] = db3;
+  p.scale = scale_dev;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NC_CHECK_CUDA(cudaFuncSetAttribute(hidden_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(splits, 8, 3);
+  hidden_wgrad_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q,
+                                          float* dw4, void* stream) {
+  NC_CHECK_ARG(a4_16 && dy && dw4);
+  NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
+  const int blocks = nchost::sm_count() * 8;
+  int rows = (int)((Q + blocks - 1) / blocks);
+  if (rows < 1) rows = 1;
+  const int grid = (int)((Q + rows - 1) / rows);
+  skinny_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)a4_16, dy, out_dim, (int)Q, rows, dw4);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

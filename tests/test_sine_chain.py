@@ -77,8 +77,9 @@ def test_forward_parity(Q, gain, out_dim):
     assert torch.equal(y2, y)
 
 
-@pytest.mark.parametrize("Q,gain,out_dim", [(1000, 1.0, 3), (20011, 1.0, 3), (4099, 2.5, 3), (777, 1.0, 4)])
+@pytest.mark.parametrize("Q,gain,out_dim", [(1000, 1.0, 3), (20011, 1.0, 3), (4099, 2.5, 3), (777, 1.0, 4), (50, 1.0, 3)])
 def test_backward_parity(Q, gain, out_dim):
+    """duv, scaled dz_1..3, and every weight/bias gradient of the atlas network against autograd."""
     sd = siren_state(11 + Q, out_dim, gain=gain)
     w0, b0, w16, wT16, bh, w4, b4 = to_dev(sd)
     g = torch.Generator().manual_seed(Q + 1)
@@ -89,12 +90,21 @@ def test_backward_parity(Q, gain, out_dim):
     scale_val = 2.0 ** math.floor(math.log2(16.0 / dy.abs().max().item()))
     scale = torch.tensor([scale_val], device="cuda")
     dz.fill_(float("nan"))
-    duv = ops.sine_mlp_bwd(uv.cuda(), w0, b0, wT16, w4, dy.cuda(), cos, scale, dz)
+    dw0 = torch.zeros(512, 2, device="cuda")
+    db0 = torch.zeros(512, device="cuda")
+    dws = [torch.zeros(512, 512, device="cuda") for _ in range(3)]
+    dbs = [torch.zeros(512, device="cuda") for _ in range(3)]
+    dw4 = torch.zeros(out_dim, 512, device="cuda")
+    dyc = dy.cuda()
+    duv = ops.sine_mlp_bwd(uv.cuda(), w0, b0, wT16, w4, dyc, cos, scale, dz, dw0, db0)
+    ops.sine_mlp_wgrad(dz, act, scale, dws, dbs)
+    ops.sine_mlp_head_wgrad(act, dyc, dw4)
     torch.cuda.synchronize()
 
     # oracle: autograd through the fp32 restatement
     uv_r = uv.clone().requires_grad_(True)
-    layers = orc.sine_mlp_layers(sd)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    layers = orc.sine_mlp_layers(sdr)
     zs = []
     h = uv_r
     for li, (W, b) in enumerate(layers):
@@ -103,10 +113,16 @@ def test_backward_parity(Q, gain, out_dim):
         zs.append(z)
         h = torch.sin(30.0 * z) if li < 4 else z
     (h * dy).sum().backward()
-    assert rel(duv.cpu(), uv_r.grad) <= 1e-2
+    errs = {"duv": rel(duv.cpu(), uv_r.grad)}
     dzc = dz.float().cpu() / scale_val
     assert torch.isfinite(dzc).all()
-    for l in range(4):
-        assert rel(dzc[l], zs[l].grad) <= 1e-2, f"dz{l}"
-    print(f"Q={Q}: duv rel {rel(duv.cpu(), uv_r.grad):.2e}; dz rel " +
-          " ".join(f"{rel(dzc[l], zs[l].grad):.2e}" for l in range(4)))
+    for l in (1, 2, 3):
+        errs[f"dz{l}"] = rel(dzc[l - 1], zs[l].grad)
+        errs[f"dW{l}"] = rel(dws[l - 1].cpu(), sdr[f"net.net.{l}.0.weight"].grad)
+        errs[f"db{l}"] = rel(dbs[l - 1].cpu(), sdr[f"net.net.{l}.0.bias"].grad)
+    errs["dW0"] = rel(dw0.cpu(), sdr["net.net.0.0.weight"].grad)
+    errs["db0"] = rel(db0.cpu(), sdr["net.net.0.0.bias"].grad)
+    errs["dW4"] = rel(dw4.cpu(), sdr["net.net.4.0.weight"].grad)
+    print(f"Q={Q} gain={gain}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v <= 1e-2, (k, v)
