@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NEUCAM_ABI_VERSION 1
+#define NEUCAM_ABI_VERSION 2
 
 #define NEUCAM_ERR_BAD_ARG (-1)
 #define NEUCAM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point unavailable */
@@ -75,6 +75,61 @@ int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const 
 
 /* neucam_sine_mlp_head_wgrad: ACCUMULATES dW4 [out_dim,512] += dy^T a4 (a4 = act16 slot 3). */
 int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q, float* dw4,
+                               void* stream);
+
+/* ---- per-pixel stages around the scene MLP ------------------------------------------------------------
+ * Layout conventions: a step samples B pixels; every pixel has K taps (K = patch_size = 9 with the blur
+ * model, 1 without); per-tap tensors are tap-major [K,B,...] exactly like the reference's coords patch
+ * (utils.py:587-612), so sample q = k*B + p.  Per-pixel feature scratch is feature-major ([F,B]).
+ *
+ * neucam_blur_fwd (training.py:101-121: utils.get_input_patch + LearnFocal gather + SimpleMLP blur net
+ *   (modules.py:282-306, nonlinear='both') + defocus offsets + centre-tap reset):
+ *   coords [B,3] (t,y,x), coord_idx [B] int64, focus [N]; blur_params = HOST array of 8 device pointers
+ *   layers.0.weight [64,3], layers.0.bias, layers.1.weight [64,64], .bias, layers.2.weight, .bias,
+ *   layers.3.weight [27,64], .bias.   Outputs: uv [K,B,2] (y,x of every tap), kout [27,B]
+ *   (softmax weights | tanh y offsets | tanh x offsets), hid [3*64,B] post-ReLU activations (for bwd). */
+int neucam_blur_fwd(const float* coords, const int64_t* coord_idx, const float* focus,
+                    const float* const* blur_params, int B, int K, int N, int H, int W, float offset_size,
+                    float* uv, float* kout, float* hid, void* stream);
+
+/* neucam_blur_bwd: autograd backward of neucam_blur_fwd. dkw [K,B] = dL/d(kernel weight), duv [K,B,2] =
+ *   dL/d(tap coords).  ACCUMULATES into blur_grads (HOST array of 8 device pointers, same order as
+ *   blur_params) and dfocus [N]. */
+int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, const float* focus,
+                    const float* const* blur_params, float* const* blur_grads, float* dfocus, int B, int K, int N,
+                    int H, int W, float offset_size, const float* kout, const float* hid, const float* dkw,
+                    const float* duv, void* stream);
+
+/* neucam_psf_crf_loss (training.py:157-188, 244-245 forward AND backward in one pass): PSF-weighted tap sum,
+ *   exposure dt = 3 tanh(exps[frame]) (LearnExps, modules.py:407-408) or fixed_exps [B], TonemapNet
+ *   (modules.py:219-247; tm_params = HOST array of 12 device pointers: for r,g,b: 0.weight [128,1], 0.bias [128],
+ *   2.weight [1,128], 2.bias [1]), image_mse (loss_functions.py:8-12) optionally with the random-gamma
+ *   augmentation (utils.py:615-619; gamma_dev = device scalar holding the step's gamma or NULL, gamma_w [B]) and mask weights (mask_w [B] or NULL), and the
+ *   white-balance term |tm(0,0) - fixed_value| weighted by ue_weight.
+ *   global_count = 3 * (pixels of the GLOBAL batch) normalises the mean.
+ *   Outputs: dy [K,B,3], dkw [K,B]; ACCUMULATES tm_grads (12 pointers), dexps [N], db4 [3] (atlas output bias), sums[0] += sum of squared
+ *   errors, sums[1] += ue_loss; atomically maxes |dy| into dy_absmax_bits and then writes
+ *   scale_out = 2^floor(log2(scale_target / max|dy|)) (the loss scale of neucam_sine_mlp_bwd).
+ *   ldr_out [B,3] optional (tone-mapped prediction). */
+int neucam_psf_crf_loss(const float* y, const float* kout, const int64_t* coord_idx, const float* exps,
+                        const float* fixed_exps, const float* gt, const float* gamma_w, const float* mask_w,
+                        const float* const* tm_params, float* const* tm_grads, int B, int K, int N, int H, int W,
+                        int has_blur, const float* gamma_dev, float fixed_value, float ue_weight,
+                        int64_t global_count, float* dy, float* dkw, float* dexps, float* db4, float* sums,
+                        uint32_t* dy_absmax_bits, float scale_target, float* scale_out, float* ldr_out,
+                        void* stream);
+
+/* ---- optimizer (torch.optim.Adam as constructed at training.py:51) --------------------------------------
+ * state = device float[4]: {step count, 1-beta1^t, 1-beta2^t, unused}.  neucam_adam_tick advances it once
+ * per step; neucam_adam_step then updates one flat range (call once per learning-rate group).
+ * grad_scale multiplies the gradient on read (1/world_size after a sum all-reduce, else 1). */
+int neucam_adam_tick(float* state, float beta1, float beta2, void* stream);
+int neucam_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* state, float lr,
+                     float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* Re-emits the fp16 operand copies of the three atlas hidden matrices (fp32 [512,512] each):
+ * w16 = [3*512,512] row-major [out,in]; wT16 = [3*512,512] transposed ([in,out]). */
+int neucam_pack_hidden_weights(const float* w1, const float* w2, const float* w3, void* w16, void* wT16,
                                void* stream);
 
 #ifdef __cplusplus

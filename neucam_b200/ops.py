@@ -74,3 +74,78 @@ def sine_mlp_head_wgrad(act16, dy, dw4):
     rc = _lib.lib().neucam_sine_mlp_head_wgrad(_lib.ptr(act16[3]), _lib.ptr(dy), dy.shape[1], ctypes.c_int64(Q),
                                                _lib.ptr(dw4), _lib.cur_stream())
     _lib.check(rc, "neucam_sine_mlp_head_wgrad")
+
+
+def pack_hidden_weights(w1, w2, w3, w16, wT16):
+    """fp32 [512,512] x3 -> fp16 stacks (plain and transposed) for the forward / dgrad chains."""
+    _chk_cuda(w1, w2, w3, w16, wT16)
+    rc = _lib.lib().neucam_pack_hidden_weights(_lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3), _lib.ptr(w16),
+                                               _lib.ptr(wT16), _lib.cur_stream())
+    _lib.check(rc, "neucam_pack_hidden_weights")
+
+
+SCALE_TARGET = 16.0
+
+
+def loss_scale_from(dy):
+    """Power-of-two loss scale 2^floor(log2(SCALE_TARGET / max|dy|)) as a device scalar (no host sync)."""
+    m = dy.abs().max().clamp_min(1e-30)
+    return torch.exp2(torch.floor(torch.log2(SCALE_TARGET / m))).clamp(2.0 ** -20, 2.0 ** 64).reshape(1).float()
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def blur_fwd(coords, coord_idx, focus, blur_params, shape, K, offset_size, uv, kout, hid):
+    """coords [B,3], coord_idx [B] int64 -> uv [K,B,2], kout [3K,B], hid [192,B]."""
+    _chk_cuda(coords, coord_idx, focus, uv, kout, hid, *blur_params)
+    N, H, W = shape
+    rc = _lib.lib().neucam_blur_fwd(_lib.ptr(coords), _lib.ptr(coord_idx), _lib.ptr(focus), _ptr_array(blur_params),
+                                    coords.shape[0], K, N, H, W, ctypes.c_float(offset_size), _lib.ptr(uv),
+                                    _lib.ptr(kout), _lib.ptr(hid), _lib.cur_stream())
+    _lib.check(rc, "neucam_blur_fwd")
+
+
+def blur_bwd(coords, coord_idx, focus, blur_params, blur_grads, dfocus, shape, K, offset_size, kout, hid, dkw, duv):
+    _chk_cuda(coords, coord_idx, focus, dfocus, kout, hid, dkw, duv, *blur_params, *blur_grads)
+    N, H, W = shape
+    rc = _lib.lib().neucam_blur_bwd(_lib.ptr(coords), _lib.ptr(coord_idx), _lib.ptr(focus), _ptr_array(blur_params),
+                                    _ptr_array(blur_grads), _lib.ptr(dfocus), coords.shape[0], K, N, H, W,
+                                    ctypes.c_float(offset_size), _lib.ptr(kout), _lib.ptr(hid), _lib.ptr(dkw),
+                                    _lib.ptr(duv), _lib.cur_stream())
+    _lib.check(rc, "neucam_blur_bwd")
+
+
+def psf_crf_loss(y, kout, coord_idx, exps, fixed_exps, gt, gamma_w, mask_w, tm_params, tm_grads, shape, K,
+                 has_blur, gamma_dev, fixed_value, ue_weight, global_count, dy, dkw, dexps, db4, sums, absmax_bits,
+                 scale_out, ldr_out=None):
+    """gamma_dev: device scalar tensor with the step's random gamma, or None (no gamma augmentation)."""
+    _chk_cuda(y, kout, coord_idx, exps, fixed_exps, gt, gamma_w, mask_w, dy, dkw, dexps, db4, sums, absmax_bits,
+              scale_out, ldr_out, gamma_dev, *tm_params, *tm_grads)
+    N, H, W = shape
+    rc = _lib.lib().neucam_psf_crf_loss(
+        _lib.ptr(y), _lib.ptr(kout), _lib.ptr(coord_idx), _lib.ptr(exps), _lib.ptr(fixed_exps), _lib.ptr(gt),
+        _lib.ptr(gamma_w), _lib.ptr(mask_w), _ptr_array(tm_params), _ptr_array(tm_grads), gt.shape[0], K, N, H, W,
+        int(has_blur), _lib.ptr(gamma_dev), ctypes.c_float(fixed_value),
+        ctypes.c_float(ue_weight), ctypes.c_int64(global_count), _lib.ptr(dy), _lib.ptr(dkw), _lib.ptr(dexps),
+        _lib.ptr(db4), _lib.ptr(sums), _lib.ptr(absmax_bits), ctypes.c_float(SCALE_TARGET), _lib.ptr(scale_out), _lib.ptr(ldr_out),
+        _lib.cur_stream())
+    _lib.check(rc, "neucam_psf_crf_loss")
+
+
+def adam_tick(state, beta1=0.9, beta2=0.999):
+    _chk_cuda(state)
+    rc = _lib.lib().neucam_adam_tick(_lib.ptr(state), ctypes.c_float(beta1), ctypes.c_float(beta2), _lib.cur_stream())
+    _lib.check(rc, "neucam_adam_tick")
+
+
+def adam_step(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    _chk_cuda(p, g, m, v, state)
+    rc = _lib.lib().neucam_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), ctypes.c_int64(p.numel()),
+                                     _lib.ptr(state), ctypes.c_float(lr), ctypes.c_float(beta1), ctypes.c_float(beta2),
+                                     ctypes.c_float(eps), ctypes.c_float(grad_scale), _lib.cur_stream())
+    _lib.check(rc, "neucam_adam_step")

@@ -1,0 +1,278 @@
+"""The fused training step: one forward + backward + Adam update of NeuCam's per-step pipeline
+(reference: training.py:95-271) executed by the library's CUDA kernels.
+
+    S2-S5   neucam_blur_fwd        neighbour patch, focus gather, blur-kernel MLP, defocus offsets
+    S7      neucam_sine_mlp_fwd    scene sine-MLP on all K*B taps (tcgen05)
+    S9-S12  neucam_psf_crf_loss    PSF sum, exposure, CRF, image_mse (+gamma/mask), ue_loss; and their backward
+    S14     neucam_sine_mlp_bwd    dgrad chain + layer-0 wgrad (tcgen05)
+            neucam_sine_mlp_wgrad  hidden-layer weight gradients (tcgen05 split-K), head wgrad
+            neucam_blur_bwd        blur MLP / focus backward
+            [all-reduce]           one NCCL sum over the flat gradient buffer when world_size > 1
+            neucam_adam_*          fused Adam over the flat buffers + fp16 operand re-pack
+
+All parameters of all models are re-homed as views into ONE flat fp32 buffer (same for gradients and
+Adam moments) so the optimizer and the all-reduce see a single tensor; module attribute names and
+state_dict keys are untouched, so utils.save_model-style checkpoints keep the reference's layout.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import _lib, ops
+from .modules import LearnExps, LearnFocal, SimpleMLP, SingleBVPNet, TonemapNet
+
+# order in which training.py:30-49 hands the models to Adam
+MODEL_ORDER = ("atlas_b", "tm", "uv_b", "uv_f", "blur", "atlas_f", "alpha", "exp", "focal", "noise", "depth")
+
+
+class FlatParameters:
+    """Flat fp32 parameter / gradient / Adam-moment storage shared by every model of the step."""
+
+    ALIGN = 4  # elements; keeps every tensor 16-byte aligned
+
+    def __init__(self, models, device):
+        self.device = torch.device(device)
+        self.entries = []  # (slot, name, param, offset, numel)
+        self.slot_ranges = OrderedDict()
+        off = 0
+        for slot in MODEL_ORDER:
+            mod = models.get(slot)
+            if mod is None:
+                continue
+            start = off
+            for name, p in mod.named_parameters():
+                n = p.numel()
+                self.entries.append((slot, name, p, off, n))
+                off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            self.slot_ranges[slot] = (start, off)
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        # {step, 1-b1^t, 1-b2^t, -}
+        self.adam_state = torch.zeros(4, dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            for slot, name, p, o, n in self.entries:
+                self.flat[o:o + n].copy_(p.detach().reshape(-1).to(self.device, torch.float32))
+                p.data = self.flat[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+        # non-parameter buffers of the modules follow their parameters to the device
+        for slot in MODEL_ORDER:
+            mod = models.get(slot)
+            if mod is not None:
+                for b in mod.buffers():
+                    b.data = b.data.to(self.device)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def reset_optimizer(self):
+        """A fresh Adam (training.py:300-313 re-creates the optimizer at start_freeze_tm)."""
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.adam_state.zero_()
+
+
+class StepOptions:
+    """The fields of the reference's `opt` namespace (configs.py) that the hot path reads."""
+
+    def __init__(self, patch_size=9, offset_size=5, use_random_gamma=False, fixed_value=0.0, lr=1e-4):
+        self.patch_size = patch_size
+        self.offset_size = offset_size
+        self.use_random_gamma = use_random_gamma
+        self.fixed_value = fixed_value
+        self.lr = lr
+
+    @classmethod
+    def from_opt(cls, opt):
+        return cls(patch_size=getattr(opt, "patch_size", 9), offset_size=getattr(opt, "offset_size", 5),
+                   use_random_gamma=bool(getattr(opt, "use_random_gamma", False)),
+                   fixed_value=float(getattr(opt, "fixed_value", 0.0)), lr=float(getattr(opt, "lr", 1e-4)))
+
+
+def _unsupported(what):
+    raise NotImplementedError(
+        f"neucam_b200 fused step: {what} is not built yet (SURVEY.md section 8f 'next' rows); the fused path "
+        "covers the static multi-focus / multi-exposure pipeline: atlas_b + blur + focal + exp + tm")
+
+
+class FusedTrainStep:
+    """Forward + backward (+ optimizer) of one NeuCam training step on the current CUDA device.
+
+    models: dict with the reference's slot names (train_video.py:157-169).  pixels_per_step = B on THIS
+    rank.  With a process_group, gradients are summed across ranks and the loss is normalised by the
+    global pixel count, so N ranks with B pixels each take the same step as one rank with N*B pixels.
+    """
+
+    def __init__(self, models, video_shape, options, pixels_per_step, device=None, process_group=None):
+        _lib.check(_lib.lib().neucam_check_device(), "neucam_check_device (need an sm_100 GPU)")
+        self.models = models
+        self.shape = tuple(int(s) for s in video_shape)
+        self.opt = options
+        self.B = int(pixels_per_step)
+        self.device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+
+        for slot in ("uv_b", "uv_f", "atlas_f", "alpha", "noise", "depth"):
+            if models.get(slot) is not None:
+                _unsupported(f"model slot '{slot}'")
+        for slot in ("atlas_b", "tm", "exp"):
+            if models.get(slot) is None:
+                _unsupported(f"a configuration without '{slot}'")
+        atlas = models["atlas_b"]
+        if not (isinstance(atlas, SingleBVPNet) and atlas.net.fused_eligible()):
+            _unsupported("an atlas that is not the sine 2 -> 512 x4 -> 3 SingleBVPNet")
+        self.has_blur = models.get("blur") is not None
+        if self.has_blur:
+            blur = models["blur"]
+            ok = (isinstance(blur, SimpleMLP) and len(blur.layers) == 4 and not blur.use_encoding
+                  and blur.layers[0].in_features == 3 and blur.layers[0].out_features == 64
+                  and blur.layers[3].out_features == 27 and blur.last_nonlinear == "both"
+                  and self.opt.patch_size == 9)
+            if not ok:
+                _unsupported("a blur model other than SimpleMLP(64, 4 layers, 3 -> 27, 'both') with patch_size 9")
+            if models.get("focal") is None:
+                _unsupported("a blur model without a focal model")
+        self.K = 9 if self.has_blur else 1
+        self.out_dim = atlas.net.dims[3]
+        if self.out_dim != 3:
+            _unsupported("an atlas_b with out_features != 3")
+
+        self.params = FlatParameters(models, self.device)
+        dev = self.device
+        B, K = self.B, self.K
+        Q = K * B
+        self.Q = Q
+        # static step inputs (H2D targets) -- fixed addresses so the step can be graph-captured
+        self.coords = torch.zeros(B, 3, device=dev)
+        self.coord_idx = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.img = torch.zeros(B, 3, device=dev)
+        self.gamma_w = torch.zeros(B, device=dev)
+        self.mask_w = torch.zeros(B, device=dev)
+        self.gamma = torch.ones(1, device=dev)
+        # workspaces
+        self.uv = torch.empty(K, B, 2, device=dev)
+        self.kout = torch.empty(27, B, device=dev)
+        self.hid = torch.empty(192, B, device=dev)
+        self.y = torch.empty(K, B, self.out_dim, device=dev)
+        self.dy = torch.empty(K, B, self.out_dim, device=dev)
+        self.dkw = torch.empty(K, B, device=dev)
+        self.duv = torch.empty(K, B, 2, device=dev)
+        self.act16, self.cos16, self.dz16 = ops.alloc_chain_workspace(Q, dev)
+        self.w16 = torch.empty(3 * ops.HID, ops.HID, dtype=torch.float16, device=dev)
+        self.wT16 = torch.empty(3 * ops.HID, ops.HID, dtype=torch.float16, device=dev)
+        # scalars: sums[0..3] | absmax bits | scale
+        self.scalars = torch.zeros(8, device=dev)
+        self.sums = self.scalars[0:4]
+        self.absmax_bits = self.scalars[4:5]
+        self.scale = torch.ones(1, device=dev)
+        self._bind()
+        self.repack()
+
+    # -- parameter / gradient pointer tables -----------------------------------------------------------
+    def _bind(self):
+        m = self.models
+        a = dict(m["atlas_b"].named_parameters())
+        self.aw = [a[f"net.net.{i}.0.weight"] for i in range(5)]
+        self.ab = [a[f"net.net.{i}.0.bias"] for i in range(5)]
+        # biases of the three hidden layers must be one contiguous [3,512] block for the forward kernel;
+        # in the flat buffer they are separated by the weight matrices, so keep a packed copy (repack()).
+        self.b_hid = torch.empty(3, ops.HID, device=self.device)
+        tm = dict(m["tm"].named_parameters())
+        self.tm_p = []
+        for ch in "rgb":
+            self.tm_p += [tm[f"layers_{ch}.0.weight"], tm[f"layers_{ch}.0.bias"], tm[f"layers_{ch}.2.weight"],
+                          tm[f"layers_{ch}.2.bias"]]
+        self.tm_g = [p.grad for p in self.tm_p]
+        self.exps = m["exp"].exps
+        if self.has_blur:
+            bl = dict(m["blur"].named_parameters())
+            self.blur_p = []
+            for i in range(4):
+                self.blur_p += [bl[f"layers.{i}.weight"], bl[f"layers.{i}.bias"]]
+            self.blur_g = [p.grad for p in self.blur_p]
+            self.focus = m["focal"].focus
+
+    def repack(self):
+        """fp16 tensor-core operand copies of the atlas hidden weights (+ packed hidden biases)."""
+        ops.pack_hidden_weights(self.aw[1].data, self.aw[2].data, self.aw[3].data, self.w16, self.wT16)
+        for i in range(3):
+            self.b_hid[i].copy_(self.ab[i + 1].data)
+
+    # -- data ----------------------------------------------------------------------------------------------
+    def load_batch(self, model_input, gt, gamma=None, non_blocking=True):
+        """Host (ideally pinned) batch in the reference's DataLoader layout ([1,B,...]) -> device buffers."""
+        self.coords.copy_(model_input["coords"].reshape(-1, 3), non_blocking=non_blocking)
+        self.coord_idx.copy_(model_input["coord_idx"].reshape(-1), non_blocking=non_blocking)
+        self.img.copy_(gt["img"].reshape(-1, 3), non_blocking=non_blocking)
+        if self.opt.use_random_gamma:
+            self.gamma_w.copy_(model_input["gamma_weights"].reshape(-1), non_blocking=non_blocking)
+            self.gamma.copy_(torch.as_tensor(gamma, dtype=torch.float32).reshape(1), non_blocking=non_blocking)
+        if "weights" in model_input:
+            self.mask_w.copy_(model_input["weights"].reshape(-1), non_blocking=non_blocking)
+
+    def h2d_bytes(self):
+        n = self.B * (3 * 4 + 8 + 3 * 4)
+        if self.opt.use_random_gamma:
+            n += self.B * 4 + 4
+        return n
+
+    # -- the step ------------------------------------------------------------------------------------------
+    def forward_backward(self, use_mask=False):
+        """Runs S2..S14 on the batch currently in the device buffers; gradients land in params.grad."""
+        o = self.opt
+        P = self.params
+        P.zero_grad()
+        self.scalars.zero_()
+        K, B = self.K, self.B
+        if self.has_blur:
+            ops.blur_fwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.shape, K,
+                         float(o.offset_size), self.uv, self.kout, self.hid)
+            uv = self.uv.view(-1, 2)
+        else:
+            uv = self.coords[:, 1:3].contiguous()
+        ops.sine_mlp_fwd(uv, self.aw[0].data, self.ab[0].data, self.w16, self.b_hid, self.aw[4].data, self.ab[4].data,
+                         y=self.y.view(-1, self.out_dim), act16=self.act16, cos16=self.cos16)
+        ops.psf_crf_loss(self.y, self.kout if self.has_blur else None, self.coord_idx, self.exps.data, None, self.img,
+                         self.gamma_w if o.use_random_gamma else None, self.mask_w if use_mask else None,
+                         [p.data for p in self.tm_p], self.tm_g, self.shape, K, self.has_blur,
+                         self.gamma if o.use_random_gamma else None, float(o.fixed_value), 1.0 / self.world,
+                         3 * B * self.world, self.dy, self.dkw if self.has_blur else None, self.exps.grad,
+                         self.ab[4].grad, self.sums, self.absmax_bits.view(torch.int32), self.scale)
+        dyf = self.dy.view(-1, self.out_dim)
+        ops.sine_mlp_bwd(uv, self.aw[0].data, self.ab[0].data, self.wT16, self.aw[4].data, dyf, self.cos16, self.scale,
+                         self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2))
+        ops.sine_mlp_wgrad(self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
+                           [self.ab[i].grad for i in (1, 2, 3)])
+        ops.sine_mlp_head_wgrad(self.act16, dyf, self.aw[4].grad)
+        if self.has_blur:
+            ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
+                         self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw, self.duv)
+
+    def optimizer_step(self, lr=None):
+        """Gradient all-reduce (when distributed) + fused Adam + operand re-pack."""
+        P = self.params
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(P.grad, op=dist.ReduceOp.SUM, group=self.pg)
+        ops.adam_tick(P.adam_state)
+        ops.adam_step(P.flat, P.grad, P.exp_avg, P.exp_avg_sq, P.adam_state, self.opt.lr if lr is None else lr)
+        self.repack()
+
+    def losses(self):
+        """Device scalars: img_loss (this rank's share of the global mean), ue_loss, total."""
+        img = self.sums[0] / float(3 * self.B * self.world)
+        ue = self.sums[1]
+        return OrderedDict(img_loss=img, ue_loss=ue, total=img + ue)
+
+    def step(self, model_input, gt, gamma=None, use_mask=False):
+        self.load_batch(model_input, gt, gamma)
+        self.forward_backward(use_mask=use_mask)
+        self.optimizer_step()
+        return self.losses()

@@ -1,0 +1,111 @@
+"""GPU parity of the WHOLE fused step (neucam_b200.step.FusedTrainStep, every kernel through the C ABI)
+against (a) the oracle on the same inputs and (b) golden vectors recorded from the unmodified reference's
+training.train loop (tests/golden/mf_static_h512.pt).  Tolerances (BASELINE.json north_star): forward
+quantities <= 1e-3 relative, gradients <= 1e-2 relative."""
+import math
+
+import pytest
+import torch
+
+from oracle_replay import batch_of, cfg_of, load_fixture, orc, rel, replay_rng
+
+from neucam_b200 import harness
+from neucam_b200.step import FusedTrainStep, StepOptions
+
+pytestmark = pytest.mark.gpu
+
+
+def make_step(fx_or_cfg, state, B, gamma):
+    shape = fx_or_cfg["shape"]
+    models = harness.build_static_models(shape, fx_or_cfg["focal_list"], hidden=512, seed=0)
+    harness.load_state(models, state)
+    opts = StepOptions(patch_size=9, offset_size=5, use_random_gamma=gamma, fixed_value=0.0, lr=1e-4)
+    return FusedTrainStep(models, shape, opts, B, device="cuda"), models
+
+
+def grads_of(models):
+    return {s: {k: p.grad.detach().float().cpu().clone() for k, p in m.named_parameters()}
+            for s, m in models.items() if m is not None}
+
+
+def test_step_matches_golden_reference_run():
+    fx = load_fixture("mf_static_h512")
+    step, models = make_step(fx, fx["init_state"], fx["B"], False)
+    cfg = cfg_of(fx)
+    state = {s: {k: v.clone() for k, v in d.items()} for s, d in fx["init_state"].items()}
+    for i in range(fx["n_steps"]):
+        inp, gt = fx["batches"][i]
+        step.load_batch(inp, gt)
+        step.forward_backward()
+        torch.cuda.synchronize()
+        losses = {k: v.item() for k, v in step.losses().items()}
+        ref = fx["losses"][i]
+        assert losses["img_loss"] == pytest.approx(ref["loss/img_loss"], rel=1e-3)
+        assert losses["ue_loss"] == pytest.approx(ref["loss/ue_loss"], rel=1e-3)
+        g = grads_of(models)
+        worst = 0.0
+        for slot, d in fx["grads_digest"][i].items():
+            for k, dg in d.items():
+                mine = g[slot][k].reshape(-1)
+                if dg["norm"] == 0:
+                    assert mine.abs().max() == 0, (slot, k)
+                    continue
+                e = abs(mine.double().norm().item() - dg["norm"]) / dg["norm"]
+                e2 = rel(mine[dg["idx"]], dg["val"])
+                worst = max(worst, e, e2)
+                assert e <= 1e-2 and e2 <= 1e-2, (i, slot, k, e, e2)
+        print(f"step {i}: img_loss {losses['img_loss']:.6f} (ref {ref['loss/img_loss']:.6f}); worst grad err {worst:.2e}")
+        step.optimizer_step()
+        torch.cuda.synchronize()
+        for slot, d in fx["params_digest"][i].items():
+            for k, dg in d.items():
+                mine = dict(models[slot].named_parameters())[k].detach().float().cpu().reshape(-1)
+                # Adam's first steps move every weight by ~lr regardless of gradient scale
+                assert (mine[dg["idx"]] - dg["val"]).abs().max() <= 2.5e-5, (i, slot, k)
+
+
+@pytest.mark.parametrize("name,gamma", [("mf", False), ("mfme_gamma", True)])
+def test_step_matches_oracle_full_gradients(name, gamma):
+    shape = (3, 40, 60) if gamma else (2, 36, 50)
+    focal = [-1.0, 0.0, 1.0] if gamma else [-1.0, 1.0]
+    B = 1111
+    models0 = harness.build_static_models(shape, focal, hidden=512, seed=3)
+    with torch.no_grad():
+        models0["exp"].exps.copy_(torch.linspace(-0.3, 0.4, shape[0]))
+        for p in models0["tm"].parameters():
+            p.mul_(1.3)
+    state = {s: {k: v.detach().clone() for k, v in m.state_dict().items()} for s, m in models0.items() if m is not None}
+    scene = harness.SyntheticScene(shape, focal, seed=5)
+    gen = torch.Generator().manual_seed(9)
+    inp, gt = scene.sample(B, gen)
+    inp["gamma_weights"] = torch.rand(1, B, 1, generator=gen)
+    gval = torch.tensor([37.5]) if gamma else None
+    step, models = make_step(dict(shape=shape, focal_list=focal), state, B, gamma)
+    step.load_batch(inp, gt, gval)
+    step.forward_backward()
+    torch.cuda.synchronize()
+
+    cfg = orc.StepConfig(shape, use_random_gamma=gamma, with_grad_loss=False)
+    batch = dict(inp)
+    batch["img"] = gt["img"]
+    losses, grads = orc.step_grads(state, batch, cfg, gval)
+    mine = {k: v.item() for k, v in step.losses().items()}
+    assert mine["img_loss"] == pytest.approx(losses["img_loss"].item(), rel=1e-3)
+    assert mine["ue_loss"] == pytest.approx(losses["ue_loss"].item(), rel=1e-3)
+    g = grads_of(models)
+    report = []
+    for slot, d in grads.items():
+        for k, gr in d.items():
+            if gr.abs().max() == 0:
+                assert g[slot][k].abs().max() == 0, (slot, k)
+                continue
+            e = rel(g[slot][k], gr)
+            report.append((e, slot, k))
+            assert e <= 1e-2, (slot, k, e)
+    report.sort(reverse=True)
+    print(f"{name}: img_loss {mine['img_loss']:.6f}; worst grads: " + ", ".join(f"{s}.{k}={e:.1e}" for e, s, k in report[:4]))
+
+    # forward intermediates: tap coordinates and atlas output
+    _, inter = orc.step_losses(state, batch, cfg, gval, return_intermediates=True)
+    assert rel(step.uv.cpu(), inter["uv"]) <= 1e-5
+    assert rel(step.y.cpu(), inter["atlas_out"]) <= 2e-3
