@@ -49,12 +49,19 @@ int neucam_umma_probe(const void* a, const void* b, float* d, int N, int K, int 
  *   w_hid16 : fp16 [3*512,512], the three hidden weight matrices stacked, each row-major [out,in]
  *             (kept in sync with the fp32 masters by neucam_pack_hidden_weights).
  *   act16   : fp16 [4,Q,512] out, a1..a4 (inputs of layers 1..4), or NULL for inference.
- *   cos16   : fp16 [3, ceil(Q/128)*128*512] out, cos(30 z_l) l=1..3 in the library's tile-blocked
- *             layout (opaque; only neucam_sine_mlp_bwd reads it); NULL iff act16 is NULL.
+ *   phase16 : 16-bit [3, ceil(Q/128)*128*512] out, the phase of 30 z_l (l=1..3) in revolutions * 65536,
+ *             in the library's tile-blocked layout (opaque; only neucam_sine_mlp_bwd reads it, to
+ *             regenerate cos(30 z_l)); NULL iff act16 is NULL.
  */
 int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float* b0, const void* w_hid16,
                         const float* b_hid, const float* w4, const float* b4, int out_dim, float* y,
-                        void* act16, void* cos16, void* stream);
+                        void* act16, void* phase16, void* stream);
+
+/* Debug aid: CTA 0 of subsequent neucam_sine_mlp_fwd/bwd launches records clock64 stamps of its warp roles
+ * into trace_dev (int64[576], device); pass NULL to switch it off.  See tools/chain_timeline.py. */
+int neucam_debug_set_chain_trace(long long* trace_dev);
+/* Debug experiments (outputs become garbage): bit0 = chain kernels issue no MMAs, bit1 = no weight TMA loads. */
+int neucam_debug_set_chain_flags(int flags);
 
 /* neucam_sine_mlp_bwd:  given dy[Q,out_dim] computes duv[Q,2], ACCUMULATES the first layer's
  *   gradients into dw0 [512,2] / db0 [512] and writes dz16 = fp16 [3,Q,512] holding
@@ -64,7 +71,7 @@ int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float
  *              gradients sit in fp16's normal range (neucam_b200/step.py derives it from max|dy|).
  */
 int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0, const void* wT_hid16,
-                        const float* w4, int out_dim, const float* dy, const void* cos16,
+                        const float* w4, int out_dim, const float* dy, const void* phase16,
                         const float* scale_dev, void* dz16, float* duv, float* dw0, float* db0, void* stream);
 
 /* neucam_sine_mlp_wgrad: ACCUMULATES dW_l [512,512] += dz_l^T a_l / scale and db_l [512] += colsum(dz_l) / scale

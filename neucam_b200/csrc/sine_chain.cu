@@ -1,28 +1,37 @@
 // sine_chain.cu -- the scene sine-MLP (SingleBVPNet 2 -> 512 -> 512 -> 512 -> 512 -> 3, modules.py:430-481)
-// forward and input/activation backward as ONE persistent kernel per direction.
+// forward and input/activation backward as ONE persistent, warp-specialised kernel per direction.
 //
 // A CTA owns a 128-sample row tile.  The tile's activations live in shared memory as the K-major
-// SWIZZLE_128B A operand (128 x 512 fp16 = 128 KB) for the whole chain; the three 512x512 hidden
-// layers run on tcgen05 tensor cores (fp16 operands, fp32 accumulators = all 512 TMEM columns);
-// weights are streamed through a 4-stage TMA ring (they are L2-resident: 1.5 MB); the sine /
-// cosine epilogue reads TMEM with tcgen05.ld and writes the next layer's A operand in place.
+// SWIZZLE_128B A operand (8 k-blocks of 128 rows x 64 fp16 = 128 KB) for the whole chain; the three
+// 512x512 hidden layers run on tcgen05 tensor cores (fp16 operands, fp32 accumulators = all 512 TMEM
+// columns); weights are streamed through a 4-stage TMA ring (they are L2-resident: 1.5 MB).
 //
 //   forward  (FCBlock.forward / BatchLinear.forward / Sine.forward, modules.py:17-35,90-95):
 //       a1 = sin(30 (uv W0^T + b0))            SIMT prologue (K = 2)
 //       a_{l+1} = sin(30 (a_l W_l^T + b_l))    l = 1..3, tcgen05 + epilogue
 //       y  = a4 W4^T + b4                      SIMT, fused in the last epilogue (N = 3)
-//     side outputs for the backward: a1..a4 (TMA-stored straight from the operand tile) and
-//     cos(30 z_l), l = 1..3 (fp16, tile-blocked layout so the per-row threads store coalesced).
+//     side outputs for the backward: a1..a4 (TMA-stored straight from the operand tile) and the PHASE
+//     of 30 z_l (l = 1..3) as 16-bit fixed point in revolutions, from which the backward regenerates
+//     cos(30 z_l) with one MUFU (tile-blocked layout so the per-row threads store/load coalesced).
 //   backward (autograd of the same, training.py:270):
 //       dz3 = (dy W4) * 30 cos(30 z3)          SIMT prologue
 //       dz_{l-1} = (dz_l W_l) * 30 cos(30 z_{l-1})   l = 3..1, tcgen05 + epilogue
 //       duv = dz0 W0                           SIMT, fused in the last epilogue
-//       dW0 = dz0^T uv, db0 = sum dz0       column pass over the dz0 tile while it is still in smem
-//     dz1..dz3 are TMA-stored for the weight-gradient kernel (wgrad.cu).  All dz are multiplied by a
-//     power-of-two loss scale read from device memory so that they sit in fp16's normal range.
+//       dW0 = dz0^T uv, db0 = sum dz0          column pass over the dz0 tile while it is still in smem
+//     dz1..dz3 are TMA-stored for the weight-gradient kernel (wgrad.cu).  All dz carry a power-of-two
+//     loss scale read from device memory so that they sit in fp16's normal range.
+//
+// Overlap of tensor cores and epilogue inside one tile: a layer's MMAs are issued as four 128-column
+// chunks with one TMEM-full barrier each, so the epilogue of chunk c runs while chunks c+1.. are still on
+// the tensor cores.  The next layer's operand overwrites the current one in place, k-block by k-block:
+// k-block kb may only be overwritten once the LAST chunk's MMAs have consumed it (kfree[kb], a
+// tcgen05.commit per k-block) and once its TMA store has drained (stored[kb]).  Until then the packed fp16
+// results of chunks 0..2 are parked in the (already drained) accumulator columns with tcgen05.st.  The
+// next layer's first chunk starts as soon as its first k-blocks land (a_ready[kb]).
 //
 // Warp roles (384 threads): warp 0 = TMA weight producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..11 = prologue/epilogue (thread = row; warps e and e+4 split the 512 columns).
+// allocator, warp 3 = TMA store issuer, warps 4..11 = prologue/epilogue (thread = row; warp e handles
+// the 64 columns [128 c + 64 (e/4), +64) of every chunk c, i.e. exactly one k-block of the next operand).
 #include "host_util.h"
 #include "tc05.cuh"
 
@@ -37,44 +46,65 @@ constexpr uint32_t STAGE_BYTES = 128 * 64 * 2;     // weight chunk: 128 output r
 constexpr uint32_t A_BLOCK_BYTES = TILE_M * 128;   // one 64-column k-block of the operand tile
 constexpr uint32_t A_BYTES = 8 * A_BLOCK_BYTES;    // 128 x 512 fp16
 constexpr int NTHREADS = 384;
-constexpr int EPI_THREADS = 256;
 constexpr int FIRST_EPI_WARP = 4;
+// CTAs per cluster sharing one weight stream: every weight tile is read from L2 once per cluster and
+// TMA-multicast into all of them (the chain is L2-bandwidth-bound on weights otherwise).
+constexpr int CLUSTER = 2;
+constexpr uint16_t CLUSTER_MASK = (1u << CLUSTER) - 1;
+constexpr uint32_t SLICE_ROWS = 128 / CLUSTER;     // weight-chunk rows each CTA of the cluster fetches
 
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_W = OFF_A + A_BYTES;
 constexpr uint32_t OFF_P0 = OFF_W + NSTAGE * STAGE_BYTES;   // float4[512]: 30*W0[j,0], 30*W0[j,1], 30*b0[j], 0
-constexpr uint32_t OFF_B30 = OFF_P0 + 512 * 16;             // float[3][512]: 30*b_l (forward)
-constexpr uint32_t OFF_W4 = OFF_B30 + 3 * 512 * 4;          // float[4][512]: W4 rows (row 3 = 0)
-constexpr uint32_t OFF_XCH = OFF_W4 + 4 * 512 * 4;          // float[128][4]: column-half exchange
+constexpr uint32_t OFF_W4 = OFF_P0 + 512 * 16;              // float4[512]: W4[0..3][j] (missing rows = 0)
+constexpr uint32_t OFF_B30 = OFF_W4 + 512 * 16;             // float[3][512]: 30*b_l                    (forward)
+constexpr uint32_t OFF_BQ = OFF_B30 + 3 * 512 * 4;          // float[3][512]: 30*b_l*65536/2pi + 1.5*2^23 (forward)
+constexpr uint32_t OFF_XCH = OFF_BQ + 3 * 512 * 4;          // float4[128]: column-half exchange
 constexpr uint32_t OFF_UV = OFF_XCH + 128 * 16;             // float2[128]: the tile's input coordinates
-constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;              // mbarriers
-constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
+constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;              // 36 mbarriers
+constexpr uint32_t OFF_TMEM = OFF_BAR + 320;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;           // + alignment slack
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+
+// mbarrier slots
+constexpr uint32_t BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_KFREE = 12, BAR_AREADY = 20, BAR_STORED = 28;
+
+constexpr float TWO_PI = 6.283185307179586f;
+constexpr float PH_PER_RAD = 65536.0f / TWO_PI;   // phase counts per radian
+constexpr float MAGIC = 12582912.0f;              // 1.5 * 2^23: float -> int rounding on the FMA pipe
 
 struct ChainParams {
   int Q;
   int ntiles;
   int out_dim;           // 3 (or 4 for a foreground atlas without alpha MLP)
-  int store_act;         // forward: write a1..a4 / cos for the backward
+  int store_act;         // forward: write a1..a4 / phases for the backward
   const float* uv;       // [Q,2]
   const float* w0;       // [512,2]
   const float* b0;       // [512]
   const float* b_hid;    // [3,512]
   const float* w4;       // [out_dim,512]
   const float* b4;       // [out_dim]
-  __half* cosbuf;        // [3][ntiles*128*512] tile-blocked
+  uint16_t* phase;       // [3][ntiles*128*512] tile-blocked 16-bit phases of 30 z_l, l = 1..3
   float* y;              // forward out [Q,out_dim]
   const float* dy;       // backward in [Q,out_dim]
   float* duv;            // backward out [Q,2]
   float* dw0;            // backward out [512,2] (accumulated into)
   float* db0;            // backward out [512]   (accumulated into)
   const float* scale;    // backward: device scalar, power-of-two loss scale
+  long long* trace;      // optional debug timeline of CTA 0 (clock64 stamps), or null
+  int dbg;               // debug experiments: bit0 = do not issue MMAs, bit1 = do not issue weight loads
 };
 
+// trace layout: [role 0=mma,1=epi half0,2=epi half1][tile 0..1][g 0..2][step 0..7][4 stamps]
+__device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i, int g, int step, int k) {
+  if (tr != nullptr && blockIdx.x == 0 && tile_i < 2)
+    tr[(((role * 2 + tile_i) * 3 + g) * 8 + step) * 4 + k] = clock64();
+}
+
 struct ChainMaps {
-  CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T)
-  CUtensorMap act[4];    // forward: a1..a4 ; backward: dz3, dz2, dz1, dz0   ([Q,512] fp16, box 64x128)
+  CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T), box 64 x SLICE_ROWS
+  CUtensorMap act[4];    // forward: a1..a4 ; backward: dz3, dz2, dz1, (unused)   ([Q,512] fp16, box 64x128)
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -90,14 +120,27 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
   return __half22float2(*reinterpret_cast<__half2*>(&v));
 }
+// cos of a 16-bit phase (revolutions * 65536): exact int->float through the mantissa, one FFMA, one MUFU
+__device__ __forceinline__ float cos_of_phase(uint32_t p16) {
+  const float f = __uint_as_float(0x4B000000u | p16);   // 2^23 + p
+  return __cosf(fmaf(f, TWO_PI / 65536.0f, -8388608.0f * (TWO_PI / 65536.0f)));
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// one 128-byte row (64 fp16 = 32 packed words) of k-block `kb` of the operand tile
+__device__ __forceinline__ void write_a_row(uint32_t a_base, uint32_t kb, uint32_t row, const uint32_t (&w)[32]) {
+  const uint32_t blk = a_base + kb * A_BLOCK_BYTES;
+#pragma unroll
+  for (uint32_t q = 0; q < 8; ++q)
+    st_shared_v4(blk + sw128_offset(row, q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
 template <bool BWD>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1)
 sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -105,14 +148,13 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   uint8_t* sm = smem_raw + (base - raw_addr);
 
   float4* s_p0 = reinterpret_cast<float4*>(sm + OFF_P0);
+  float4* s_w4 = reinterpret_cast<float4*>(sm + OFF_W4);
   float* s_b30 = reinterpret_cast<float*>(sm + OFF_B30);
-  float* s_w4 = reinterpret_cast<float*>(sm + OFF_W4);
+  float* s_bq = reinterpret_cast<float*>(sm + OFF_BQ);
   float4* s_xch = reinterpret_cast<float4*>(sm + OFF_XCH);
   float2* s_uv = reinterpret_cast<float2*>(sm + OFF_UV);
-  const uint32_t bar_full = base + OFF_BAR;           // [NSTAGE]
-  const uint32_t bar_empty = bar_full + 8 * NSTAGE;   // [NSTAGE]
-  const uint32_t bar_aready = bar_empty + 8 * NSTAGE;
-  const uint32_t bar_accfull = bar_aready + 8;
+  const uint32_t bars = base + OFF_BAR;
+  auto bar = [bars](uint32_t slot) { return bars + 8u * slot; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,18 +162,28 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   // ---- one-time setup -------------------------------------------------------------------------
   for (int j = tid; j < HID; j += NTHREADS) {
     s_p0[j] = make_float4(30.f * p.w0[2 * j], 30.f * p.w0[2 * j + 1], 30.f * p.b0[j], 0.f);
-    for (int c = 0; c < 4; ++c) s_w4[c * HID + j] = (c < p.out_dim) ? p.w4[c * HID + j] : 0.f;
+    float w4v[4];
+    for (int c = 0; c < 4; ++c) w4v[c] = (c < p.out_dim) ? p.w4[c * HID + j] : 0.f;
+    s_w4[j] = make_float4(w4v[0], w4v[1], w4v[2], w4v[3]);
     if (!BWD) {
-      for (int l = 0; l < 3; ++l) s_b30[l * HID + j] = 30.f * p.b_hid[l * HID + j];
+      for (int l = 0; l < 3; ++l) {
+        const float b30 = 30.f * p.b_hid[l * HID + j];
+        s_b30[l * HID + j] = b30;
+        s_bq[l * HID + j] = fmaf(b30, PH_PER_RAD, MAGIC);
+      }
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+    for (uint32_t s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar(BAR_WFULL + s), 1);
+      mbar_init(bar(BAR_WEMPTY + s), CLUSTER);   // every CTA of the cluster must have consumed the stage
+      mbar_init(bar(BAR_ACC + s), 1);
     }
-    mbar_init(bar_aready, 1);
-    mbar_init(bar_accfull, 1);
+    for (uint32_t k = 0; k < 8; ++k) {
+      mbar_init(bar(BAR_KFREE + k), 1);
+      mbar_init(bar(BAR_AREADY + k), 128);
+      mbar_init(bar(BAR_STORED + k), 1);
+    }
     mbar_fence_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -141,22 +193,35 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const bool do_store_any = BWD || p.store_act;
+  const uint32_t crank = (CLUSTER > 1) ? cluster_ctarank() : 0;
+  // all CTAs of a cluster walk the weight stream in lockstep, so they run the same number of tile
+  // iterations; iterations past the last tile ("phantom") only drain the weight ring
+  const int n_iter = (p.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA weight producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int it = 0; it < n_iter; ++it) {
         for (int g = 0; g < 3; ++g) {
           const int wl = BWD ? (2 - g) : g;
-          for (int nq = 0; nq < 4; ++nq) {
+          for (int c = 0; c < 4; ++c) {
             for (int kb = 0; kb < 8; ++kb) {
-              mbar_wait(bar_empty + 8 * s, ph ^ 1);
-              mbar_arrive_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-              tma_load_2d(base + OFF_W + s * STAGE_BYTES, &maps.w, bar_full + 8 * s, kb * 64,
-                          wl * HID + nq * 128);
+              mbar_wait(bar(BAR_WEMPTY + s), ph ^ 1);
+              if (p.dbg & 2) {
+                mbar_arrive(bar(BAR_WFULL + s));
+                if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                continue;
+              }
+              mbar_arrive_expect_tx(bar(BAR_WFULL + s), STAGE_BYTES);
+              const uint32_t dst = base + OFF_W + s * STAGE_BYTES + crank * (SLICE_ROWS * 128);
+              const int row0 = wl * HID + c * 128 + (int)(crank * SLICE_ROWS);
+              if (CLUSTER > 1) tma_load_2d_multicast(dst, &maps.w, bar(BAR_WFULL + s), kb * 64, row0, CLUSTER_MASK);
+              else             tma_load_2d(dst, &maps.w, bar(BAR_WFULL + s), kb * 64, row0);
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
           }
@@ -167,50 +232,103 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, 128, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
-      uint32_t s = 0, ph = 0, ar = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      uint32_t s = 0, ph = 0, ev = 0;   // ev = operand-write event counter (a_ready parity)
+      for (int tile_i = 0; tile_i < n_iter; ++tile_i) {
+        const int tile = blockIdx.x + tile_i * (int)gridDim.x;
+        if (tile >= p.ntiles) {
+          // phantom iteration: release the weight stages the cluster peers are still consuming
+          for (int k = 0; k < 96; ++k) {
+            mbar_wait(bar(BAR_WFULL + s), ph);
+            if (CLUSTER > 1) umma_commit_multicast(bar(BAR_WEMPTY + s), CLUSTER_MASK);
+            else             umma_commit(bar(BAR_WEMPTY + s));
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+          continue;
+        }
         for (int g = 0; g < 3; ++g) {
-          mbar_wait(bar_aready, ar);
-          ar ^= 1;
-          tc_fence_after_sync();
-          for (int nq = 0; nq < 4; ++nq) {
+          for (int c = 0; c < 4; ++c) {
+            trace_stamp(p.trace, 0, tile_i, g, c, 0);
             for (int kb = 0; kb < 8; ++kb) {
-              mbar_wait(bar_full + 8 * s, ph);
+              if (c == 0) {
+                // the first chunk chases the epilogue of the previous layer k-block by k-block; both
+                // halves of accumulator chunk 0 (k-blocks 0 and 1) must be drained before it is overwritten
+                if (kb == 0) {
+                  mbar_wait(bar(BAR_AREADY + 0), ev & 1);
+                  mbar_wait(bar(BAR_AREADY + 1), ev & 1);
+                } else if (kb >= 2) {
+                  mbar_wait(bar(BAR_AREADY + kb), ev & 1);
+                }
+                if (kb == 0) trace_stamp(p.trace, 0, tile_i, g, c, 1);
+                if (kb == 7) trace_stamp(p.trace, 0, tile_i, g, c, 2);
+              }
+              mbar_wait(bar(BAR_WFULL + s), ph);
               tc_fence_after_sync();
               const uint32_t a_addr = base + OFF_A + kb * A_BLOCK_BYTES;
               const uint32_t b_addr = base + OFF_W + s * STAGE_BYTES;
 #pragma unroll
               for (int k16 = 0; k16 < 4; ++k16) {
-                umma_f16_ss(tmem_base + nq * 128, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
-                            make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc,
-                            (kb | k16) != 0 ? 1u : 0u);
+                if (p.dbg & 1) break;
+                umma_f16_ss(tmem_base + c * 128, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
+                            make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, (kb | k16) != 0 ? 1u : 0u);
               }
-              umma_commit(bar_empty + 8 * s);
+              if (CLUSTER > 1) umma_commit_multicast(bar(BAR_WEMPTY + s), CLUSTER_MASK);
+              else             umma_commit(bar(BAR_WEMPTY + s));
+              if (c == 3) umma_commit(bar(BAR_KFREE + kb));   // operand k-block kb is dead from here on
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
+            umma_commit(bar(BAR_ACC + c));
+            trace_stamp(p.trace, 0, tile_i, g, c, 3);
           }
-          umma_commit(bar_accfull);
+          ++ev;
+        }
+        // stay phase-locked with a_ready: consume the event of the tile's output (a4 / dz0)
+        for (int kb = 0; kb < 8; ++kb) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
+        ++ev;
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA store issuer =====================
+    if (lane == 0) {
+      uint32_t ev = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const bool do_store = BWD ? (e4 < 3) : (p.store_act != 0);
+          for (int kb = 0; kb < 8; ++kb) {
+            mbar_wait(bar(BAR_AREADY + kb), ev & 1);
+            if (do_store) {
+              tma_store_2d(&maps.act[e4], base + OFF_A + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
+              tma_store_commit();
+              if (kb > 0) tma_store_wait_read1();
+            }
+            if (kb > 0) mbar_arrive(bar(BAR_STORED + kb - 1));
+          }
+          if (do_store) tma_store_wait_read0();
+          mbar_arrive(bar(BAR_STORED + 7));
+          ++ev;
         }
       }
+      if (do_store_any) tma_store_wait0();
     }
   } else if (warp >= FIRST_EPI_WARP) {
     // ===================== prologue / epilogue warps =====================
     const uint32_t e = warp - FIRST_EPI_WARP;
     const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may access
-    const uint32_t half = e >> 2;            // which 256 columns
+    const uint32_t half = e >> 2;            // which 64 columns of every 128-column chunk
     const uint32_t row = quad * 32 + lane;   // row inside the tile
-    const uint32_t col0 = half * 256;
-    const bool issuer = (e == 0 && lane == 0);
     const uint32_t a_base = base + OFF_A;
     const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
-    uint32_t af = 0;
+    uint32_t lp = 0;                         // layer parity (acc_full / kfree phases)
+    uint32_t ev = 0;                         // operand-write event counter (stored parity)
     float gscale = 1.f;
     if (BWD) gscale = *p.scale;
-    // layer-0 weight-gradient partials of this CTA (backward): columns 2*et, 2*et+1
     const uint32_t et = tid - FIRST_EPI_WARP * 32;
-    float gw0[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    float gw0[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // layer-0 weight-gradient partials (backward)
+    const size_t ph_layer_stride = (size_t)p.ntiles * TILE_M * HID;
+    long long* tr = (quad == 0 && lane == 0) ? p.trace : nullptr;
+    const int role = 1 + (int)half;
+    int tile_i = 0;
 
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
       const long long grow = (long long)tile * TILE_M + row;
       const bool valid = grow < p.Q;
       float u = 0.f, v = 0.f;
@@ -219,210 +337,236 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         u = t.x;
         v = t.y;
       }
-      const size_t cos_tile_stride = (size_t)p.ntiles * TILE_M * HID;   // elements per layer
-      const size_t cos_row_off = ((size_t)tile * 64 * TILE_M + row) * 8; // + chunk64 * 128 * 8
+      const size_t ph_row_off = ((size_t)tile * 64 * TILE_M + row) * 8;   // + chunk8 * 128 * 8
 
-      // ---------------- prologue: first operand tile ----------------
-      if (issuer) tma_store_wait_read0();
-      epi_bar_sync();
-      if (BWD && half == 0) s_uv[row] = make_float2(u, v);
-      if (!BWD) {
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          uint32_t w[4];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = col0 + i * 8 + jj * 2;
-            const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
-            const float h0 = __sinf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
-            const float h1 = __sinf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
-            w[jj] = pack_h2(h0, h1);
-          }
-          const uint32_t c = col0 + i * 8;
-          st_shared_v4(a_base + (c >> 6) * A_BLOCK_BYTES + sw128_offset(row, (c & 63) >> 3), w[0], w[1], w[2], w[3]);
-        }
-      } else {
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      // ---------------- prologue: first operand tile (k-blocks 2c + half) ----------------
+      trace_stamp(tr, role, tile_i, 0, 7, 0);
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      if (BWD) {
+        if (half == 0) s_uv[row] = make_float2(u, v);
         if (valid) {
           const float* dyr = p.dy + (size_t)grow * p.out_dim;
-          d0 = dyr[0] * gscale * 30.f;
-          d1 = dyr[1] * gscale * 30.f;
-          d2 = dyr[2] * gscale * 30.f;
-          if (p.out_dim > 3) d3 = dyr[3] * gscale * 30.f;
+          const float sc = gscale * 30.f;
+          d0 = dyr[0] * sc;
+          d1 = dyr[1] * sc;
+          d2 = dyr[2] * sc;
+          if (p.out_dim > 3) d3 = dyr[3] * sc;
         }
-        const __half* cos3 = p.cosbuf + 2 * cos_tile_stride + cos_row_off;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const uint32_t c = col0 + i * 8;
-          const uint4 cv = *reinterpret_cast<const uint4*>(cos3 + (size_t)(c >> 3) * (TILE_M * 8));
-          const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
-          uint32_t w[4];
+      }
+#pragma unroll 1
+      for (uint32_t c = 0; c < 4; ++c) {
+        const uint32_t kb = 2 * c + half;
+        const uint32_t col = kb * 64;
+        uint32_t w[32];
+        if (!BWD) {
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = c + jj * 2;
-            const float2 cc = unpack_h2(cw[jj]);
-            float g0 = d0 * s_w4[j] + d1 * s_w4[HID + j] + d2 * s_w4[2 * HID + j] + d3 * s_w4[3 * HID + j];
-            float g1 = d0 * s_w4[j + 1] + d1 * s_w4[HID + j + 1] + d2 * s_w4[2 * HID + j + 1] + d3 * s_w4[3 * HID + j + 1];
-            w[jj] = pack_h2_sat(g0 * cc.x, g1 * cc.y);
+          for (int i = 0; i < 32; ++i) {
+            const float4 q0 = s_p0[col + 2 * i], q1 = s_p0[col + 2 * i + 1];
+            w[i] = pack_h2(__sinf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z))), __sinf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z))));
           }
-          st_shared_v4(a_base + (c >> 6) * A_BLOCK_BYTES + sw128_offset(row, (c & 63) >> 3), w[0], w[1], w[2], w[3]);
+        } else {
+          const uint16_t* ph3 = p.phase + 2 * ph_layer_stride + ph_row_off + (size_t)(col >> 3) * (TILE_M * 8);
+          uint4 pv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pv[q] = *reinterpret_cast<const uint4*>(ph3 + (size_t)q * (TILE_M * 8));
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = col + q * 8 + jj * 2;
+              const float4 wa = s_w4[j], wb = s_w4[j + 1];
+              const float g0 = fmaf(d0, wa.x, fmaf(d1, wa.y, fmaf(d2, wa.z, d3 * wa.w)));
+              const float g1 = fmaf(d0, wb.x, fmaf(d1, wb.y, fmaf(d2, wb.z, d3 * wb.w)));
+              w[q * 4 + jj] = pack_h2_sat(g0 * cos_of_phase(pw[jj] & 0xFFFFu), g1 * cos_of_phase(pw[jj] >> 16));
+            }
+          }
         }
+        if (ev > 0) mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
+        write_a_row(a_base, kb, row, w);
+        fence_proxy_async_smem();
+        mbar_arrive(bar(BAR_AREADY + kb));
       }
-      fence_proxy_async_smem();
-      epi_bar_sync();
-      if (issuer) {
-        if (BWD || p.store_act) {
-          for (int kb = 0; kb < 8; ++kb)
-            tma_store_2d(&maps.act[0], a_base + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
-          tma_store_commit();
-        }
-        mbar_arrive(bar_aready);
-      }
+      ++ev;
+      trace_stamp(tr, role, tile_i, 0, 7, 1);
 
       // ---------------- three tensor-core layers ----------------
+#pragma unroll 1
       for (int g = 0; g < 3; ++g) {
-        mbar_wait(bar_accfull, af);
-        af ^= 1;
-        tc_fence_after_sync();
-        if (issuer) tma_store_wait_read0();
-        epi_bar_sync();
-
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // head (fwd) / duv (bwd) partials
         const float* b30 = s_b30 + g * HID;
-        // forward: cos(30 z_{g+1}) -> cosbuf[g]; backward: reads cos(30 z_{2-g}) from cosbuf[1-g] (g<2)
-        __half* cos_out = p.cosbuf + (size_t)g * cos_tile_stride + cos_row_off;
-        const __half* cos_in = p.cosbuf + (size_t)(g < 2 ? 1 - g : 0) * cos_tile_stride + cos_row_off;
+        const float* bq = s_bq + g * HID;
+        uint16_t* ph_out = p.phase + (size_t)g * ph_layer_stride + ph_row_off;
+        const uint16_t* ph_in = p.phase + (size_t)(g < 2 ? 1 - g : 0) * ph_layer_stride + ph_row_off;
 
-        for (int i = 0; i < 8; ++i) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + col0 + i * 32, r);
-          tmem_ld_wait();
+        // order: A(0) A(1) A(2) B(0) B(1) B(2) A(3)+write   (A = drain + math, B = parked result -> operand)
+#pragma unroll 1
+        for (int step = 0; step < 7; ++step) {
+          const bool is_b = (step >= 3 && step < 6);
+          const uint32_t c = is_b ? (step - 3) : (step == 6 ? 3 : step);
+          const uint32_t kb = 2 * c + half;
+          const uint32_t col = kb * 64;
+          uint32_t w[32];
+          trace_stamp(tr, role, tile_i, g, step, 0);
+          if (!is_b) {
+            uint4 pv[8];
+            if (BWD && g < 2) {
+              // phases do not depend on the MMA: fetch them while waiting for the accumulator
+              const uint16_t* src = ph_in + (size_t)(col >> 3) * (TILE_M * 8);
 #pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            const uint32_t c = col0 + i * 32 + q8 * 8;
-            uint32_t w[4];
+              for (int q = 0; q < 8; ++q) pv[q] = *reinterpret_cast<const uint4*>(src + (size_t)q * (TILE_M * 8));
+            }
+            mbar_wait(bar(BAR_ACC + c), lp);
+            tc_fence_after_sync();
+            trace_stamp(tr, role, tile_i, g, step, 1);
+            uint32_t r[64];
+            {
+              uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+              uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
+              tmem_ld_32x32b_x32(t_row + col, r0);
+              tmem_ld_32x32b_x32(t_row + col + 32, r1);
+              tmem_ld_wait();
+            }
             if (!BWD) {
-              uint32_t cw[4];
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = c + jj * 2;
-                const float t0 = fmaf(__uint_as_float(r[q8 * 8 + jj * 2]), 30.f, b30[j]);
-                const float t1 = fmaf(__uint_as_float(r[q8 * 8 + jj * 2 + 1]), 30.f, b30[j + 1]);
-                const float h0 = __sinf(t0), h1 = __sinf(t1);
-                w[jj] = pack_h2(h0, h1);
-                if (p.store_act) cw[jj] = pack_h2(__cosf(t0), __cosf(t1));
-                if (g == 2) {
-                  acc0 = fmaf(h0, s_w4[j], fmaf(h1, s_w4[j + 1], acc0));
-                  acc1 = fmaf(h0, s_w4[HID + j], fmaf(h1, s_w4[HID + j + 1], acc1));
-                  acc2 = fmaf(h0, s_w4[2 * HID + j], fmaf(h1, s_w4[2 * HID + j + 1], acc2));
-                  acc3 = fmaf(h0, s_w4[3 * HID + j], fmaf(h1, s_w4[3 * HID + j + 1], acc3));
+              for (int q = 0; q < 8; ++q) {
+                uint32_t pw[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const int i = q * 8 + jj * 2;
+                  const int j = col + i;
+                  const float z0 = __uint_as_float(r[i]), z1 = __uint_as_float(r[i + 1]);
+                  const float h0 = __sinf(fmaf(z0, 30.f, b30[j])), h1 = __sinf(fmaf(z1, 30.f, b30[j + 1]));
+                  w[q * 4 + jj] = pack_h2(h0, h1);
+                  if (p.store_act) {
+                    const uint32_t p0 = __float_as_uint(fmaf(z0, 30.f * PH_PER_RAD, bq[j]));
+                    const uint32_t p1 = __float_as_uint(fmaf(z1, 30.f * PH_PER_RAD, bq[j + 1]));
+                    pw[jj] = __byte_perm(p0, p1, 0x5410);
+                  }
+                  if (g == 2) {
+                    const float4 wa = s_w4[j], wb = s_w4[j + 1];
+                    acc0 = fmaf(h0, wa.x, fmaf(h1, wb.x, acc0));
+                    acc1 = fmaf(h0, wa.y, fmaf(h1, wb.y, acc1));
+                    acc2 = fmaf(h0, wa.z, fmaf(h1, wb.z, acc2));
+                    acc3 = fmaf(h0, wa.w, fmaf(h1, wb.w, acc3));
+                  }
                 }
+                if (p.store_act)
+                  *reinterpret_cast<uint4*>(ph_out + (size_t)((col >> 3) + q) * (TILE_M * 8)) =
+                      make_uint4(pw[0], pw[1], pw[2], pw[3]);
               }
-              if (p.store_act)
-                *reinterpret_cast<uint4*>(cos_out + (size_t)(c >> 3) * (TILE_M * 8)) =
-                    make_uint4(cw[0], cw[1], cw[2], cw[3]);
             } else {
-              uint32_t cw[4] = {0, 0, 0, 0};
-              if (g < 2) {
-                const uint4 cv = *reinterpret_cast<const uint4*>(cos_in + (size_t)(c >> 3) * (TILE_M * 8));
-                cw[0] = cv.x; cw[1] = cv.y; cw[2] = cv.z; cw[3] = cv.w;
-              }
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = c + jj * 2;
-                float c0v, c1v;
-                if (g < 2) {
-                  const float2 cc = unpack_h2(cw[jj]);
-                  c0v = cc.x;
-                  c1v = cc.y;
-                } else {
-                  const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
-                  c0v = __cosf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
-                  c1v = __cosf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
-                  // placeholders; duv accumulated below
-                }
-                const float z0 = __uint_as_float(r[q8 * 8 + jj * 2]) * 30.f * c0v;
-                const float z1 = __uint_as_float(r[q8 * 8 + jj * 2 + 1]) * 30.f * c1v;
-                w[jj] = pack_h2_sat(z0, z1);
-                if (g == 2) {
-                  const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
-                  acc0 = fmaf(z0, q0.x, fmaf(z1, q1.x, acc0));
-                  acc1 = fmaf(z0, q0.y, fmaf(z1, q1.y, acc1));
+              for (int q = 0; q < 8; ++q) {
+                const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const int i = q * 8 + jj * 2;
+                  const int j = col + i;
+                  float c0v, c1v;
+                  if (g < 2) {
+                    c0v = cos_of_phase(pw[jj] & 0xFFFFu);
+                    c1v = cos_of_phase(pw[jj] >> 16);
+                  } else {
+                    const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
+                    c0v = __cosf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
+                    c1v = __cosf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
+                    const float z0 = __uint_as_float(r[i]) * 30.f * c0v;
+                    const float z1 = __uint_as_float(r[i + 1]) * 30.f * c1v;
+                    acc0 = fmaf(z0, q0.x, fmaf(z1, q1.x, acc0));
+                    acc1 = fmaf(z0, q0.y, fmaf(z1, q1.y, acc1));
+                  }
+                  w[q * 4 + jj] = pack_h2_sat(__uint_as_float(r[i]) * 30.f * c0v, __uint_as_float(r[i + 1]) * 30.f * c1v);
                 }
               }
             }
-            st_shared_v4(a_base + (c >> 6) * A_BLOCK_BYTES + sw128_offset(row, (c & 63) >> 3), w[0], w[1], w[2], w[3]);
-          }
-        }
-
-        if (g == 2 && half == 1) s_xch[row] = make_float4(acc0, acc1, acc2, acc3);
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        epi_bar_sync();
-        if (issuer) {
-          if (BWD ? (g < 2) : (p.store_act != 0)) {
-            for (int kb = 0; kb < 8; ++kb)
-              tma_store_2d(&maps.act[g + 1], a_base + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
-            tma_store_commit();
-          }
-          if (g < 2) mbar_arrive(bar_aready);
-        }
-        if (BWD && g == 2) {
-          // dW0[j,:] += sum_r dz0[r,j] * uv[r,:], db0[j] += sum_r dz0[r,j]: column pass over the dz0 tile
-          // that now sits in the operand buffer (never stored to HBM).
-          const uint32_t c = et * 2;
-          const uint32_t col_addr = a_base + (c >> 6) * A_BLOCK_BYTES + (c & 7) * 2;
-          const uint32_t chunk = (c & 63) >> 3;
-#pragma unroll 8
-          for (uint32_t r2 = 0; r2 < TILE_M; ++r2) {
-            uint32_t wv;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(col_addr + sw128_offset(r2, chunk)));
-            const float2 z = unpack_h2(wv);
-            const float2 t = s_uv[r2];
-            gw0[0][0] = fmaf(z.x, t.x, gw0[0][0]);
-            gw0[0][1] = fmaf(z.x, t.y, gw0[0][1]);
-            gw0[0][2] += z.x;
-            gw0[1][0] = fmaf(z.y, t.x, gw0[1][0]);
-            gw0[1][1] = fmaf(z.y, t.y, gw0[1][1]);
-            gw0[1][2] += z.y;
-          }
-        }
-        if (g == 2 && half == 0 && valid) {
-          const float4 o = s_xch[row];
-          if (!BWD) {
-            float* yr = p.y + (size_t)grow * p.out_dim;
-            yr[0] = acc0 + o.x + p.b4[0];
-            yr[1] = acc1 + o.y + p.b4[1];
-            yr[2] = acc2 + o.z + p.b4[2];
-            if (p.out_dim > 3) yr[3] = acc3 + o.w + p.b4[3];
+            trace_stamp(tr, role, tile_i, g, step, 2);
+            if (step < 3) {
+              // park the packed result in the accumulator columns this thread has just drained
+              tmem_st_32x32b_x32(t_row + col, w);
+              tmem_st_wait();
+              trace_stamp(tr, role, tile_i, g, step, 3);
+              continue;
+            }
           } else {
-            // s_p0 holds 30*W0 and dz carries the loss scale: undo both
-            const float inv = 1.f / (30.f * gscale);
-            *reinterpret_cast<float2*>(p.duv + 2 * grow) = make_float2((acc0 + o.x) * inv, (acc1 + o.y) * inv);
+            tmem_ld_32x32b_x32(t_row + col, w);
+            tmem_ld_wait();
+            mbar_wait(bar(BAR_KFREE + kb), lp);
+            trace_stamp(tr, role, tile_i, g, step, 1);
+          }
+          // operand write of k-block kb (B steps and the last chunk)
+          mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
+          if (is_b) trace_stamp(tr, role, tile_i, g, step, 2);
+          write_a_row(a_base, kb, row, w);
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          mbar_arrive(bar(BAR_AREADY + kb));
+          trace_stamp(tr, role, tile_i, g, step, 3);
+        }
+        lp ^= 1;
+        ++ev;
+
+        if (g == 2) {
+          if (half == 1) s_xch[row] = make_float4(acc0, acc1, acc2, acc3);
+          epi_bar_sync();
+          if (half == 0 && valid) {
+            const float4 o = s_xch[row];
+            if (!BWD) {
+              float* yr = p.y + (size_t)grow * p.out_dim;
+              yr[0] = acc0 + o.x + p.b4[0];
+              yr[1] = acc1 + o.y + p.b4[1];
+              yr[2] = acc2 + o.z + p.b4[2];
+              if (p.out_dim > 3) yr[3] = acc3 + o.w + p.b4[3];
+            } else {
+              // s_p0 holds 30*W0 and dz carries the loss scale: undo both
+              const float inv = 1.f / (30.f * gscale);
+              *reinterpret_cast<float2*>(p.duv + 2 * grow) = make_float2((acc0 + o.x) * inv, (acc1 + o.y) * inv);
+            }
+          }
+          if (BWD) {
+            // dW0[j,:] += sum_r dz0[r,j] * uv[r,:], db0[j] += sum_r dz0[r,j]: column pass over the dz0 tile
+            // that now sits in the operand buffer (never stored to HBM).  epi_bar_sync above ordered all writes.
+            const uint32_t cc = et * 2;
+            const uint32_t col_addr = a_base + (cc >> 6) * A_BLOCK_BYTES + (cc & 7) * 2;
+            const uint32_t chunk = (cc & 63) >> 3;
+#pragma unroll 8
+            for (uint32_t r2 = 0; r2 < TILE_M; ++r2) {
+              uint32_t wv;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(col_addr + sw128_offset(r2, chunk)));
+              const float2 z = unpack_h2(wv);
+              const float2 t = s_uv[r2];
+              gw0[0][0] = fmaf(z.x, t.x, gw0[0][0]);
+              gw0[0][1] = fmaf(z.x, t.y, gw0[0][1]);
+              gw0[0][2] += z.x;
+              gw0[1][0] = fmaf(z.y, t.x, gw0[1][0]);
+              gw0[1][1] = fmaf(z.y, t.y, gw0[1][1]);
+              gw0[1][2] += z.y;
+            }
+            epi_bar_sync();   // the next tile's prologue overwrites the operand tile and s_uv
           }
         }
       }
     }
-    if (issuer) tma_store_wait0();
     if (BWD) {
       const float inv = 1.f / gscale;
-      const uint32_t c = et * 2;
+      const uint32_t cc = et * 2;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        atomicAdd(p.dw0 + (c + k) * 2 + 0, gw0[k][0] * inv);
-        atomicAdd(p.dw0 + (c + k) * 2 + 1, gw0[k][1] * inv);
-        atomicAdd(p.db0 + (c + k), gw0[k][2] * inv);
+        atomicAdd(p.dw0 + (cc + k) * 2 + 0, gw0[k][0] * inv);
+        atomicAdd(p.dw0 + (cc + k) * 2 + 1, gw0[k][1] * inv);
+        atomicAdd(p.db0 + (cc + k), gw0[k][2] * inv);
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();   // no CTA exits while a peer can still multicast into it
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, bool need_act) {
-  int rc = nchost::make_tmap_16b(&m->w, w16, 3 * HID, HID, HID, 128, 64);
+  int rc = nchost::make_tmap_16b(&m->w, w16, 3 * HID, HID, HID, SLICE_ROWS, 64);
   if (rc) return rc;
   for (int i = 0; i < 4; ++i) {
     if (!need_act) {
@@ -435,6 +579,9 @@ int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, boo
   return 0;
 }
 
+long long* g_trace = nullptr;
+int g_dbg = 0;
+
 template <bool BWD>
 int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
   static bool attr_set = false;
@@ -445,6 +592,7 @@ int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
   }
   int grid = nchost::sm_count();
   if (grid > p.ntiles) grid = p.ntiles;
+  grid = (grid + CLUSTER - 1) / CLUSTER * CLUSTER;   // whole clusters; surplus CTAs run phantom iterations
   sine_chain_kernel<BWD><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -452,22 +600,36 @@ int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+// Debug: when non-null, CTA 0 of the next chain launches writes clock64 stamps of its MMA / epilogue roles
+// into trace[3*2*3*8*4] (tools/chain_timeline.py decodes it).
+extern "C" int neucam_debug_set_chain_trace(long long* trace_dev) {
+  g_trace = trace_dev;
+  return 0;
+}
+// Debug experiments on the chain kernels (results are garbage): bit0 = no MMA issue, bit1 = no weight loads.
+extern "C" int neucam_debug_set_chain_flags(int flags) {
+  g_dbg = flags;
+  return 0;
+}
+
 extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float* b0,
                                    const void* w_hid16, const float* b_hid, const float* w4,
-                                   const float* b4, int out_dim, float* y, void* act16, void* cos16,
+                                   const float* b4, int out_dim, float* y, void* act16, void* phase16,
                                    void* stream) {
   NC_CHECK_ARG(uv && w0 && b0 && w_hid16 && b_hid && w4 && b4 && y);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - TILE_M);
   NC_CHECK_ARG(out_dim == 3 || out_dim == 4);
-  NC_CHECK_ARG((act16 == nullptr) == (cos16 == nullptr));
+  NC_CHECK_ARG((act16 == nullptr) == (phase16 == nullptr));
   ChainParams p{};
   p.Q = (int)Q;
   p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
   p.out_dim = out_dim;
   p.store_act = act16 != nullptr;
   p.uv = uv; p.w0 = w0; p.b0 = b0; p.b_hid = b_hid; p.w4 = w4; p.b4 = b4;
-  p.cosbuf = reinterpret_cast<__half*>(cos16);
+  p.phase = reinterpret_cast<uint16_t*>(phase16);
   p.y = y;
+  p.trace = g_trace;
+  p.dbg = g_dbg;
   ChainMaps maps;
   void* act[4];
   for (int i = 0; i < 4; ++i) act[i] = act16 ? (void*)((__half*)act16 + (size_t)i * Q * HID) : nullptr;
@@ -478,9 +640,9 @@ extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, 
 
 extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0,
                                    const void* wT_hid16, const float* w4, int out_dim, const float* dy,
-                                   const void* cos16, const float* scale_dev, void* dz16, float* duv,
+                                   const void* phase16, const float* scale_dev, void* dz16, float* duv,
                                    float* dw0, float* db0, void* stream) {
-  NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4 && dy && cos16 && scale_dev && dz16 && duv && dw0 && db0);
+  NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4 && dy && phase16 && scale_dev && dz16 && duv && dw0 && db0);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - TILE_M);
   NC_CHECK_ARG(out_dim == 3 || out_dim == 4);
   ChainParams p{};
@@ -489,8 +651,11 @@ extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, 
   p.out_dim = out_dim;
   p.store_act = 1;
   p.uv = uv; p.w0 = w0; p.b0 = b0; p.w4 = w4;
-  p.cosbuf = reinterpret_cast<__half*>(const_cast<void*>(cos16));
+  p.phase = reinterpret_cast<uint16_t*>(const_cast<void*>(phase16));
   p.dy = dy; p.duv = duv; p.scale = scale_dev; p.dw0 = dw0; p.db0 = db0;
+  p.trace = g_trace;
+  p.dbg = g_dbg;
+  p.dbg = g_dbg;
   ChainMaps maps;
   // store order of the backward chain: dz3 (prologue), dz2, dz1 -> dz16 = [3,Q,512] holding dz_1..dz_3
   // (dz0 never leaves the SM: its weight gradient is reduced in-kernel)

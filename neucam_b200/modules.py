@@ -133,7 +133,7 @@ class _SineMLPFunction(torch.autograd.Function):
         uvc, w0c, b0c, w4c, b4c = uv.contiguous(), w0.contiguous(), b0.contiguous(), w4.contiguous(), b4.contiguous()
         if need_grad:
             act, cos, dz = ops.alloc_chain_workspace(Q, dev)
-            y = ops.sine_mlp_fwd(uvc, w0c, b0c, w16, b_hid, w4c, b4c, act16=act, cos16=cos)
+            y = ops.sine_mlp_fwd(uvc, w0c, b0c, w16, b_hid, w4c, b4c, act16=act, phase16=cos)
             ctx.save_for_backward(uvc, w0c, b0c, w4c, wT16, act, cos)
             ctx.dz = dz
         else:

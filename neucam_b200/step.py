@@ -164,7 +164,7 @@ class FusedTrainStep:
         self.dy = torch.empty(K, B, self.out_dim, device=dev)
         self.dkw = torch.empty(K, B, device=dev)
         self.duv = torch.empty(K, B, 2, device=dev)
-        self.act16, self.cos16, self.dz16 = ops.alloc_chain_workspace(Q, dev)
+        self.act16, self.phase16, self.dz16 = ops.alloc_chain_workspace(Q, dev)
         self.w16 = torch.empty(3 * ops.HID, ops.HID, dtype=torch.float16, device=dev)
         self.wT16 = torch.empty(3 * ops.HID, ops.HID, dtype=torch.float16, device=dev)
         # scalars: sums[0..3] | absmax bits | scale
@@ -238,7 +238,7 @@ class FusedTrainStep:
         else:
             uv = self.coords[:, 1:3].contiguous()
         ops.sine_mlp_fwd(uv, self.aw[0].data, self.ab[0].data, self.w16, self.b_hid, self.aw[4].data, self.ab[4].data,
-                         y=self.y.view(-1, self.out_dim), act16=self.act16, cos16=self.cos16)
+                         y=self.y.view(-1, self.out_dim), act16=self.act16, phase16=self.phase16)
         ops.psf_crf_loss(self.y, self.kout if self.has_blur else None, self.coord_idx, self.exps.data, None, self.img,
                          self.gamma_w if o.use_random_gamma else None, self.mask_w if use_mask else None,
                          [p.data for p in self.tm_p], self.tm_g, self.shape, K, self.has_blur,
@@ -246,7 +246,7 @@ class FusedTrainStep:
                          3 * B * self.world, self.dy, self.dkw if self.has_blur else None, self.exps.grad,
                          self.ab[4].grad, self.sums, self.absmax_bits.view(torch.int32), self.scale)
         dyf = self.dy.view(-1, self.out_dim)
-        ops.sine_mlp_bwd(uv, self.aw[0].data, self.ab[0].data, self.wT16, self.aw[4].data, dyf, self.cos16, self.scale,
+        ops.sine_mlp_bwd(uv, self.aw[0].data, self.ab[0].data, self.wT16, self.aw[4].data, dyf, self.phase16, self.scale,
                          self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2))
         ops.sine_mlp_wgrad(self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
                            [self.ab[i].grad for i in (1, 2, 3)])

@@ -53,7 +53,7 @@ def test_forward_parity(Q, gain, out_dim):
     uv = (torch.rand(Q, 2, generator=torch.Generator().manual_seed(Q)) * 2 - 1)
     act, cos, dz = ops.alloc_chain_workspace(Q, "cuda")
     act.fill_(float("nan"))
-    y = ops.sine_mlp_fwd(uv.cuda(), w0, b0, w16, bh, w4, b4, act16=act, cos16=cos)
+    y = ops.sine_mlp_fwd(uv.cuda(), w0, b0, w16, bh, w4, b4, act16=act, phase16=cos)
     torch.cuda.synchronize()
     y_ref, hidden = orc.sine_mlp(sd, uv, return_hidden=True)
     a = act.float().cpu()
@@ -86,7 +86,7 @@ def test_backward_parity(Q, gain, out_dim):
     uv = (torch.rand(Q, 2, generator=g) * 2 - 1)
     dy = torch.randn(Q, out_dim, generator=g) * 1e-5
     act, cos, dz = ops.alloc_chain_workspace(Q, "cuda")
-    ops.sine_mlp_fwd(uv.cuda(), w0, b0, w16, bh, w4, b4, act16=act, cos16=cos)
+    ops.sine_mlp_fwd(uv.cuda(), w0, b0, w16, bh, w4, b4, act16=act, phase16=cos)
     scale_val = 2.0 ** math.floor(math.log2(16.0 / dy.abs().max().item()))
     scale = torch.tensor([scale_val], device="cuda")
     dz.fill_(float("nan"))

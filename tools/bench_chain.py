@@ -31,7 +31,7 @@ def main():
     dw4 = torch.zeros(3, 512, device=dev)
 
     fns = {
-        "fwd(train)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, cos16=cos),
+        "fwd(train)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, phase16=cos),
         "fwd(infer)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y),
         "bwd": lambda: ops.sine_mlp_bwd(uv, w0, b0, wT16, w4, dy, cos, scale, dz, dw0, db0, duv=duv),
         "wgrad": lambda: ops.sine_mlp_wgrad(dz, act, scale, dws, dbs),
@@ -39,6 +39,11 @@ def main():
     }
     flops = {"fwd(train)": 2 * 788992, "fwd(infer)": 2 * 788992, "bwd": 2 * 788992, "wgrad": 2 * 3 * 512 * 512, "head_wgrad": 2 * 3 * 512}
     total = 0.0
+    dbg = int(os.environ.get("NEUCAM_CHAIN_DBG", "0"))
+    if dbg:
+        from neucam_b200 import _lib
+        _lib.lib().neucam_debug_set_chain_flags(dbg)
+        print("debug flags", dbg)
     for name, fn in fns.items():
         for _ in range(3):
             fn()
