@@ -4,7 +4,11 @@
 // A CTA owns a 128-sample row tile.  The tile's activations live in shared memory as the K-major
 // SWIZZLE_128B A operand (8 k-blocks of 128 rows x 64 fp16 = 128 KB) for the whole chain; the three
 // 512x512 hidden layers run on tcgen05 tensor cores (fp16 operands, fp32 accumulators = all 512 TMEM
-// columns); weights are streamed through a 4-stage TMA ring (they are L2-resident: 1.5 MB).
+// columns).  Two CTAs form a pair (cluster of 2, tcgen05 cta_group::2): the leader's MMA thread issues
+// M=256 x N=256 x K=16 instructions that multiply BOTH CTAs' operand tiles by one 256-row weight tile of
+// which each CTA stages only half (128 rows, 16 KB per k-block) through its 4-stage TMA ring.  That halves
+// the shared-memory operand bandwidth and the L2->SMEM weight traffic per SM, which is what bounds a
+// single-CTA version (measured: 128x128x16 MMAs at 41 % of tensor peak, see profiles/).
 //
 //   forward  (FCBlock.forward / BatchLinear.forward / Sine.forward, modules.py:17-35,90-95):
 //       a1 = sin(30 (uv W0^T + b0))            SIMT prologue (K = 2)
@@ -21,16 +25,17 @@
 //     dz1..dz3 are TMA-stored for the weight-gradient kernel (wgrad.cu).  All dz carry a power-of-two
 //     loss scale read from device memory so that they sit in fp16's normal range.
 //
-// Overlap of tensor cores and epilogue inside one tile: a layer's MMAs are issued as four 128-column
-// chunks with one TMEM-full barrier each, so the epilogue of chunk c runs while chunks c+1.. are still on
-// the tensor cores.  The next layer's operand overwrites the current one in place, k-block by k-block:
-// k-block kb may only be overwritten once the LAST chunk's MMAs have consumed it (kfree[kb], a
-// tcgen05.commit per k-block) and once its TMA store has drained (stored[kb]).  Until then the packed fp16
+// Overlap of tensor cores and epilogue inside one tile: a layer's MMAs are issued as two 256-column
+// halves with their own TMEM-full barriers, so the epilogue of half 0 runs while half 1 is still on
+// the tensor cores; the epilogue itself works in four 128-column chunks.  The next layer's operand overwrites the current one in place, k-block by k-block:
+// k-block kb may only be overwritten once the LAST half's MMAs have consumed it (kfree[kb/2], a
+// tcgen05.commit after k-blocks 1 and 3) and once its TMA store has drained (stored[kb]).  Until then the packed fp16
 // results of chunks 0..2 are parked in the (already drained) accumulator columns with tcgen05.st.  The
 // next layer's first chunk starts as soon as its first k-blocks land (a_ready[kb]).
 //
-// Warp roles (384 threads): warp 0 = TMA weight producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warp 3 = TMA store issuer, warps 4..11 = prologue/epilogue (thread = row; warp e handles
+// Warp roles (384 threads per CTA): warp 0 = TMA weight producer, warp 1 = MMA issuer (leader CTA only),
+// warp 2 = TMEM allocator, warp 3 = TMA store issuer (the peer's also relays "operand k-block ready" to
+// the leader), warps 4..11 = prologue/epilogue (thread = row; warp e handles
 // the 64 columns [128 c + 64 (e/4), +64) of every chunk c, i.e. exactly one k-block of the next operand).
 #include "host_util.h"
 #include "tc05.cuh"
@@ -47,11 +52,8 @@ constexpr uint32_t A_BLOCK_BYTES = TILE_M * 128;   // one 64-column k-block of t
 constexpr uint32_t A_BYTES = 8 * A_BLOCK_BYTES;    // 128 x 512 fp16
 constexpr int NTHREADS = 384;
 constexpr int FIRST_EPI_WARP = 4;
-// CTAs per cluster sharing one weight stream: every weight tile is read from L2 once per cluster and
-// TMA-multicast into all of them (the chain is L2-bandwidth-bound on weights otherwise).
-constexpr int CLUSTER = 2;
-constexpr uint16_t CLUSTER_MASK = (1u << CLUSTER) - 1;
-constexpr uint32_t SLICE_ROWS = 128 / CLUSTER;     // weight-chunk rows each CTA of the cluster fetches
+constexpr int PAIR = 2;                            // CTAs per cluster (tcgen05 cta_group::2)
+constexpr uint16_t PAIR_MASK = 0x3;
 
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_W = OFF_A + A_BYTES;
@@ -61,14 +63,18 @@ constexpr uint32_t OFF_B30 = OFF_W4 + 512 * 16;             // float[3][512]: 30
 constexpr uint32_t OFF_BQ = OFF_B30 + 3 * 512 * 4;          // float[3][512]: 30*b_l*65536/2pi + 1.5*2^23 (forward)
 constexpr uint32_t OFF_XCH = OFF_BQ + 3 * 512 * 4;          // float4[128]: column-half exchange
 constexpr uint32_t OFF_UV = OFF_XCH + 128 * 16;             // float2[128]: the tile's input coordinates
-constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;              // 36 mbarriers
-constexpr uint32_t OFF_TMEM = OFF_BAR + 320;
+constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;              // 52 mbarriers
+constexpr uint32_t OFF_TMEM = OFF_BAR + 448;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;           // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 // mbarrier slots
-constexpr uint32_t BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_KFREE = 12, BAR_AREADY = 20, BAR_STORED = 28;
+constexpr uint32_t BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_KFREE = 12, BAR_AREADY = 20, BAR_STORED = 28,
+                   BAR_PEER = 36,   // leader only: the peer CTA's operand k-block kb is ready
+                   BAR_AOUT = 44;   // k-block kb of the tile's LAST output (a4 / dz0) is written (store warp only)
+// a_ready / peer count the MMA-visible operand events only (prologue + first two layers = 3 per tile): every
+// such event needs MMA progress on the previous one, so no waiter can be lapped by a full barrier phase.
 
 constexpr float TWO_PI = 6.283185307179586f;
 constexpr float PH_PER_RAD = 65536.0f / TWO_PI;   // phase counts per radian
@@ -103,7 +109,7 @@ __device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i,
 }
 
 struct ChainMaps {
-  CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T), box 64 x SLICE_ROWS
+  CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T), box 64 x 128
   CUtensorMap act[4];    // forward: a1..a4 ; backward: dz3, dz2, dz1, (unused)   ([Q,512] fp16, box 64x128)
 };
 
@@ -140,7 +146,7 @@ __device__ __forceinline__ void write_a_row(uint32_t a_base, uint32_t kb, uint32
 }
 
 template <bool BWD>
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(PAIR, 1, 1) __launch_bounds__(NTHREADS, 1)
 sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -176,52 +182,55 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   if (tid == 0) {
     for (uint32_t s = 0; s < NSTAGE; ++s) {
       mbar_init(bar(BAR_WFULL + s), 1);
-      mbar_init(bar(BAR_WEMPTY + s), CLUSTER);   // every CTA of the cluster must have consumed the stage
+      mbar_init(bar(BAR_WEMPTY + s), 1);
       mbar_init(bar(BAR_ACC + s), 1);
     }
     for (uint32_t k = 0; k < 8; ++k) {
       mbar_init(bar(BAR_KFREE + k), 1);
       mbar_init(bar(BAR_AREADY + k), 128);
       mbar_init(bar(BAR_STORED + k), 1);
+      mbar_init(bar(BAR_PEER + k), 1);
+      mbar_init(bar(BAR_AOUT + k), 128);
     }
     mbar_fence_init();
     tma_prefetch_desc(&maps.w);
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
+    tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish_2cta();
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
+  cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / commit / TMA signal
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const bool do_store_any = BWD || p.store_act;
-  const uint32_t crank = (CLUSTER > 1) ? cluster_ctarank() : 0;
-  // all CTAs of a cluster walk the weight stream in lockstep, so they run the same number of tile
-  // iterations; iterations past the last tile ("phantom") only drain the weight ring
-  const int n_iter = (p.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = (crank == 0);
+  // a pair walks tiles (2j, 2j+1) + it * gridDim.x together; it runs while its leader's tile exists.  When
+  // only the peer's tile is past the end it runs a phantom tile (all rows invalid, no global traffic).
+  const int lead0 = (int)(blockIdx.x & ~1u);
 
   if (warp == 0) {
     // ===================== TMA weight producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int it = 0; it < n_iter; ++it) {
+      uint32_t full_bar[NSTAGE];   // the leader's w_full barriers (shared::cluster addresses)
+      for (uint32_t k = 0; k < NSTAGE; ++k) full_bar[k] = mapa_shared(bar(BAR_WFULL + k), 0);
+      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
         for (int g = 0; g < 3; ++g) {
           const int wl = BWD ? (2 - g) : g;
-          for (int c = 0; c < 4; ++c) {
+          for (int h = 0; h < 2; ++h) {
             for (int kb = 0; kb < 8; ++kb) {
               mbar_wait(bar(BAR_WEMPTY + s), ph ^ 1);
               if (p.dbg & 2) {
-                mbar_arrive(bar(BAR_WFULL + s));
-                if (++s == NSTAGE) { s = 0; ph ^= 1; }
-                continue;
+                if (leader) mbar_arrive(bar(BAR_WFULL + s));
+              } else {
+                // the leader's barrier collects both halves of the 256-row weight tile
+                if (leader) mbar_arrive_expect_tx(bar(BAR_WFULL + s), 2 * STAGE_BYTES);
+                tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w, full_bar[s], kb * 64,
+                                 wl * HID + h * 256 + (int)crank * 128);
               }
-              mbar_arrive_expect_tx(bar(BAR_WFULL + s), STAGE_BYTES);
-              const uint32_t dst = base + OFF_W + s * STAGE_BYTES + crank * (SLICE_ROWS * 128);
-              const int row0 = wl * HID + c * 128 + (int)(crank * SLICE_ROWS);
-              if (CLUSTER > 1) tma_load_2d_multicast(dst, &maps.w, bar(BAR_WFULL + s), kb * 64, row0, CLUSTER_MASK);
-              else             tma_load_2d(dst, &maps.w, bar(BAR_WFULL + s), kb * 64, row0);
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
           }
@@ -229,37 +238,30 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, 128, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
+    // ===================== MMA issuer (leader CTA of the pair) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
       uint32_t s = 0, ph = 0, ev = 0;   // ev = operand-write event counter (a_ready parity)
-      for (int tile_i = 0; tile_i < n_iter; ++tile_i) {
-        const int tile = blockIdx.x + tile_i * (int)gridDim.x;
-        if (tile >= p.ntiles) {
-          // phantom iteration: release the weight stages the cluster peers are still consuming
-          for (int k = 0; k < 96; ++k) {
-            mbar_wait(bar(BAR_WFULL + s), ph);
-            if (CLUSTER > 1) umma_commit_multicast(bar(BAR_WEMPTY + s), CLUSTER_MASK);
-            else             umma_commit(bar(BAR_WEMPTY + s));
-            if (++s == NSTAGE) { s = 0; ph ^= 1; }
-          }
-          continue;
-        }
+      int tile_i = 0;
+      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
         for (int g = 0; g < 3; ++g) {
-          for (int c = 0; c < 4; ++c) {
-            trace_stamp(p.trace, 0, tile_i, g, c, 0);
+          for (int h = 0; h < 2; ++h) {
+            trace_stamp(p.trace, 0, tile_i, g, 2 * h, 0);
             for (int kb = 0; kb < 8; ++kb) {
-              if (c == 0) {
-                // the first chunk chases the epilogue of the previous layer k-block by k-block; both
-                // halves of accumulator chunk 0 (k-blocks 0 and 1) must be drained before it is overwritten
+              if (h == 0) {
+                // the first half chases the epilogues of the previous layer k-block by k-block; accumulator
+                // half 0 (chunks 0,1 = k-blocks 0..3) must be drained in BOTH CTAs before it is overwritten
                 if (kb == 0) {
-                  mbar_wait(bar(BAR_AREADY + 0), ev & 1);
-                  mbar_wait(bar(BAR_AREADY + 1), ev & 1);
-                } else if (kb >= 2) {
+                  for (int k = 0; k < 4; ++k) {
+                    mbar_wait(bar(BAR_AREADY + k), ev & 1);
+                    mbar_wait(bar(BAR_PEER + k), ev & 1);
+                  }
+                } else if (kb >= 4) {
                   mbar_wait(bar(BAR_AREADY + kb), ev & 1);
+                  mbar_wait(bar(BAR_PEER + kb), ev & 1);
                 }
-                if (kb == 0) trace_stamp(p.trace, 0, tile_i, g, c, 1);
-                if (kb == 7) trace_stamp(p.trace, 0, tile_i, g, c, 2);
+                if (kb == 0) trace_stamp(p.trace, 0, tile_i, g, 0, 1);
+                if (kb == 7) trace_stamp(p.trace, 0, tile_i, g, 0, 2);
               }
               mbar_wait(bar(BAR_WFULL + s), ph);
               tc_fence_after_sync();
@@ -268,33 +270,48 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
               for (int k16 = 0; k16 < 4; ++k16) {
                 if (p.dbg & 1) break;
-                umma_f16_ss(tmem_base + c * 128, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
-                            make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, (kb | k16) != 0 ? 1u : 0u);
+                umma_f16_ss_2cta(tmem_base + h * 256, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
+                                 make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, (kb | k16) != 0 ? 1u : 0u);
               }
-              if (CLUSTER > 1) umma_commit_multicast(bar(BAR_WEMPTY + s), CLUSTER_MASK);
-              else             umma_commit(bar(BAR_WEMPTY + s));
-              if (c == 3) umma_commit(bar(BAR_KFREE + kb));   // operand k-block kb is dead from here on
+              umma_commit_2cta(bar(BAR_WEMPTY + s), PAIR_MASK);
+              // operand k-blocks (2c, 2c+1) of chunk c = 0,1 are dead once the last half has consumed them
+              if (h == 1 && (kb == 1 || kb == 3)) umma_commit_2cta(bar(BAR_KFREE + (kb >> 1)), PAIR_MASK);
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
-            umma_commit(bar(BAR_ACC + c));
-            trace_stamp(p.trace, 0, tile_i, g, c, 3);
+            umma_commit_2cta(bar(BAR_ACC + 2 * h), PAIR_MASK);
+            umma_commit_2cta(bar(BAR_ACC + 2 * h + 1), PAIR_MASK);
+            trace_stamp(p.trace, 0, tile_i, g, 2 * h, 3);
           }
           ++ev;
         }
-        // stay phase-locked with a_ready: consume the event of the tile's output (a4 / dz0)
-        for (int kb = 0; kb < 8; ++kb) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
-        ++ev;
+      }
+    } else if (lane == 0) {
+      // peer CTA: this warp has no MMAs to issue; it relays "operand k-block ready" to the leader
+      uint32_t ev = 0;
+      uint32_t peer_bar[8];
+      for (uint32_t k = 0; k < 8; ++k) peer_bar[k] = mapa_shared(bar(BAR_PEER + k), 0);
+      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
+        for (int e3 = 0; e3 < 3; ++e3) {
+          for (int kb = 0; kb < 8; ++kb) {
+            mbar_wait(bar(BAR_AREADY + kb), ev & 1);
+            mbar_arrive_cluster(peer_bar[kb]);
+          }
+          ++ev;
+        }
       }
     }
   } else if (warp == 3) {
-    // ===================== TMA store issuer =====================
+    // ===================== TMA store issuer (+ peer -> leader "k-block ready" relay) =====================
     if (lane == 0) {
-      uint32_t ev = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      uint32_t ev = 0, tcount = 0;
+      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tcount) {
+        const int tile = lt + (int)crank;
+        const bool tile_ok = tile < p.ntiles;
         for (int e4 = 0; e4 < 4; ++e4) {
-          const bool do_store = BWD ? (e4 < 3) : (p.store_act != 0);
+          const bool do_store = tile_ok && (BWD ? (e4 < 3) : (p.store_act != 0));
           for (int kb = 0; kb < 8; ++kb) {
-            mbar_wait(bar(BAR_AREADY + kb), ev & 1);
+            if (e4 < 3) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
+            else        mbar_wait(bar(BAR_AOUT + kb), tcount & 1);
             if (do_store) {
               tma_store_2d(&maps.act[e4], base + OFF_A + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
               tma_store_commit();
@@ -304,7 +321,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           }
           if (do_store) tma_store_wait_read0();
           mbar_arrive(bar(BAR_STORED + 7));
-          ++ev;
+          if (e4 < 3) ++ev;
         }
       }
       if (do_store_any) tma_store_wait0();
@@ -328,9 +345,11 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const int role = 1 + (int)half;
     int tile_i = 0;
 
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
+    for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
+      const int tile = lt + (int)crank;
+      const bool tile_ok = tile < p.ntiles;       // false: phantom tile of a half-empty pair
       const long long grow = (long long)tile * TILE_M + row;
-      const bool valid = grow < p.Q;
+      const bool valid = tile_ok && grow < p.Q;
       float u = 0.f, v = 0.f;
       if (valid) {
         const float2 t = *reinterpret_cast<const float2*>(p.uv + 2 * grow);
@@ -338,6 +357,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         v = t.y;
       }
       const size_t ph_row_off = ((size_t)tile * 64 * TILE_M + row) * 8;   // + chunk8 * 128 * 8
+      const bool store_ph = tile_ok && p.store_act != 0;
 
       // ---------------- prologue: first operand tile (k-blocks 2c + half) ----------------
       trace_stamp(tr, role, tile_i, 0, 7, 0);
@@ -368,7 +388,8 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           const uint16_t* ph3 = p.phase + 2 * ph_layer_stride + ph_row_off + (size_t)(col >> 3) * (TILE_M * 8);
           uint4 pv[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) pv[q] = *reinterpret_cast<const uint4*>(ph3 + (size_t)q * (TILE_M * 8));
+          for (int q = 0; q < 8; ++q)
+            pv[q] = tile_ok ? *reinterpret_cast<const uint4*>(ph3 + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
@@ -399,11 +420,15 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         uint16_t* ph_out = p.phase + (size_t)g * ph_layer_stride + ph_row_off;
         const uint16_t* ph_in = p.phase + (size_t)(g < 2 ? 1 - g : 0) * ph_layer_stride + ph_row_off;
 
-        // order: A(0) A(1) A(2) B(0) B(1) B(2) A(3)+write   (A = drain + math, B = parked result -> operand)
+        // order: A(0) A(1) B(0) B(1) A(2) A(3)   (A = drain + math, B = parked result -> operand).
+        // Chunks 0,1 (accumulator half 0) are drained and parked while half 1 is still on the tensor cores; their
+        // k-blocks 0..3 free up early in half 1 (kfree), so B(0), B(1) also run under it and the next layer's
+        // first half can start the moment half 1 retires.  Chunks 2,3 then write their k-blocks directly.
 #pragma unroll 1
-        for (int step = 0; step < 7; ++step) {
-          const bool is_b = (step >= 3 && step < 6);
-          const uint32_t c = is_b ? (step - 3) : (step == 6 ? 3 : step);
+        for (int step = 0; step < 6; ++step) {
+          const bool is_b = (step == 2 || step == 3);
+          const uint32_t c = is_b ? (step - 2) : (step < 2 ? step : step - 2);
+          const bool park = (step < 2);
           const uint32_t kb = 2 * c + half;
           const uint32_t col = kb * 64;
           uint32_t w[32];
@@ -414,7 +439,8 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               // phases do not depend on the MMA: fetch them while waiting for the accumulator
               const uint16_t* src = ph_in + (size_t)(col >> 3) * (TILE_M * 8);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) pv[q] = *reinterpret_cast<const uint4*>(src + (size_t)q * (TILE_M * 8));
+              for (int q = 0; q < 8; ++q)
+                pv[q] = tile_ok ? *reinterpret_cast<const uint4*>(src + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
             }
             mbar_wait(bar(BAR_ACC + c), lp);
             tc_fence_after_sync();
@@ -438,7 +464,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                   const float z0 = __uint_as_float(r[i]), z1 = __uint_as_float(r[i + 1]);
                   const float h0 = __sinf(fmaf(z0, 30.f, b30[j])), h1 = __sinf(fmaf(z1, 30.f, b30[j + 1]));
                   w[q * 4 + jj] = pack_h2(h0, h1);
-                  if (p.store_act) {
+                  if (store_ph) {
                     const uint32_t p0 = __float_as_uint(fmaf(z0, 30.f * PH_PER_RAD, bq[j]));
                     const uint32_t p1 = __float_as_uint(fmaf(z1, 30.f * PH_PER_RAD, bq[j + 1]));
                     pw[jj] = __byte_perm(p0, p1, 0x5410);
@@ -451,7 +477,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                     acc3 = fmaf(h0, wa.w, fmaf(h1, wb.w, acc3));
                   }
                 }
-                if (p.store_act)
+                if (store_ph)
                   *reinterpret_cast<uint4*>(ph_out + (size_t)((col >> 3) + q) * (TILE_M * 8)) =
                       make_uint4(pw[0], pw[1], pw[2], pw[3]);
               }
@@ -481,7 +507,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               }
             }
             trace_stamp(tr, role, tile_i, g, step, 2);
-            if (step < 3) {
+            if (park) {
               // park the packed result in the accumulator columns this thread has just drained
               tmem_st_32x32b_x32(t_row + col, w);
               tmem_st_wait();
@@ -491,7 +517,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           } else {
             tmem_ld_32x32b_x32(t_row + col, w);
             tmem_ld_wait();
-            mbar_wait(bar(BAR_KFREE + kb), lp);
+            mbar_wait(bar(BAR_KFREE + c), lp);
             trace_stamp(tr, role, tile_i, g, step, 1);
           }
           // operand write of k-block kb (B steps and the last chunk)
@@ -500,7 +526,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           write_a_row(a_base, kb, row, w);
           fence_proxy_async_smem();
           tc_fence_before_sync();
-          mbar_arrive(bar(BAR_AREADY + kb));
+          mbar_arrive(bar((g < 2 ? BAR_AREADY : BAR_AOUT) + kb));
           trace_stamp(tr, role, tile_i, g, step, 3);
         }
         lp ^= 1;
@@ -561,12 +587,12 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 
   tc_fence_before_sync();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();   // no CTA exits while a peer can still multicast into it
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();   // neither CTA exits (or frees TMEM) while the pair's MMAs / remote arrives are in flight
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, bool need_act) {
-  int rc = nchost::make_tmap_16b(&m->w, w16, 3 * HID, HID, HID, SLICE_ROWS, 64);
+  int rc = nchost::make_tmap_16b(&m->w, w16, 3 * HID, HID, HID, 128, 64);
   if (rc) return rc;
   for (int i = 0; i < 4; ++i) {
     if (!need_act) {
@@ -592,7 +618,7 @@ int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
   }
   int grid = nchost::sm_count();
   if (grid > p.ntiles) grid = p.ntiles;
-  grid = (grid + CLUSTER - 1) / CLUSTER * CLUSTER;   // whole clusters; surplus CTAs run phantom iterations
+  grid = (grid + PAIR - 1) / PAIR * PAIR;   // whole pairs; an odd tile count gives one pair a phantom tile
   sine_chain_kernel<BWD><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;

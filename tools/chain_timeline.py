@@ -25,6 +25,7 @@ def run(bwd, Q=148 * 128 * 4):
     for it in range(2):
         ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, phase16=ph)
     lib = _lib.lib()
+    lib.neucam_debug_set_chain_flags(int(os.environ.get("NEUCAM_CHAIN_DBG", "0")))
     if not bwd:
         lib.neucam_debug_set_chain_trace(ctypes.c_void_p(trace.data_ptr()))
         ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, phase16=ph)
@@ -45,10 +46,10 @@ def run(bwd, Q=148 * 128 * 4):
             for c in range(4):
                 m = t[0, tile_i, g, c]
                 print(f"   MMA chunk {c}: start {rel(m[0])} first-A-ready {rel(m[1])} kb7-ready {rel(m[2])} issued {rel(m[3])}")
-            names = ["A0", "A1", "A2", "B0", "B1", "B2", "A3"]
+            names = ["A0", "A1", "B0", "B1", "A2", "A3"]
             for h in (0, 1):
                 row = []
-                for st in range(7):
+                for st in range(6):
                     e = t[1 + h, tile_i, g, st]
                     row.append(f"{names[st]}[{rel(e[0])},{rel(e[1])},{rel(e[2])},{rel(e[3])}]")
                 print(f"   epi half{h}: " + " ".join(row))
