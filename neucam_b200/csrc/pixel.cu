@@ -20,7 +20,6 @@ constexpr int KT = 9;           // taps (patch_size) supported by the fused path
 constexpr int BH = 64;          // blur MLP hidden width
 constexpr int BO = 3 * KT;      // blur MLP outputs
 constexpr int PB = 128;         // pixels per block
-constexpr int PS = PB + 1;      // padded pixel stride of the [feature][pixel] smem tiles in blur_bwd
 constexpr int TMW = 128;        // TonemapNet hidden width
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -373,19 +372,48 @@ struct BlurGrads {
   float *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *focus;   // accumulated into
 };
 
-// dW[o][i] += sum_p dz[o][p] * h[i][p] for a PB-pixel block, dz/h in smem as [feature][PB].
-// NOUT x NIN outputs are spread over the PB threads in 4 x (NIN*NOUT/PB/4) register blocks.
+// Tiles of the blur backward live in smem as [pixel][feature] with a 68-float row pitch: a pixel-thread
+// writes/reads its own row with conflict-free 128-bit accesses, and the block-level outer products read
+// 4-feature vectors of a common pixel row.
+constexpr int TP = 68;
+
+// gw[o][i] += sum_q dz[q][o] * h[q][i]   (NOUT x NIN <= 64 x 64, NOUT % 8 == 0 or handled by guards, NIN % 4 == 0)
+// thread t owns the 8 x 4 block  o in [8*(t/16), +8), i in [4*(t%16), +4).
 template <int NOUT, int NIN>
-__device__ __forceinline__ void block_outer_accum(const float* s_dz, const float* s_h, int np, float* gw,
-                                                  int tid) {
-  constexpr int TOTAL = NOUT * NIN;
-  for (int e = tid; e < TOTAL; e += PB) {
-    const int o = e / NIN, i = e % NIN;
-    float acc = 0.f;
-    const float* a = s_dz + o * PS;
-    const float* b = s_h + i * PS;
-    for (int q = 0; q < np; ++q) acc = fmaf(a[q], b[q], acc);
-    atomicAdd(gw + e, acc);
+__device__ __forceinline__ void block_outer_accum(const float* s_dz, const float* s_h, int np, float* gw, int tid) {
+  const int o0 = (tid >> 4) * 8, i0 = (tid & 15) * 4;
+  if (o0 >= NOUT || i0 >= NIN) return;
+  float acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
+  for (int q = 0; q < np; ++q) {
+    const float4 d0 = *reinterpret_cast<const float4*>(s_dz + q * TP + o0);
+    const float4 d1 = *reinterpret_cast<const float4*>(s_dz + q * TP + o0 + 4);
+    const float4 hv = *reinterpret_cast<const float4*>(s_h + q * TP + i0);
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dd[a], hh[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (o0 + a < NOUT && i0 + b < NIN) atomicAdd(gw + (o0 + a) * NIN + i0 + b, acc[a][b]);
+}
+
+// gb[o] += sum_q dz[q][o]
+template <int NOUT>
+__device__ __forceinline__ void block_bias_accum(const float* s_dz, int np, float* gb, int tid) {
+  if (tid < NOUT) {
+    float t = 0.f;
+    for (int q = 0; q < np; ++q) t += s_dz[q * TP + tid];
+    atomicAdd(gb + tid, t);
   }
 }
 
@@ -394,29 +422,31 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
                 const float* __restrict__ focus, BlurParams bp, BlurGrads bg, int B, int HW, int N, float sy,
                 float sx, float offset_size, const float* __restrict__ kout, const float* __restrict__ hid,
                 const float* __restrict__ dkw, const float* __restrict__ duv) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* s_w2 = sm;                    // [64][64] (out, in) as stored
   float* s_w3 = s_w2 + BH * BH;        // [64][64]
-  float* s_w4 = s_w3 + BH * BH;        // [27][64]
-  float* s_dz = s_w4 + BO * BH;        // [64][PB]   current layer's d(pre-activation)
-  float* s_h = s_dz + BH * PS;         // [64][PB]   that layer's input activation
-  float* s_red = s_h + BH * PS;        // [PB]
+  float* s_w4 = s_w3 + BH * BH;        // [28][64] (rows 27.. zero)
+  float* s_dz = s_w4 + 28 * BH;        // [PB][TP]  current layer's d(pre-activation)
+  float* s_h = s_dz + PB * TP;         // [PB][TP]  that layer's input activation
+  float* s_red = s_h + PB * TP;        // [PB]
   const int tid = threadIdx.x;
   for (int i = tid; i < BH * BH; i += PB) {
     s_w2[i] = bp.w2[i];
     s_w3[i] = bp.w3[i];
   }
-  for (int i = tid; i < BO * BH; i += PB) s_w4[i] = bp.w4[i];
-  __syncthreads();
+  for (int i = tid; i < 28 * BH; i += PB) s_w4[i] = (i < BO * BH) ? bp.w4[i] : 0.f;
 
   const int p0 = blockIdx.x * PB;
   const int p = p0 + tid;
   const bool valid = p < B;
   int np = B - p0;
   if (np > PB) np = PB;
+  float* my_dz = s_dz + tid * TP;
+  float* my_h = s_h + tid * TP;
 
   // ---- d(logits) of the head ----
-  float dlog[BO];
+  float dlog[28];
+  dlog[27] = 0.f;
   if (valid) {
     float w[KT], gsum = 0.f;
 #pragma unroll
@@ -442,22 +472,23 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
 
   // ---- layer 4 (64 -> 27): dW4, db4, dh3 ----
 #pragma unroll
-  for (int o = 0; o < BO; ++o) s_dz[o * PS + tid] = dlog[o];
-#pragma unroll 8
-  for (int i = 0; i < BH; ++i) s_h[i * PS + tid] = valid ? hid[(size_t)(2 * BH + i) * B + p] : 0.f;
+  for (int o = 0; o < 28; o += 4) *reinterpret_cast<float4*>(my_dz + o) = make_float4(dlog[o], dlog[o + 1], dlog[o + 2], dlog[o + 3]);
+#pragma unroll
+  for (int o = 28; o < 32; o += 4) *reinterpret_cast<float4*>(my_dz + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+  float hcur[BH];   // post-ReLU activation of the layer whose pre-activation gradient is being formed
+#pragma unroll
+  for (int i = 0; i < BH; ++i) hcur[i] = valid ? hid[(size_t)(2 * BH + i) * B + p] : 0.f;
+#pragma unroll
+  for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_h + i) = make_float4(hcur[i], hcur[i + 1], hcur[i + 2], hcur[i + 3]);
   __syncthreads();
   block_outer_accum<BO, BH>(s_dz, s_h, np, bg.w4, tid);
-  for (int o = tid; o < BO; o += PB) {
-    float t = 0.f;
-    for (int q = 0; q < np; ++q) t += s_dz[o * PS + q];
-    atomicAdd(bg.b4 + o, t);
-  }
+  block_bias_accum<BO>(s_dz, np, bg.b4, tid);
   float dh[BH];
 #pragma unroll
   for (int i = 0; i < BH; ++i) dh[i] = 0.f;
-#pragma unroll 1
+#pragma unroll
   for (int o = 0; o < BO; ++o) {
-    const float d = s_dz[o * PS + tid];
+    const float d = dlog[o];
     const float* wr = s_w4 + o * BH;
 #pragma unroll
     for (int i = 0; i < BH; ++i) dh[i] = fmaf(wr[i], d, dh[i]);
@@ -467,30 +498,27 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
   // ---- layers 3 and 2 (64 -> 64) ----
 #pragma unroll 1
   for (int l = 2; l >= 1; --l) {
-    // dz_l = dh * relu'(h_l);  input activation of layer l is h_{l-1}
+    float dz[BH];
 #pragma unroll
-    for (int i = 0; i < BH; ++i) {
-      const float h = s_h[i * PS + tid];          // h_l (post-ReLU) of this pixel, loaded in the previous phase
-      s_dz[i * PS + tid] = (h > 0.f) ? dh[i] : 0.f;
-    }
-    __syncthreads();   // everyone has consumed s_h (own column only, but block_outer reads all columns next)
-#pragma unroll 8
-    for (int i = 0; i < BH; ++i) s_h[i * PS + tid] = valid ? hid[(size_t)((l - 1) * BH + i) * B + p] : 0.f;
+    for (int i = 0; i < BH; ++i) dz[i] = (hcur[i] > 0.f) ? dh[i] : 0.f;   // ReLU backward
+#pragma unroll
+    for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_dz + i) = make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
+    // input activation of layer l+1 (0-based hidden index l-1)
+#pragma unroll
+    for (int i = 0; i < BH; ++i) hcur[i] = valid ? hid[(size_t)((l - 1) * BH + i) * B + p] : 0.f;
+#pragma unroll
+    for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_h + i) = make_float4(hcur[i], hcur[i + 1], hcur[i + 2], hcur[i + 3]);
     __syncthreads();
     float* gw = (l == 2) ? bg.w3 : bg.w2;
     float* gb = (l == 2) ? bg.b3 : bg.b2;
     const float* sw = (l == 2) ? s_w3 : s_w2;
     block_outer_accum<BH, BH>(s_dz, s_h, np, gw, tid);
-    for (int o = tid; o < BH; o += PB) {
-      float t = 0.f;
-      for (int q = 0; q < np; ++q) t += s_dz[o * PS + q];
-      atomicAdd(gb + o, t);
-    }
+    block_bias_accum<BH>(s_dz, np, gb, tid);
 #pragma unroll
     for (int i = 0; i < BH; ++i) dh[i] = 0.f;
-#pragma unroll 1
+#pragma unroll 4
     for (int o = 0; o < BH; ++o) {
-      const float d = s_dz[o * PS + tid];
+      const float d = my_dz[o];
       const float* wr = sw + o * BH;
 #pragma unroll
       for (int i = 0; i < BH; ++i) dh[i] = fmaf(wr[i], d, dh[i]);
@@ -502,24 +530,20 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
   const int pc = valid ? p : (B - 1);
   const float in0 = focus[(int)(coord_idx[pc] / HW)], in1 = coords[3 * pc + 1], in2 = coords[3 * pc + 2];
   float dfocus = 0.f;
+  {
+    float dz[BH];
 #pragma unroll
-  for (int i = 0; i < BH; ++i) {
-    const float h = s_h[i * PS + tid];            // h_1
-    const float d = (valid && h > 0.f) ? dh[i] : 0.f;
-    s_dz[i * PS + tid] = d;
-    dfocus = fmaf(bp.w1[i * 3], d, dfocus);
+    for (int i = 0; i < BH; ++i) {
+      dz[i] = (valid && hcur[i] > 0.f) ? dh[i] : 0.f;
+      dfocus = fmaf(bp.w1[i * 3], dz[i], dfocus);
+    }
+#pragma unroll
+    for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_dz + i) = make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
   }
-  __syncthreads();
-  s_h[0 * PS + tid] = in0;
-  s_h[1 * PS + tid] = in1;
-  s_h[2 * PS + tid] = in2;
+  *reinterpret_cast<float4*>(my_h) = make_float4(in0, in1, in2, 0.f);
   __syncthreads();
   block_outer_accum<BH, 3>(s_dz, s_h, np, bg.w1, tid);
-  for (int o = tid; o < BH; o += PB) {
-    float t = 0.f;
-    for (int q = 0; q < np; ++q) t += s_dz[o * PS + q];
-    atomicAdd(bg.b1 + o, t);
-  }
+  block_bias_accum<BH>(s_dz, np, bg.b1, tid);
   // focus gradient: per-frame scatter (training.py:104-108 backward)
   if (N <= PB) {
     s_red[tid] = 0.f;
@@ -568,7 +592,7 @@ extern "C" int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, co
                 blur_params[4], blur_params[5], blur_params[6], blur_params[7]};
   BlurGrads bg{blur_grads[0], blur_grads[1], blur_grads[2], blur_grads[3],
                blur_grads[4], blur_grads[5], blur_grads[6], blur_grads[7], dfocus};
-  const size_t smem = sizeof(float) * (2 * BH * BH + BO * BH + 2 * BH * PS + PB);
+  const size_t smem = sizeof(float) * (2 * BH * BH + 28 * BH + 2 * PB * TP + PB);
   static bool attr_set = false;
   if (!attr_set) {
     NC_CHECK_CUDA(cudaFuncSetAttribute(blur_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

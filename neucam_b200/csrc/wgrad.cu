@@ -152,30 +152,63 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// out[c][k] += sum_r s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound.
-__global__ void __launch_bounds__(256)
+// out[c][k] += sum_r s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
+// 512 threads = 8 row lanes x 64 column groups of 8 (one 16-byte load each), 4 rows in flight per thread.
+__global__ void __launch_bounds__(512)
 skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int nc, int Q,
                     int rows_per_block, float* __restrict__ out) {
+  extern __shared__ float s_acc_raw[];   // [8][4][512] floats = 64 KB (dynamic: above the 48 KB static limit)
+  float (*s_acc)[4][HID] = reinterpret_cast<float (*)[4][HID]>(s_acc_raw);
   const int r0 = blockIdx.x * rows_per_block;
   int r1 = r0 + rows_per_block;
   if (r1 > Q) r1 = Q;
-  const int k = threadIdx.x * 2;
-  float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  for (int r = r0; r < r1; ++r) {
-    const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + (size_t)r * HID + k));
-    const float* sr = s + (size_t)r * nc;
+  const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  float acc[4][8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (c < nc) {
-        const float sv = __ldg(sr + c);
-        acc[c][0] = fmaf(sv, xv.x, acc[c][0]);
-        acc[c][1] = fmaf(sv, xv.y, acc[c][1]);
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  for (int rb = r0 + rl; rb < r1; rb += 32) {
+    uint4 v[4];
+    float sv[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + 8 * u;
+      if (r < r1) {
+        v[u] = *reinterpret_cast<const uint4*>(x + (size_t)r * HID + cg * 8);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sv[u][c] = (c < nc) ? __ldg(s + (size_t)r * nc + c) : 0.f;
+      } else {
+        v[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sv[u][c] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[jj]));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[c][2 * jj] = fmaf(sv[u][c], f.x, acc[c][2 * jj]);
+          acc[c][2 * jj + 1] = fmaf(sv[u][c], f.y, acc[c][2 * jj + 1]);
+        }
       }
     }
   }
-  for (int c = 0; c < nc; ++c) {
-    atomicAdd(out + c * HID + k, acc[c][0]);
-    atomicAdd(out + c * HID + k + 1, acc[c][1]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[rl][c][cg * 8 + j] = acc[c][j];
+  __syncthreads();
+  for (int e = threadIdx.x; e < nc * HID; e += 512) {
+    const int c = e / HID, k = e % HID;
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += s_acc[l][c][k];
+    atomicAdd(out + c * HID + k, t);
   }
 }
 
@@ -223,11 +256,16 @@ extern "C" int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, in
                                           float* dw4, void* stream) {
   NC_CHECK_ARG(a4_16 && dy && dw4);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  const int blocks = nchost::sm_count() * 8;
+  const int blocks = nchost::sm_count() * 2;
   int rows = (int)((Q + blocks - 1) / blocks);
-  if (rows < 1) rows = 1;
+  if (rows < 32) rows = 32;
   const int grid = (int)((Q + rows - 1) / rows);
-  skinny_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)a4_16, dy, out_dim, (int)Q, rows, dw4);
+  static bool attr_set2 = false;
+  if (!attr_set2) {
+    NC_CHECK_CUDA(cudaFuncSetAttribute(skinny_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr_set2 = true;
+  }
+  skinny_wgrad_kernel<<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)a4_16, dy, out_dim, (int)Q, rows, dw4);
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
