@@ -271,8 +271,45 @@ class FusedTrainStep:
         ue = self.sums[1]
         return OrderedDict(img_loss=img, ue_loss=ue, total=img + ue)
 
+    # -- CUDA graph ---------------------------------------------------------------------------------------
+    def capture(self, use_mask=False, lr=None):
+        """Captures forward_backward + optimizer_step into one CUDA graph (all kernel arguments are pointers
+        to fixed buffers; the step's inputs are read from the static device buffers filled by load_batch, the
+        step counter and loss scale live on the device).  `step()` replays it afterwards.  Re-capture after
+        changing the learning rate or use_mask."""
+        # one eager step first: sets kernel attributes and warms NCCL outside of capture
+        saved = [t.clone() for t in (self.params.flat, self.params.exp_avg, self.params.exp_avg_sq,
+                                     self.params.adam_state)]
+        self.forward_backward(use_mask=use_mask)
+        self.optimizer_step(lr)
+        torch.cuda.synchronize(self.device)
+        for dst, src in zip((self.params.flat, self.params.exp_avg, self.params.exp_avg_sq, self.params.adam_state),
+                            saved):
+            dst.copy_(src)
+        self.repack()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward_backward(use_mask=use_mask)
+            self.optimizer_step(lr)
+        self._graph = g
+        self._graph_key = (bool(use_mask), lr)
+        return g
+
     def step(self, model_input, gt, gamma=None, use_mask=False):
         self.load_batch(model_input, gt, gamma)
-        self.forward_backward(use_mask=use_mask)
-        self.optimizer_step()
+        g = getattr(self, "_graph", None)
+        if g is not None and self._graph_key == (bool(use_mask), None):
+            g.replay()
+        else:
+            self.forward_backward(use_mask=use_mask)
+            self.optimizer_step()
         return self.losses()
+
+    def run_resident(self, use_mask=False):
+        """One step on the batch already in the device buffers (graph replay when captured)."""
+        g = getattr(self, "_graph", None)
+        if g is not None and self._graph_key == (bool(use_mask), None):
+            g.replay()
+        else:
+            self.forward_backward(use_mask=use_mask)
+            self.optimizer_step()
