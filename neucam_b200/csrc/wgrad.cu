@@ -2,10 +2,10 @@
 // BatchLinear, modules.py:24-25, reduced over all Q samples of the step).
 //
 //   hidden layers l = 1..3:  dW_l[j,k] = sum_r dz_l[r,j] * a_l[r,k],   db_l[j] = sum_r dz_l[r,j]
-//     a split-K tcgen05 GEMM: both operands are read as MN-major tiles straight out of the row-major
-//     [Q,512] fp16 buffers the chain kernels TMA-stored (no transposes anywhere); each CTA owns one
-//     128 x 256 output tile of one layer for one slice of the Q axis and reduces into the fp32 gradient
-//     with red.global.add.  The bias gradient rides along as a 16-column MMA against an all-ones tile.
+//     a split-K tcgen05 GEMM on CTA pairs (cta_group::2): both operands are read as MN-major tiles straight
+//     out of the row-major [Q,512] fp16 buffers the chain kernels TMA-stored (no transposes anywhere); each
+//     pair owns one 256 x 256 output tile of one layer for one slice of the Q axis and reduces into the fp32
+//     gradient with red.global.add.  The bias gradient rides along as a 16-column MMA against an all-ones tile.
 //   head:  dW4[c,k] = sum_r dy[r,c] * a4[r,k]  (c < 4) -- an HBM-bound SIMT column reduction.
 //
 // dz carries the power-of-two loss scale of the backward chain; it is divided out here.
@@ -17,16 +17,17 @@ using namespace tc05;
 namespace {
 
 constexpr int HID = 512;
-constexpr int NSTAGE = 4;
-constexpr uint32_t A_STAGE = 64 * 128 * 2;   // 64 k-rows x 128 m   (2 atoms of 64 m)
-constexpr uint32_t B_STAGE = 64 * 256 * 2;   // 64 k-rows x 256 n   (4 atoms of 64 n)
-constexpr uint32_t ATOM_BYTES = 64 * 128;    // 64 k-rows x 128 B
+constexpr int NSTAGE = 6;
+constexpr uint32_t ATOM_BYTES = 64 * 128;    // 64 k-rows x 64 MN elements (128 B)
+constexpr uint32_t A_STAGE = 2 * ATOM_BYTES; // 64 k-rows x 128 m  (this CTA's half of the pair's 256 m)
+constexpr uint32_t B_STAGE = 2 * ATOM_BYTES; // 64 k-rows x 128 n  (this CTA's half of the pair's 256 n)
 constexpr uint32_t STAGE_BYTES = A_STAGE + B_STAGE;
 constexpr uint32_t OFF_ONES = NSTAGE * STAGE_BYTES;   // 8 KB of fp16 1.0
 constexpr uint32_t OFF_BAR = OFF_ONES + ATOM_BYTES;
 constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
 constexpr int NTHREADS = 192;
+constexpr uint16_t PAIR_MASK = 0x3;
 
 struct WgradMaps {
   CUtensorMap dz[3];    // dz_1..dz_3   [Q,512] fp16, box 64 x 64
@@ -42,7 +43,10 @@ struct WgradParams {
   const float* scale;   // device scalar: loss scale carried by dz
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// A CTA pair (cluster of 2, cta_group::2) owns one 256 x 256 tile of one layer's dW for one slice of the Q
+// axis: each CTA stages its 128 dz-columns (A, M side) and its 128 activation-columns (B, N side) per 64-row
+// k-block; the leader issues M256 x N256 x K16 MMAs; each CTA's TMEM holds its own 128 output rows.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -52,14 +56,18 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int split = blockIdx.x;
-  const int mt = blockIdx.y >> 1, nt = blockIdx.y & 1;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int split = blockIdx.x >> 1;
+  const int mt = blockIdx.y >> 1, nt = blockIdx.y & 1;   // 256-wide tile coordinates
   const int layer = blockIdx.z;
   const int kb0 = split * p.kb_per_split;
   int kb1 = kb0 + p.kb_per_split;
   if (kb1 > p.nkb) kb1 = p.nkb;
-  const int nk = kb1 - kb0;   // may be <= 0 for trailing splits
+  const int nk = kb1 - kb0;   // may be <= 0 for trailing splits (identical in both CTAs of a pair)
   const bool with_bias = (nt == 0);
+  const int m0 = mt * 256 + (int)crank * 128;   // this CTA's dz columns  = dW rows
+  const int n0 = nt * 256 + (int)crank * 128;   // this CTA's act columns = dW columns it STAGES (not the ones it owns)
 
   // all-ones tile for the bias-gradient MMA
   for (uint32_t i = tid; i < ATOM_BYTES / 4; i += NTHREADS)
@@ -74,11 +82,12 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
+    tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish_2cta();
   }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -90,19 +99,18 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
         uint32_t s = 0, ph = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+          const uint32_t full_leader = mapa_shared(bar_full + 8 * s, 0);
+          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);
           const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
-          for (int a = 0; a < 2; ++a)
-            tma_load_2d(a_st + a * ATOM_BYTES, ta, bar_full + 8 * s, mt * 128 + a * 64, kb * 64);
-          for (int a = 0; a < 4; ++a)
-            tma_load_2d(b_st + a * ATOM_BYTES, tb, bar_full + 8 * s, nt * 256 + a * 64, kb * 64);
+          for (int a = 0; a < 2; ++a) tma_load_2d_2cta(a_st + a * ATOM_BYTES, ta, full_leader, m0 + a * 64, kb * 64);
+          for (int a = 0; a < 2; ++a) tma_load_2d_2cta(b_st + a * ATOM_BYTES, tb, full_leader, n0 + a * 64, kb * 64);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc_f16(128, 256, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
-        const uint32_t idesc_b = make_idesc_f16(128, 16, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
+      if (lane == 0 && leader) {
+        const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
+        const uint32_t idesc_b = make_idesc_f16(256, 16, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
         const uint32_t ones = base + OFF_ONES;
         uint32_t s = 0, ph = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -113,23 +121,23 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
           for (int k16 = 0; k16 < 4; ++k16) {
             const uint64_t ad = make_sdesc_sw128(a_st + k16 * 2048, ATOM_BYTES, 1024);
             const uint32_t accum = (kb > kb0 || k16 > 0) ? 1u : 0u;
-            umma_f16_ss(tmem_base, ad, make_sdesc_sw128(b_st + k16 * 2048, ATOM_BYTES, 1024), idesc, accum);
+            umma_f16_ss_2cta(tmem_base, ad, make_sdesc_sw128(b_st + k16 * 2048, ATOM_BYTES, 1024), idesc, accum);
             if (with_bias)
-              umma_f16_ss(tmem_base + 256, ad, make_sdesc_sw128(ones + k16 * 2048, ATOM_BYTES, 1024), idesc_b, accum);
+              umma_f16_ss_2cta(tmem_base + 256, ad, make_sdesc_sw128(ones + k16 * 2048, ATOM_BYTES, 1024), idesc_b, accum);
           }
-          umma_commit(bar_empty + 8 * s);
+          umma_commit_2cta(bar_empty + 8 * s, PAIR_MASK);
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_acc);
+        umma_commit_2cta(bar_acc, PAIR_MASK);
       }
     } else {
-      // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+      // epilogue warps 2..5: TMEM lane quadrant = warp % 4; this CTA owns dW rows m0.., all 256 columns of the tile
       const uint32_t quad = warp & 3;
       const uint32_t row = quad * 32 + lane;
       const float inv = 1.f / *p.scale;
       mbar_wait(bar_acc, 0);
       tc_fence_after_sync();
-      float* out = p.dw[layer] + (size_t)(mt * 128 + row) * HID + nt * 256;
+      float* out = p.dw[layer] + (size_t)(m0 + row) * HID + nt * 256;
       const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
       for (int i = 0; i < 8; ++i) {
         uint32_t r[32];
@@ -142,14 +150,15 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_row + 256, r);
         tmem_ld_wait();
-        atomicAdd(p.db[layer] + mt * 128 + row, __uint_as_float(r[0]) * inv);
+        atomicAdd(p.db[layer] + m0 + row, __uint_as_float(r[0]) * inv);
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // out[c][k] += sum_r s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
@@ -232,8 +241,8 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
   WgradParams p{};
   p.Q = (int)Q;
   p.nkb = (int)((Q + 63) / 64);
-  // 24 output tiles; fill the machine with ~6 Q-slices per tile
-  int splits = nchost::sm_count() / 24;
+  // 12 pair-tiles of 256 x 256; fill the machine's 74 CTA pairs with ~6 Q-slices per tile
+  int splits = (nchost::sm_count() / 2) / 12;
   if (splits < 1) splits = 1;
   if (splits > p.nkb) splits = p.nkb;
   p.kb_per_split = (p.nkb + splits - 1) / splits;
@@ -246,7 +255,7 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
                                        (int)SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(splits, 8, 3);
+  dim3 grid(2 * splits, 4, 3);
   hidden_wgrad_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
