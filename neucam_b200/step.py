@@ -106,7 +106,8 @@ class FusedTrainStep:
     global pixel count, so N ranks with B pixels each take the same step as one rank with N*B pixels.
     """
 
-    def __init__(self, models, video_shape, options, pixels_per_step, device=None, process_group=None):
+    def __init__(self, models, video_shape, options, pixels_per_step, device=None, process_group=None,
+                 global_pixels=None):
         _lib.check(_lib.lib().neucam_check_device(), "neucam_check_device (need an sm_100 GPU)")
         self.models = models
         self.shape = tuple(int(s) for s in video_shape)
@@ -118,6 +119,8 @@ class FusedTrainStep:
         if process_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
+        # pixels of the GLOBAL batch (sum over ranks); differs from B * world only for ragged shards
+        self.global_pixels = int(global_pixels) if global_pixels is not None else self.B * self.world
 
         for slot in ("uv_b", "uv_f", "atlas_f", "alpha", "noise", "depth"):
             if models.get(slot) is not None:
@@ -243,7 +246,7 @@ class FusedTrainStep:
                          self.gamma_w if o.use_random_gamma else None, self.mask_w if use_mask else None,
                          [p.data for p in self.tm_p], self.tm_g, self.shape, K, self.has_blur,
                          self.gamma if o.use_random_gamma else None, float(o.fixed_value), 1.0 / self.world,
-                         3 * B * self.world, self.dy, self.dkw if self.has_blur else None, self.exps.grad,
+                         3 * self.global_pixels, self.dy, self.dkw if self.has_blur else None, self.exps.grad,
                          self.ab[4].grad, self.sums, self.absmax_bits.view(torch.int32), self.scale)
         dyf = self.dy.view(-1, self.out_dim)
         ops.sine_mlp_bwd(uv, self.aw[0].data, self.ab[0].data, self.wT16, self.aw[4].data, dyf, self.phase16, self.scale,
@@ -259,15 +262,15 @@ class FusedTrainStep:
         """Gradient all-reduce (when distributed) + fused Adam + operand re-pack."""
         P = self.params
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(P.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            from .dist import allreduce_flat_gradients
+            allreduce_flat_gradients(P.grad, self.pg)
         ops.adam_tick(P.adam_state)
         ops.adam_step(P.flat, P.grad, P.exp_avg, P.exp_avg_sq, P.adam_state, self.opt.lr if lr is None else lr)
         self.repack()
 
     def losses(self):
         """Device scalars: img_loss (this rank's share of the global mean), ue_loss, total."""
-        img = self.sums[0] / float(3 * self.B * self.world)
+        img = self.sums[0] / float(3 * self.global_pixels)
         ue = self.sums[1]
         return OrderedDict(img_loss=img, ue_loss=ue, total=img + ue)
 

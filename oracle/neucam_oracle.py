@@ -167,7 +167,8 @@ class StepConfig:
         self.with_grad_loss = with_grad_loss
 
 
-def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_intermediates=False):
+def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_intermediates=False,
+                img_weight=1.0, ue_weight=1.0):
     """One forward pass of the 'Main Pipeline' + 'Loss Function' blocks of training.train
     (training.py:95-267) for the static multi-focus / multi-exposure configuration: blur MLP + focus,
     atlas_b, PSF sum, learned exposure, CRF, image_mse (+ random gamma), ue_loss, value-only grad_loss.
@@ -193,7 +194,7 @@ def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_int
         py = patch[:, :, 1] + y_off * (2 / (H - 1)) * cfg.offset_size               # 118
         px = patch[:, :, 2] + x_off * (2 / (W - 1)) * cfg.offset_size               # 119
         patch = torch.stack((patch[:, :, 0], py, px), -1)
-        centre = torch.zeros(K, 1, 1, dtype=torch.bool)
+        centre = torch.zeros(K, 1, 1, dtype=torch.bool, device=coords.device)
         centre[K // 2] = True
         patch = torch.where(centre, coords.expand(K, -1, -1), patch)                # 120 (centre tap reset)
         weights = kernel_out[:, 0:K].t().unsqueeze(-1)                              # 121
@@ -217,26 +218,29 @@ def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_int
     fake, real = ldr, batch["img"]
     if cfg.use_random_gamma:                                                        # 180-183
         gw = batch["gamma_weights"].view(-1, 1)
-        g = torch.as_tensor(gamma, dtype=torch.float32).view(1)
+        g = torch.as_tensor(gamma, dtype=torch.float32, device=coords.device).view(1)
         fake = fake + gamma_map(ldr, g) * gw
         real = real + gamma_map(batch["img"], g) * gw
     losses = OrderedDict()
     losses["img_loss"] = ((fake - real) ** 2).mean()                                # loss_functions.py:12
 
-    z3, z1 = torch.zeros(1, 3), torch.zeros(1, 1)
+    z3, z1 = torch.zeros(1, 3, device=coords.device), torch.zeros(1, 1, device=coords.device)
     ue, _ = tonemap(state["tm"], z3, z1)
     losses["ue_loss"] = torch.mean(torch.abs(ue - cfg.fixed_value))                 # 244-245
     if cfg.with_grad_loss and grad_loss_points is not None:
         slope = tonemap_min_slope(state["tm"], grad_loss_points[0], grad_loss_points[1])
         losses["grad_loss"] = torch.relu(-slope) * 1e6                              # 248-252 (value only)
+    # img_weight / ue_weight = 1 reproduce the reference; data-parallel ranks use (B_local/B_global, 1/world)
+    # so that the per-rank totals SUM to the single-process loss (neucam_b200/dist.py)
+    weights = {"img_loss": img_weight, "ue_loss": ue_weight}
     total = 0.0
-    for v in losses.values():
-        total = total + v.mean()                                                    # 256-265
+    for k, v in losses.items():
+        total = total + v.mean() * weights.get(k, 1.0)                              # 256-265
     losses["total"] = total
     return (losses, inter) if return_intermediates else losses
 
 
-def step_grads(state, batch, cfg, gamma=None, grad_loss_points=None):
+def step_grads(state, batch, cfg, gamma=None, grad_loss_points=None, img_weight=1.0, ue_weight=1.0):
     """Losses + gradients of the total loss w.r.t. every tensor in `state` (training.py:269-270)."""
     leaves = {}
     st = {}
@@ -249,7 +253,7 @@ def step_grads(state, batch, cfg, gamma=None, grad_loss_points=None):
             t = v.detach().clone().requires_grad_(True)
             st[slot][k] = t
             leaves[(slot, k)] = t
-    losses = step_losses(st, batch, cfg, gamma, grad_loss_points)
+    losses = step_losses(st, batch, cfg, gamma, grad_loss_points, img_weight=img_weight, ue_weight=ue_weight)
     grads = torch.autograd.grad(losses["total"], list(leaves.values()), allow_unused=True)
     out = {}
     for (slot, k), g in zip(leaves.keys(), grads):
