@@ -258,12 +258,17 @@ class FusedTrainStep:
             ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
                          self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw, self.duv)
 
-    def optimizer_step(self, lr=None):
-        """Gradient all-reduce (when distributed) + fused Adam + operand re-pack."""
-        P = self.params
+    def reduce_gradients(self):
+        """The step's only collective: SUM of the flat gradient buffer across the data-parallel ranks."""
         if self.world > 1:
             from .dist import allreduce_flat_gradients
-            allreduce_flat_gradients(P.grad, self.pg)
+            allreduce_flat_gradients(self.params.grad, self.pg)
+
+    def optimizer_step(self, lr=None, reduce=True):
+        """Gradient all-reduce (when distributed) + fused Adam + operand re-pack."""
+        P = self.params
+        if reduce:
+            self.reduce_gradients()
         ops.adam_tick(P.adam_state)
         ops.adam_step(P.flat, P.grad, P.exp_avg, P.exp_avg_sq, P.adam_state, self.opt.lr if lr is None else lr)
         self.repack()
@@ -290,29 +295,35 @@ class FusedTrainStep:
                             saved):
             dst.copy_(src)
         self.repack()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # the NCCL all-reduce stays outside the graphs (eager, same stream): graph 1 = forward + backward,
+        # graph 2 = Adam + re-pack.  Single GPU: one graph.
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
             self.forward_backward(use_mask=use_mask)
-            self.optimizer_step(lr)
-        self._graph = g
+            if self.world == 1:
+                self.optimizer_step(lr, reduce=False)
+        g2 = None
+        if self.world > 1:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self.optimizer_step(lr, reduce=False)
+        self._graph = (g1, g2)
         self._graph_key = (bool(use_mask), lr)
-        return g
-
-    def step(self, model_input, gt, gamma=None, use_mask=False):
-        self.load_batch(model_input, gt, gamma)
-        g = getattr(self, "_graph", None)
-        if g is not None and self._graph_key == (bool(use_mask), None):
-            g.replay()
-        else:
-            self.forward_backward(use_mask=use_mask)
-            self.optimizer_step()
-        return self.losses()
+        return self._graph
 
     def run_resident(self, use_mask=False):
         """One step on the batch already in the device buffers (graph replay when captured)."""
         g = getattr(self, "_graph", None)
         if g is not None and self._graph_key == (bool(use_mask), None):
-            g.replay()
+            g[0].replay()
+            if g[1] is not None:
+                self.reduce_gradients()
+                g[1].replay()
         else:
             self.forward_backward(use_mask=use_mask)
             self.optimizer_step()
+
+    def step(self, model_input, gt, gamma=None, use_mask=False):
+        self.load_batch(model_input, gt, gamma)
+        self.run_resident(use_mask=use_mask)
+        return self.losses()
