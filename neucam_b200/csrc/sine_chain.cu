@@ -33,10 +33,10 @@
 // results of chunks 0..2 are parked in the (already drained) accumulator columns with tcgen05.st.  The
 // next layer's first chunk starts as soon as its first k-blocks land (a_ready[kb]).
 //
-// Warp roles (384 threads per CTA): warp 0 = TMA weight producer, warp 1 = MMA issuer (leader CTA only),
-// warp 2 = TMEM allocator, warp 3 = TMA store issuer (the peer's also relays "operand k-block ready" to
-// the leader), warps 4..11 = prologue/epilogue (thread = row; warp e handles
-// the 64 columns [128 c + 64 (e/4), +64) of every chunk c, i.e. exactly one k-block of the next operand).
+// Warp roles (640 threads per CTA): warp 0 = TMA weight producer, warp 1 = MMA issuer (leader CTA only),
+// warp 2 = TMEM allocator, warp 3 = TMA store issuer, warps 4..19 = prologue/epilogue (thread = row; warp e
+// handles the 32 columns [128 c + 32 (e/4), +32) of every chunk c, i.e. half a row of one operand k-block).
+// 16 epilogue warps = 4 per scheduler: the epilogue is latency-bound, not pipe-bound (profiles/).
 #include "host_util.h"
 #include "tc05.cuh"
 
@@ -50,7 +50,7 @@ constexpr int NSTAGE = 4;
 constexpr uint32_t STAGE_BYTES = 128 * 64 * 2;     // weight chunk: 128 output rows x 64 k
 constexpr uint32_t A_BLOCK_BYTES = TILE_M * 128;   // one 64-column k-block of the operand tile
 constexpr uint32_t A_BYTES = 8 * A_BLOCK_BYTES;    // 128 x 512 fp16
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 640;
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int PAIR = 2;                            // CTAs per cluster (tcgen05 cta_group::2)
 constexpr uint16_t PAIR_MASK = 0x3;
@@ -60,9 +60,8 @@ constexpr uint32_t OFF_W = OFF_A + A_BYTES;
 constexpr uint32_t OFF_P0 = OFF_W + NSTAGE * STAGE_BYTES;   // float4[512]: 30*W0[j,0], 30*W0[j,1], 30*b0[j], 0
 constexpr uint32_t OFF_W4 = OFF_P0 + 512 * 16;              // float4[512]: W4[0..3][j] (missing rows = 0)
 constexpr uint32_t OFF_B30 = OFF_W4 + 512 * 16;             // float[3][512]: 30*b_l                    (forward)
-constexpr uint32_t OFF_BQ = OFF_B30 + 3 * 512 * 4;          // float[3][512]: 30*b_l*65536/2pi + 1.5*2^23 (forward)
-constexpr uint32_t OFF_XCH = OFF_BQ + 3 * 512 * 4;          // float4[128]: column-half exchange
-constexpr uint32_t OFF_UV = OFF_XCH + 128 * 16;             // float2[128]: the tile's input coordinates
+constexpr uint32_t OFF_XCH = OFF_B30 + 3 * 512 * 4;         // float4[4][128]: per-column-quarter partial sums
+constexpr uint32_t OFF_UV = OFF_XCH + 4 * 128 * 16;         // float2[128]: the tile's input coordinates
 constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;              // 52 mbarriers
 constexpr uint32_t OFF_TMEM = OFF_BAR + 448;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
@@ -131,7 +130,7 @@ __device__ __forceinline__ float cos_of_phase(uint32_t p16) {
   const float f = __uint_as_float(0x4B000000u | p16);   // 2^23 + p
   return __cosf(fmaf(f, TWO_PI / 65536.0f, -8388608.0f * (TWO_PI / 65536.0f)));
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -145,6 +144,15 @@ __device__ __forceinline__ void write_a_row(uint32_t a_base, uint32_t kb, uint32
     st_shared_v4(blk + sw128_offset(row, q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
+// half of a 128-byte row (32 fp16 = 16 packed words): 16-byte chunks qb..qb+3 of k-block `kb`
+__device__ __forceinline__ void write_a_half_row(uint32_t a_base, uint32_t kb, uint32_t row, uint32_t qb,
+                                                 const uint32_t (&w)[16]) {
+  const uint32_t blk = a_base + kb * A_BLOCK_BYTES;
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q)
+    st_shared_v4(blk + sw128_offset(row, qb + q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
 template <bool BWD>
 __global__ void __cluster_dims__(PAIR, 1, 1) __launch_bounds__(NTHREADS, 1)
 sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
@@ -156,7 +164,6 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   float4* s_p0 = reinterpret_cast<float4*>(sm + OFF_P0);
   float4* s_w4 = reinterpret_cast<float4*>(sm + OFF_W4);
   float* s_b30 = reinterpret_cast<float*>(sm + OFF_B30);
-  float* s_bq = reinterpret_cast<float*>(sm + OFF_BQ);
   float4* s_xch = reinterpret_cast<float4*>(sm + OFF_XCH);
   float2* s_uv = reinterpret_cast<float2*>(sm + OFF_UV);
   const uint32_t bars = base + OFF_BAR;
@@ -175,7 +182,6 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       for (int l = 0; l < 3; ++l) {
         const float b30 = 30.f * p.b_hid[l * HID + j];
         s_b30[l * HID + j] = b30;
-        s_bq[l * HID + j] = fmaf(b30, PH_PER_RAD, MAGIC);
       }
     }
   }
@@ -187,10 +193,10 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     }
     for (uint32_t k = 0; k < 8; ++k) {
       mbar_init(bar(BAR_KFREE + k), 1);
-      mbar_init(bar(BAR_AREADY + k), 128);
+      mbar_init(bar(BAR_AREADY + k), 256);
       mbar_init(bar(BAR_STORED + k), 1);
       mbar_init(bar(BAR_PEER + k), 1);
-      mbar_init(bar(BAR_AOUT + k), 128);
+      mbar_init(bar(BAR_AOUT + k), 256);
     }
     mbar_fence_init();
     tma_prefetch_desc(&maps.w);
@@ -328,21 +334,24 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     }
   } else if (warp >= FIRST_EPI_WARP) {
     // ===================== prologue / epilogue warps =====================
+    // 16 warps: warp e owns rows 32*(e%4).. (its TMEM lane quadrant) and, of every 128-column chunk c, the 32
+    // columns [128 c + 32 (e/4), +32) = one half of the 128-byte row of k-block 2c + (e/8).
     const uint32_t e = warp - FIRST_EPI_WARP;
     const uint32_t quad = warp & 3;          // TMEM lane quadrant this warp may access
-    const uint32_t half = e >> 2;            // which 64 columns of every 128-column chunk
+    const uint32_t sub = e >> 2;             // which 32 columns of every 128-column chunk
     const uint32_t row = quad * 32 + lane;   // row inside the tile
+    const uint32_t qb = (sub & 1) * 4;       // first 16-byte chunk of this thread's half row
     const uint32_t a_base = base + OFF_A;
     const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
     uint32_t lp = 0;                         // layer parity (acc_full / kfree phases)
     uint32_t ev = 0;                         // operand-write event counter (stored parity)
     float gscale = 1.f;
     if (BWD) gscale = *p.scale;
-    const uint32_t et = tid - FIRST_EPI_WARP * 32;
-    float gw0[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // layer-0 weight-gradient partials (backward)
+    const uint32_t et = tid - FIRST_EPI_WARP * 32;          // 0..511: column owned in the dW0 column pass
+    float gw0[3] = {0.f, 0.f, 0.f};                         // layer-0 weight-gradient partials (backward)
     const size_t ph_layer_stride = (size_t)p.ntiles * TILE_M * HID;
-    long long* tr = (quad == 0 && lane == 0) ? p.trace : nullptr;
-    const int role = 1 + (int)half;
+    long long* tr = (quad == 0 && lane == 0 && (sub & 1) == 0) ? p.trace : nullptr;
+    const int role = 1 + (int)(sub >> 1);
     int tile_i = 0;
 
     for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
@@ -359,11 +368,11 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       const size_t ph_row_off = ((size_t)tile * 64 * TILE_M + row) * 8;   // + chunk8 * 128 * 8
       const bool store_ph = tile_ok && p.store_act != 0;
 
-      // ---------------- prologue: first operand tile (k-blocks 2c + half) ----------------
+      // ---------------- prologue: first operand tile ----------------
       trace_stamp(tr, role, tile_i, 0, 7, 0);
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
       if (BWD) {
-        if (half == 0) s_uv[row] = make_float2(u, v);
+        if (sub == 0) s_uv[row] = make_float2(u, v);
         if (valid) {
           const float* dyr = p.dy + (size_t)grow * p.out_dim;
           const float sc = gscale * 30.f;
@@ -375,23 +384,23 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       }
 #pragma unroll 1
       for (uint32_t c = 0; c < 4; ++c) {
-        const uint32_t kb = 2 * c + half;
-        const uint32_t col = kb * 64;
-        uint32_t w[32];
+        const uint32_t col = c * 128 + sub * 32;
+        const uint32_t kb = col >> 6;
+        uint32_t w[16];
         if (!BWD) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const float4 q0 = s_p0[col + 2 * i], q1 = s_p0[col + 2 * i + 1];
             w[i] = pack_h2(__sinf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z))), __sinf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z))));
           }
         } else {
           const uint16_t* ph3 = p.phase + 2 * ph_layer_stride + ph_row_off + (size_t)(col >> 3) * (TILE_M * 8);
-          uint4 pv[8];
+          uint4 pv[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
+          for (int q = 0; q < 4; ++q)
             pv[q] = tile_ok ? *reinterpret_cast<const uint4*>(ph3 + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -404,7 +413,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           }
         }
         if (ev > 0) mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
-        write_a_row(a_base, kb, row, w);
+        write_a_half_row(a_base, kb, row, qb, w);
         fence_proxy_async_smem();
         mbar_arrive(bar(BAR_AREADY + kb));
       }
@@ -416,7 +425,6 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       for (int g = 0; g < 3; ++g) {
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // head (fwd) / duv (bwd) partials
         const float* b30 = s_b30 + g * HID;
-        const float* bq = s_bq + g * HID;
         uint16_t* ph_out = p.phase + (size_t)g * ph_layer_stride + ph_row_off;
         const uint16_t* ph_in = p.phase + (size_t)(g < 2 ? 1 - g : 0) * ph_layer_stride + ph_row_off;
 
@@ -429,33 +437,28 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           const bool is_b = (step == 2 || step == 3);
           const uint32_t c = is_b ? (step - 2) : (step < 2 ? step : step - 2);
           const bool park = (step < 2);
-          const uint32_t kb = 2 * c + half;
-          const uint32_t col = kb * 64;
-          uint32_t w[32];
+          const uint32_t col = c * 128 + sub * 32;
+          const uint32_t kb = col >> 6;
+          uint32_t w[16];
           trace_stamp(tr, role, tile_i, g, step, 0);
           if (!is_b) {
-            uint4 pv[8];
+            uint4 pv[4];
             if (BWD && g < 2) {
               // phases do not depend on the MMA: fetch them while waiting for the accumulator
               const uint16_t* src = ph_in + (size_t)(col >> 3) * (TILE_M * 8);
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
+              for (int q = 0; q < 4; ++q)
                 pv[q] = tile_ok ? *reinterpret_cast<const uint4*>(src + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
             }
             mbar_wait(bar(BAR_ACC + c), lp);
             tc_fence_after_sync();
             trace_stamp(tr, role, tile_i, g, step, 1);
-            uint32_t r[64];
-            {
-              uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
-              uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
-              tmem_ld_32x32b_x32(t_row + col, r0);
-              tmem_ld_32x32b_x32(t_row + col + 32, r1);
-              tmem_ld_wait();
-            }
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + col, r);
+            tmem_ld_wait();
             if (!BWD) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
+              for (int q = 0; q < 4; ++q) {
                 uint32_t pw[4];
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
@@ -465,8 +468,9 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                   const float h0 = __sinf(fmaf(z0, 30.f, b30[j])), h1 = __sinf(fmaf(z1, 30.f, b30[j + 1]));
                   w[q * 4 + jj] = pack_h2(h0, h1);
                   if (store_ph) {
-                    const uint32_t p0 = __float_as_uint(fmaf(z0, 30.f * PH_PER_RAD, bq[j]));
-                    const uint32_t p1 = __float_as_uint(fmaf(z1, 30.f * PH_PER_RAD, bq[j + 1]));
+                    // phase in revolutions * 65536, rounded on the FMA pipe (1.5 * 2^23 magic number)
+                    const uint32_t p0 = __float_as_uint(fmaf(z0, 30.f * PH_PER_RAD, fmaf(b30[j], PH_PER_RAD, MAGIC)));
+                    const uint32_t p1 = __float_as_uint(fmaf(z1, 30.f * PH_PER_RAD, fmaf(b30[j + 1], PH_PER_RAD, MAGIC)));
                     pw[jj] = __byte_perm(p0, p1, 0x5410);
                   }
                   if (g == 2) {
@@ -483,7 +487,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               }
             } else {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
+              for (int q = 0; q < 4; ++q) {
                 const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
@@ -509,21 +513,21 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             trace_stamp(tr, role, tile_i, g, step, 2);
             if (park) {
               // park the packed result in the accumulator columns this thread has just drained
-              tmem_st_32x32b_x32(t_row + col, w);
+              tmem_st_32x32b_x16(t_row + col, w);
               tmem_st_wait();
               trace_stamp(tr, role, tile_i, g, step, 3);
               continue;
             }
           } else {
-            tmem_ld_32x32b_x32(t_row + col, w);
+            tmem_ld_32x32b_x16(t_row + col, w);
             tmem_ld_wait();
             mbar_wait(bar(BAR_KFREE + c), lp);
             trace_stamp(tr, role, tile_i, g, step, 1);
           }
-          // operand write of k-block kb (B steps and the last chunk)
+          // operand write of this thread's half row of k-block kb (B steps and chunks 2,3)
           mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
           if (is_b) trace_stamp(tr, role, tile_i, g, step, 2);
-          write_a_row(a_base, kb, row, w);
+          write_a_half_row(a_base, kb, row, qb, w);
           fence_proxy_async_smem();
           tc_fence_before_sync();
           mbar_arrive(bar((g < 2 ? BAR_AREADY : BAR_AOUT) + kb));
@@ -533,55 +537,56 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         ++ev;
 
         if (g == 2) {
-          if (half == 1) s_xch[row] = make_float4(acc0, acc1, acc2, acc3);
+          // combine the 4 column quarters of every row: head output (forward) / coordinate gradient (backward)
+          s_xch[sub * TILE_M + row] = make_float4(acc0, acc1, acc2, acc3);
           epi_bar_sync();
-          if (half == 0 && valid) {
-            const float4 o = s_xch[row];
-            if (!BWD) {
-              float* yr = p.y + (size_t)grow * p.out_dim;
-              yr[0] = acc0 + o.x + p.b4[0];
-              yr[1] = acc1 + o.y + p.b4[1];
-              yr[2] = acc2 + o.z + p.b4[2];
-              if (p.out_dim > 3) yr[3] = acc3 + o.w + p.b4[3];
-            } else {
-              // s_p0 holds 30*W0 and dz carries the loss scale: undo both
-              const float inv = 1.f / (30.f * gscale);
-              *reinterpret_cast<float2*>(p.duv + 2 * grow) = make_float2((acc0 + o.x) * inv, (acc1 + o.y) * inv);
+          if (sub == 0) {
+            float4 o = s_xch[row];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {   // fixed order: results are bit-reproducible run to run
+              const float4 t = s_xch[q * TILE_M + row];
+              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            if (valid) {
+              if (!BWD) {
+                float* yr = p.y + (size_t)grow * p.out_dim;
+                yr[0] = o.x + p.b4[0];
+                yr[1] = o.y + p.b4[1];
+                yr[2] = o.z + p.b4[2];
+                if (p.out_dim > 3) yr[3] = o.w + p.b4[3];
+              } else {
+                // s_p0 holds 30*W0 and dz carries the loss scale: undo both
+                const float inv = 1.f / (30.f * gscale);
+                *reinterpret_cast<float2*>(p.duv + 2 * grow) = make_float2(o.x * inv, o.y * inv);
+              }
             }
           }
           if (BWD) {
             // dW0[j,:] += sum_r dz0[r,j] * uv[r,:], db0[j] += sum_r dz0[r,j]: column pass over the dz0 tile
             // that now sits in the operand buffer (never stored to HBM).  epi_bar_sync above ordered all writes.
-            const uint32_t cc = et * 2;
+            const uint32_t cc = et;
             const uint32_t col_addr = a_base + (cc >> 6) * A_BLOCK_BYTES + (cc & 7) * 2;
             const uint32_t chunk = (cc & 63) >> 3;
 #pragma unroll 8
             for (uint32_t r2 = 0; r2 < TILE_M; ++r2) {
-              uint32_t wv;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(col_addr + sw128_offset(r2, chunk)));
-              const float2 z = unpack_h2(wv);
+              unsigned short hv;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(col_addr + sw128_offset(r2, chunk)));
+              const float z = __half2float(__ushort_as_half(hv));
               const float2 t = s_uv[r2];
-              gw0[0][0] = fmaf(z.x, t.x, gw0[0][0]);
-              gw0[0][1] = fmaf(z.x, t.y, gw0[0][1]);
-              gw0[0][2] += z.x;
-              gw0[1][0] = fmaf(z.y, t.x, gw0[1][0]);
-              gw0[1][1] = fmaf(z.y, t.y, gw0[1][1]);
-              gw0[1][2] += z.y;
+              gw0[0] = fmaf(z, t.x, gw0[0]);
+              gw0[1] = fmaf(z, t.y, gw0[1]);
+              gw0[2] += z;
             }
-            epi_bar_sync();   // the next tile's prologue overwrites the operand tile and s_uv
           }
+          epi_bar_sync();   // the next tile's prologue overwrites the operand tile, s_uv and re-uses s_xch
         }
       }
     }
     if (BWD) {
       const float inv = 1.f / gscale;
-      const uint32_t cc = et * 2;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        atomicAdd(p.dw0 + (cc + k) * 2 + 0, gw0[k][0] * inv);
-        atomicAdd(p.dw0 + (cc + k) * 2 + 1, gw0[k][1] * inv);
-        atomicAdd(p.db0 + (cc + k), gw0[k][2] * inv);
-      }
+      atomicAdd(p.dw0 + et * 2 + 0, gw0[0] * inv);
+      atomicAdd(p.dw0 + et * 2 + 1, gw0[1] * inv);
+      atomicAdd(p.db0 + et, gw0[2] * inv);
     }
   }
 
