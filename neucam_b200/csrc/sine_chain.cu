@@ -33,8 +33,9 @@
 // results of chunks 0..2 are parked in the (already drained) accumulator columns with tcgen05.st.  The
 // next layer's first chunk starts as soon as its first k-blocks land (a_ready[kb]).
 //
-// Warp roles (640 threads per CTA): warp 0 = TMA weight producer, warp 1 = MMA issuer (leader CTA only),
-// warp 2 = TMEM allocator, warp 3 = TMA store issuer, warps 4..19 = prologue/epilogue (thread = row; warp e
+// Warp roles (640 threads per CTA): warps 0..15 = prologue/epilogue, warp 16 = TMA weight producer, warp 17 =
+// MMA issuer (leader CTA) / k-block-ready relay (peer CTA), warp 18 = TMEM allocator, warp 19 = TMA store
+// issuer.  Epilogue: thread = row; warp e
 // handles the 32 columns [128 c + 32 (e/4), +32) of every chunk c, i.e. half a row of one operand k-block).
 // 16 epilogue warps = 4 per scheduler: the epilogue is latency-bound, not pipe-bound (profiles/).
 #include "host_util.h"
@@ -51,7 +52,11 @@ constexpr uint32_t STAGE_BYTES = 128 * 64 * 2;     // weight chunk: 128 output r
 constexpr uint32_t A_BLOCK_BYTES = TILE_M * 128;   // one 64-column k-block of the operand tile
 constexpr uint32_t A_BYTES = 8 * A_BLOCK_BYTES;    // 128 x 512 fp16
 constexpr int NTHREADS = 640;
-constexpr int FIRST_EPI_WARP = 4;
+constexpr int FIRST_EPI_WARP = 0;
+// Control warps take the HIGHEST warp ids: the warp scheduler arbitrates highest-id-first, and the single-lane
+// producer / MMA-issuer / relay / store threads must never queue behind the 16 busy epilogue warps (measured:
+// with control warps at ids 0..3 every mbarrier poll of the MMA thread took 100-900 ns).
+constexpr int WARP_PRODUCER = 16, WARP_MMA = 17, WARP_ALLOC = 18, WARP_STORE = 19;
 constexpr int PAIR = 2;                            // CTAs per cluster (tcgen05 cta_group::2)
 constexpr uint16_t PAIR_MASK = 0x3;
 
@@ -101,10 +106,14 @@ struct ChainParams {
   int dbg;               // debug experiments: bit0 = do not issue MMAs, bit1 = do not issue weight loads
 };
 
-// trace layout: [role 0=mma,1=epi half0,2=epi half1][tile 0..1][g 0..2][step 0..7][4 stamps]
+// trace layout: [role 0=mma,1=epi half0,2=epi half1 | +3 for the peer CTA][tile 0..1][g 0..2][step 0..7][4 stamps]
+// (globaltimer so that the two SMs of the pair share a time base)
 __device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i, int g, int step, int k) {
-  if (tr != nullptr && blockIdx.x == 0 && tile_i < 2)
-    tr[(((role * 2 + tile_i) * 3 + g) * 8 + step) * 4 + k] = clock64();
+  if (tr != nullptr && blockIdx.x < 2 && tile_i < 2) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tr[((((role + 3 * (int)blockIdx.x) * 2 + tile_i) * 3 + g) * 8 + step) * 4 + k] = (long long)t;
+  }
 }
 
 struct ChainMaps {
@@ -201,7 +210,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     mbar_fence_init();
     tma_prefetch_desc(&maps.w);
   }
-  if (warp == 2) {
+  if (warp == WARP_ALLOC) {
     tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     tmem_relinquish_2cta();
   }
@@ -217,7 +226,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   // only the peer's tile is past the end it runs a phantom tile (all rows invalid, no global traffic).
   const int lead0 = (int)(blockIdx.x & ~1u);
 
-  if (warp == 0) {
+  if (warp == WARP_PRODUCER) {
     // ===================== TMA weight producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
@@ -243,7 +252,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (leader CTA of the pair) =====================
     if (lane == 0 && leader) {
       const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
@@ -260,7 +269,9 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                 if (kb == 0) {
                   for (int k = 0; k < 4; ++k) {
                     mbar_wait(bar(BAR_AREADY + k), ev & 1);
+                    trace_stamp(p.trace, 0, tile_i, g, 4, k);
                     mbar_wait(bar(BAR_PEER + k), ev & 1);
+                    trace_stamp(p.trace, 0, tile_i, g, 5, k);
                   }
                 } else if (kb >= 4) {
                   mbar_wait(bar(BAR_AREADY + kb), ev & 1);
@@ -296,17 +307,20 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       uint32_t ev = 0;
       uint32_t peer_bar[8];
       for (uint32_t k = 0; k < 8; ++k) peer_bar[k] = mapa_shared(bar(BAR_PEER + k), 0);
-      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
+      int tile_i = 0;
+      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
         for (int e3 = 0; e3 < 3; ++e3) {
           for (int kb = 0; kb < 8; ++kb) {
             mbar_wait(bar(BAR_AREADY + kb), ev & 1);
             mbar_arrive_cluster(peer_bar[kb]);
+            // debug timeline: relay times of the event consumed by layer e3 (stored under "MMA role" of the peer)
+            trace_stamp(p.trace, 0, tile_i, e3, 4 + (kb >> 2), kb & 3);
           }
           ++ev;
         }
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == WARP_STORE) {
     // ===================== TMA store issuer (+ peer -> leader "k-block ready" relay) =====================
     if (lane == 0) {
       uint32_t ev = 0, tcount = 0;
@@ -332,7 +346,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       }
       if (do_store_any) tma_store_wait0();
     }
-  } else if (warp >= FIRST_EPI_WARP) {
+  } else if (warp < 16) {
     // ===================== prologue / epilogue warps =====================
     // 16 warps: warp e owns rows 32*(e%4).. (its TMEM lane quadrant) and, of every 128-column chunk c, the 32
     // columns [128 c + 32 (e/4), +32) = one half of the 128-byte row of k-block 2c + (e/8).
@@ -593,7 +607,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();   // neither CTA exits (or frees TMEM) while the pair's MMAs / remote arrives are in flight
-  if (warp == 2) tmem_dealloc_2cta(tmem_base, 512);
+  if (warp == WARP_ALLOC) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, bool need_act) {
@@ -632,7 +646,7 @@ int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
 }  // namespace
 
 // Debug: when non-null, CTA 0 of the next chain launches writes clock64 stamps of its MMA / epilogue roles
-// into trace[3*2*3*8*4] (tools/chain_timeline.py decodes it).
+// into trace[6*2*3*8*4] (tools/chain_timeline.py decodes it).
 extern "C" int neucam_debug_set_chain_trace(long long* trace_dev) {
   g_trace = trace_dev;
   return 0;

@@ -341,8 +341,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// NOTE: deliberately NOT `.release.cluster`: ptxas lowers that to MEMBAR.ALL.GPU + ERRBAR in front of every
+// arrive (measured ~1 us each inside a busy SM).  The payload this signals is shared-memory data already
+// published with fence.proxy.async + a CTA-scope mbarrier hand-off, consumed by the tensor core.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;

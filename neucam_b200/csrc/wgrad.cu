@@ -81,7 +81,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
     mbar_init(bar_acc, 1);
     mbar_fence_init();
   }
-  if (warp == 2) {
+  if (warp == 4) {
     tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     tmem_relinquish_2cta();
   }
@@ -92,7 +92,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
   const uint32_t tmem_base = *tmem_slot;
 
   if (nk > 0) {
-    if (warp == 0) {
+    if (warp == 4) {
       if (lane == 0) {
         const CUtensorMap* ta = &maps.dz[layer];
         const CUtensorMap* tb = &maps.act[layer];
@@ -107,7 +107,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
       if (lane == 0 && leader) {
         const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
         const uint32_t idesc_b = make_idesc_f16(256, 16, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
@@ -131,7 +131,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
         umma_commit_2cta(bar_acc, PAIR_MASK);
       }
     } else {
-      // epilogue warps 2..5: TMEM lane quadrant = warp % 4; this CTA owns dW rows m0.., all 256 columns of the tile
+      // epilogue warps 0..3 (control warps 4,5 have the highest ids = scheduling priority): TMEM lane quadrant = warp; this CTA owns dW rows m0.., all 256 columns of the tile
       const uint32_t quad = warp & 3;
       const uint32_t row = quad * 32 + lane;
       const float inv = 1.f / *p.scale;
@@ -158,7 +158,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 2) tmem_dealloc_2cta(tmem_base, 512);
+  if (warp == 4) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // out[c][k] += sum_r s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):

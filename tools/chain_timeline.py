@@ -21,7 +21,7 @@ def run(bwd, Q=148 * 128 * 4):
     y = torch.empty(Q, 3, device=dev)
     scale = torch.tensor([2.0 ** 18], device=dev)
     dw0 = torch.zeros(512, 2, device=dev); db0 = torch.zeros(512, device=dev)
-    trace = torch.zeros(576, dtype=torch.int64, device=dev)
+    trace = torch.zeros(1152, dtype=torch.int64, device=dev)
     for it in range(2):
         ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, phase16=ph)
     lib = _lib.lib()
@@ -35,10 +35,10 @@ def run(bwd, Q=148 * 128 * 4):
         ops.sine_mlp_bwd(uv, w0, b0, wT16, w4, dy, ph, scale, dz, dw0, db0)
     lib.neucam_debug_set_chain_trace(ctypes.c_void_p(0))
     torch.cuda.synchronize()
-    t = trace.cpu().view(3, 2, 3, 8, 4)
+    t = trace.cpu().view(6, 2, 3, 8, 4)
     t0 = int(t[t > 0].min())
     rel = lambda x: int(x) - t0 if int(x) > 0 else -1
-    print("==== %s (cycles since first stamp; CTA 0, tile 1 = steady state)" % ("BWD" if bwd else "FWD"))
+    print("==== %s (ns since first stamp; CTA pair 0, tile 1 = steady state)" % ("BWD" if bwd else "FWD"))
     for tile_i in (0, 1):
         print(f"-- tile {tile_i}: prologue half0 {rel(t[1,tile_i,0,7,0])}..{rel(t[1,tile_i,0,7,1])}")
         for g in range(3):
@@ -46,13 +46,17 @@ def run(bwd, Q=148 * 128 * 4):
             for c in range(4):
                 m = t[0, tile_i, g, c]
                 print(f"   MMA chunk {c}: start {rel(m[0])} first-A-ready {rel(m[1])} kb7-ready {rel(m[2])} issued {rel(m[3])}")
+            print("   MMA waits at kb=0: local a_ready[0..3] " + str([rel(x) for x in t[0, tile_i, g, 4]]) +
+                  "  peer[0..3] " + str([rel(x) for x in t[0, tile_i, g, 5]]))
+            print("   peer relay of this layer's INPUT k-blocks 0..7: " + str([rel(x) for x in t[3, tile_i, g, 4]] + [rel(x) for x in t[3, tile_i, g, 5]]))
             names = ["A0", "A1", "B0", "B1", "A2", "A3"]
-            for h in (0, 1):
-                row = []
-                for st in range(6):
-                    e = t[1 + h, tile_i, g, st]
-                    row.append(f"{names[st]}[{rel(e[0])},{rel(e[1])},{rel(e[2])},{rel(e[3])}]")
-                print(f"   epi half{h}: " + " ".join(row))
+            for cta in (0, 1):
+                for h in (0, 1):
+                    row = []
+                    for st in range(6):
+                        e = t[3 * cta + 1 + h, tile_i, g, st]
+                        row.append(f"{names[st]}[{rel(e[0])},{rel(e[1])},{rel(e[2])},{rel(e[3])}]")
+                    print(f"   cta{cta} epi half{h}: " + " ".join(row))
 
 if __name__ == "__main__":
     run(False)
