@@ -40,6 +40,11 @@ int neucam_check_device(void);
  * bit4 A tile staged by threads instead of TMA. */
 int neucam_umma_probe(const void* a, const void* b, float* d, int N, int K, int flags, void* stream);
 
+/* Tensor-pipe issue-rate microbenchmark (tools/umma_rate.py): `grid` CTAs in pairs; the leader of each pair
+ * issues iters x 4 back-to-back MMAs (cta_group::2 M256xNxK16 if two_cta else cta_group::1 M128xNxK16) on
+ * resident smem tiles; out_dev[2*cta] = issue cycles, out_dev[2*cta+1] = cycles until completion. */
+int neucam_umma_rate(int N, int iters, int two_cta, int kblocks, int grid, long long* out_dev, void* stream);
+
 /* ---- scene sine-MLP (replaces SingleBVPNet.forward -> FCBlock.forward -> BatchLinear/Sine chain,
  * modules.py:455-475, 90-95, 17-35, for the shipped shape 2 -> 512 x4 -> out_dim, and its autograd
  * backward w.r.t. activations and input coordinates, training.py:270) -------------------------

@@ -228,7 +228,9 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 
   if (warp == WARP_PRODUCER) {
     // ===================== TMA weight producer =====================
-    if (lane == 0) {
+    // (the whole warp runs the loop and the waits; only the issue instructions are predicated to lane 0, so the
+    //  warp never sits diverged against lanes parked at the final barrier)
+    {
       uint32_t s = 0, ph = 0;
       uint32_t full_bar[NSTAGE];   // the leader's w_full barriers (shared::cluster addresses)
       for (uint32_t k = 0; k < NSTAGE; ++k) full_bar[k] = mapa_shared(bar(BAR_WFULL + k), 0);
@@ -238,14 +240,17 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int h = 0; h < 2; ++h) {
             for (int kb = 0; kb < 8; ++kb) {
               mbar_wait(bar(BAR_WEMPTY + s), ph ^ 1);
-              if (p.dbg & 2) {
-                if (leader) mbar_arrive(bar(BAR_WFULL + s));
-              } else {
-                // the leader's barrier collects both halves of the 256-row weight tile
-                if (leader) mbar_arrive_expect_tx(bar(BAR_WFULL + s), 2 * STAGE_BYTES);
-                tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w, full_bar[s], kb * 64,
-                                 wl * HID + h * 256 + (int)crank * 128);
+              if (lane == 0) {
+                if (p.dbg & 2) {
+                  if (leader) mbar_arrive(bar(BAR_WFULL + s));
+                } else {
+                  // the leader's barrier collects both halves of the 256-row weight tile
+                  if (leader) mbar_arrive_expect_tx(bar(BAR_WFULL + s), 2 * STAGE_BYTES);
+                  tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w, full_bar[s], kb * 64,
+                                   wl * HID + h * 256 + (int)crank * 128);
+                }
               }
+              __syncwarp();
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
           }
@@ -254,14 +259,15 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     }
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (leader CTA of the pair) =====================
-    if (lane == 0 && leader) {
+    if (leader) {
       const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
       uint32_t s = 0, ph = 0, ev = 0;   // ev = operand-write event counter (a_ready parity)
+      long long* trm = (lane == 0) ? p.trace : nullptr;
       int tile_i = 0;
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
         for (int g = 0; g < 3; ++g) {
           for (int h = 0; h < 2; ++h) {
-            trace_stamp(p.trace, 0, tile_i, g, 2 * h, 0);
+            trace_stamp(trm, 0, tile_i, g, 2 * h, 0);
             for (int kb = 0; kb < 8; ++kb) {
               if (h == 0) {
                 // the first half chases the epilogues of the previous layer k-block by k-block; accumulator
@@ -269,60 +275,68 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                 if (kb == 0) {
                   for (int k = 0; k < 4; ++k) {
                     mbar_wait(bar(BAR_AREADY + k), ev & 1);
-                    trace_stamp(p.trace, 0, tile_i, g, 4, k);
+                    trace_stamp(trm, 0, tile_i, g, 4, k);
                     mbar_wait(bar(BAR_PEER + k), ev & 1);
-                    trace_stamp(p.trace, 0, tile_i, g, 5, k);
+                    trace_stamp(trm, 0, tile_i, g, 5, k);
                   }
                 } else if (kb >= 4) {
                   mbar_wait(bar(BAR_AREADY + kb), ev & 1);
                   mbar_wait(bar(BAR_PEER + kb), ev & 1);
                 }
-                if (kb == 0) trace_stamp(p.trace, 0, tile_i, g, 0, 1);
-                if (kb == 7) trace_stamp(p.trace, 0, tile_i, g, 0, 2);
+                if (kb == 0) trace_stamp(trm, 0, tile_i, g, 0, 1);
+                if (kb == 7) trace_stamp(trm, 0, tile_i, g, 0, 2);
               }
               mbar_wait(bar(BAR_WFULL + s), ph);
               tc_fence_after_sync();
-              const uint32_t a_addr = base + OFF_A + kb * A_BLOCK_BYTES;
-              const uint32_t b_addr = base + OFF_W + s * STAGE_BYTES;
+              if (lane == 0) {
+                const uint32_t a_addr = base + OFF_A + kb * A_BLOCK_BYTES;
+                const uint32_t b_addr = base + OFF_W + s * STAGE_BYTES;
 #pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16) {
-                if (p.dbg & 1) break;
-                umma_f16_ss_2cta(tmem_base + h * 256, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
-                                 make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, (kb | k16) != 0 ? 1u : 0u);
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  if (p.dbg & 1) break;
+                  umma_f16_ss_2cta(tmem_base + h * 256, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
+                                   make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, (kb | k16) != 0 ? 1u : 0u);
+                }
+                umma_commit_2cta(bar(BAR_WEMPTY + s), PAIR_MASK);
+                // operand k-blocks (2c, 2c+1) of chunk c = 0,1 are dead once the last half has consumed them
+                if (h == 1 && (kb == 1 || kb == 3)) umma_commit_2cta(bar(BAR_KFREE + (kb >> 1)), PAIR_MASK);
               }
-              umma_commit_2cta(bar(BAR_WEMPTY + s), PAIR_MASK);
-              // operand k-blocks (2c, 2c+1) of chunk c = 0,1 are dead once the last half has consumed them
-              if (h == 1 && (kb == 1 || kb == 3)) umma_commit_2cta(bar(BAR_KFREE + (kb >> 1)), PAIR_MASK);
+              __syncwarp();
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
-            umma_commit_2cta(bar(BAR_ACC + 2 * h), PAIR_MASK);
-            umma_commit_2cta(bar(BAR_ACC + 2 * h + 1), PAIR_MASK);
-            trace_stamp(p.trace, 0, tile_i, g, 2 * h, 3);
+            if (lane == 0) {
+              umma_commit_2cta(bar(BAR_ACC + 2 * h), PAIR_MASK);
+              umma_commit_2cta(bar(BAR_ACC + 2 * h + 1), PAIR_MASK);
+            }
+            __syncwarp();
+            trace_stamp(trm, 0, tile_i, g, 2 * h, 3);
           }
           ++ev;
         }
       }
-    } else if (lane == 0) {
+    } else {
       // peer CTA: this warp has no MMAs to issue; it relays "operand k-block ready" to the leader
       uint32_t ev = 0;
       uint32_t peer_bar[8];
       for (uint32_t k = 0; k < 8; ++k) peer_bar[k] = mapa_shared(bar(BAR_PEER + k), 0);
+      long long* trm = (lane == 0) ? p.trace : nullptr;
       int tile_i = 0;
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
         for (int e3 = 0; e3 < 3; ++e3) {
           for (int kb = 0; kb < 8; ++kb) {
             mbar_wait(bar(BAR_AREADY + kb), ev & 1);
-            mbar_arrive_cluster(peer_bar[kb]);
+            if (lane == 0) mbar_arrive_cluster(peer_bar[kb]);
+            __syncwarp();
             // debug timeline: relay times of the event consumed by layer e3 (stored under "MMA role" of the peer)
-            trace_stamp(p.trace, 0, tile_i, e3, 4 + (kb >> 2), kb & 3);
+            trace_stamp(trm, 0, tile_i, e3, 4 + (kb >> 2), kb & 3);
           }
           ++ev;
         }
       }
     }
   } else if (warp == WARP_STORE) {
-    // ===================== TMA store issuer (+ peer -> leader "k-block ready" relay) =====================
-    if (lane == 0) {
+    // ===================== TMA store issuer =====================
+    {
       uint32_t ev = 0, tcount = 0;
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tcount) {
         const int tile = lt + (int)crank;
@@ -332,19 +346,25 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int kb = 0; kb < 8; ++kb) {
             if (e4 < 3) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
             else        mbar_wait(bar(BAR_AOUT + kb), tcount & 1);
-            if (do_store) {
-              tma_store_2d(&maps.act[e4], base + OFF_A + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
-              tma_store_commit();
-              if (kb > 0) tma_store_wait_read1();
+            if (lane == 0) {
+              if (do_store) {
+                tma_store_2d(&maps.act[e4], base + OFF_A + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
+                tma_store_commit();
+                if (kb > 0) tma_store_wait_read1();
+              }
+              if (kb > 0) mbar_arrive(bar(BAR_STORED + kb - 1));
             }
-            if (kb > 0) mbar_arrive(bar(BAR_STORED + kb - 1));
+            __syncwarp();
           }
-          if (do_store) tma_store_wait_read0();
-          mbar_arrive(bar(BAR_STORED + 7));
+          if (lane == 0) {
+            if (do_store) tma_store_wait_read0();
+            mbar_arrive(bar(BAR_STORED + 7));
+          }
+          __syncwarp();
           if (e4 < 3) ++ev;
         }
       }
-      if (do_store_any) tma_store_wait0();
+      if (lane == 0 && do_store_any) tma_store_wait0();
     }
   } else if (warp < 16) {
     // ===================== prologue / epilogue warps =====================
@@ -396,23 +416,43 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           if (p.out_dim > 3) d3 = dyr[3] * sc;
         }
       }
+      if (!BWD) {
 #pragma unroll 1
-      for (uint32_t c = 0; c < 4; ++c) {
-        const uint32_t col = c * 128 + sub * 32;
-        const uint32_t kb = col >> 6;
-        uint32_t w[16];
-        if (!BWD) {
+        for (uint32_t c = 0; c < 4; ++c) {
+          const uint32_t col = c * 128 + sub * 32;
+          const uint32_t kb = col >> 6;
+          uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 q0 = s_p0[col + 2 * i], q1 = s_p0[col + 2 * i + 1];
             w[i] = pack_h2(__sinf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z))), __sinf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z))));
           }
-        } else {
-          const uint16_t* ph3 = p.phase + 2 * ph_layer_stride + ph_row_off + (size_t)(col >> 3) * (TILE_M * 8);
+          if (ev > 0) mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
+          write_a_half_row(a_base, kb, row, qb, w);
+          fence_proxy_async_smem();
+          mbar_arrive(bar(BAR_AREADY + kb));
+        }
+      } else {
+        // the layer-3 phases come from HBM: keep the next chunk's 4 loads in flight while this one is computed
+        const uint16_t* ph3 = p.phase + 2 * ph_layer_stride + ph_row_off + (size_t)((sub * 32) >> 3) * (TILE_M * 8);
+        uint4 pvn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          pvn[q] = tile_ok ? *reinterpret_cast<const uint4*>(ph3 + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (uint32_t c = 0; c < 4; ++c) {
+          const uint32_t col = c * 128 + sub * 32;
+          const uint32_t kb = col >> 6;
           uint4 pv[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            pv[q] = tile_ok ? *reinterpret_cast<const uint4*>(ph3 + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < 4; ++q) pv[q] = pvn[q];
+          if (c < 3) {
+            const uint16_t* nxt = ph3 + (size_t)((c + 1) * 16) * (TILE_M * 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              pvn[q] = tile_ok ? *reinterpret_cast<const uint4*>(nxt + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
+          }
+          uint32_t w[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
@@ -425,11 +465,11 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               w[q * 4 + jj] = pack_h2_sat(g0 * cos_of_phase(pw[jj] & 0xFFFFu), g1 * cos_of_phase(pw[jj] >> 16));
             }
           }
+          if (ev > 0) mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
+          write_a_half_row(a_base, kb, row, qb, w);
+          fence_proxy_async_smem();
+          mbar_arrive(bar(BAR_AREADY + kb));
         }
-        if (ev > 0) mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
-        write_a_half_row(a_base, kb, row, qb, w);
-        fence_proxy_async_smem();
-        mbar_arrive(bar(BAR_AREADY + kb));
       }
       ++ev;
       trace_stamp(tr, role, tile_i, 0, 7, 1);
@@ -470,7 +510,11 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_row + col, r);
             tmem_ld_wait();
-            if (!BWD) {
+            if (p.dbg & 4) {
+              // debug: no epilogue math (isolates tensor-pipe rate from SIMT/LDS contention)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w[i] = r[2 * i];
+            } else if (!BWD) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 uint32_t pw[4];

@@ -144,3 +144,87 @@ extern "C" int neucam_umma_probe(const void* a, const void* b, float* d, int N, 
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// MMA issue-rate microbenchmark: one CTA pair, the leader issues `iters` back-to-back
+// tcgen05.mma.cta_group::2 M256 x N x K16 (or cta_group::1 M128 x N) on resident smem tiles and reports
+// clock64 cycles from first issue to completion.  Tells what the tensor pipe can sustain for a shape.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_rate_kernel(int N, int iters, int two_cta, int kblocks, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar_dummy[2];
+  const int overhead = kblocks >> 8;   // bits 8..: per-iteration control overhead to emulate (1 = commit, 2 = wait+fence)
+  kblocks &= 0xff;
+  __shared__ uint32_t slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < (192u * 1024u) / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0x3C003C00u;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_init(smem_u32(&bar_dummy[0]), 1u << 20);   // commit target that never completes a phase
+    mbar_init(smem_u32(&bar_dummy[1]), 1);          // fresh barrier: waiting on parity 1 returns at once
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    if (two_cta) { tmem_alloc_2cta(smem_u32(&slot), 512); tmem_relinquish_2cta(); }
+    else         { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tm = slot;
+  const bool leader = cluster_ctarank() == 0;
+  if (tid == 0 && (leader || !two_cta)) {
+    const uint32_t idesc = make_idesc_f16(two_cta ? 256 : 128, (uint32_t)N, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
+    const uint32_t a0 = base, b0 = base + 128 * 1024;   // A: 8 k-blocks of 16 KB; B: up to 4 stages of 16 KB
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (overhead & 2) {
+        mbar_wait(smem_u32(&bar_dummy[1]), 1);
+        tc_fence_after_sync();
+      }
+      const uint32_t a_addr = a0 + (it % kblocks) * 16384;
+      const uint32_t b_addr = b0 + (it & 1) * 32768;   // a full N=256 tile is 32 KB (1-CTA) / 16 KB (2-CTA half)
+#pragma unroll
+      for (int k16 = 0; k16 < 4; ++k16) {
+        if (two_cta) umma_f16_ss_2cta(tm, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024), make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, 1u);
+        else         umma_f16_ss(tm, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024), make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, 1u);
+      }
+      if (overhead & 1) {
+        if (two_cta) umma_commit_2cta(smem_u32(&bar_dummy[0]), 0x3);
+        else         umma_commit(smem_u32(&bar_dummy[0]));
+      }
+    }
+    const long long t1 = clock64();
+    if (two_cta) umma_commit_2cta(smem_u32(&bar), 0x1);
+    else         umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t2 = clock64();
+    out[blockIdx.x * 2 + 0] = t1 - t0;
+    out[blockIdx.x * 2 + 1] = t2 - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    if (two_cta) tmem_dealloc_2cta(tm, 512);
+    else         tmem_dealloc(tm, 512);
+  }
+}
+}  // namespace
+
+extern "C" int neucam_umma_rate(int N, int iters, int two_cta, int kblocks, int grid, long long* out_dev,
+                                void* stream) {
+  NC_CHECK_ARG(N >= 16 && N <= 256 && iters > 0 && (kblocks & 0xff) >= 1 && (kblocks & 0xff) <= 8 && grid >= 2 && grid % 2 == 0);
+  const size_t smem = 193 * 1024 + 1024;
+  NC_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(N, iters, two_cta, kblocks, out_dev);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -93,22 +93,24 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
 
   if (nk > 0) {
     if (warp == 4) {
-      if (lane == 0) {
-        const CUtensorMap* ta = &maps.dz[layer];
-        const CUtensorMap* tb = &maps.act[layer];
-        uint32_t s = 0, ph = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      // whole warp runs the loop / waits; lane 0 issues (no permanently diverged control warp)
+      const CUtensorMap* ta = &maps.dz[layer];
+      const CUtensorMap* tb = &maps.act[layer];
+      uint32_t s = 0, ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (lane == 0) {
           const uint32_t full_leader = mapa_shared(bar_full + 8 * s, 0);
           if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);
           const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
           for (int a = 0; a < 2; ++a) tma_load_2d_2cta(a_st + a * ATOM_BYTES, ta, full_leader, m0 + a * 64, kb * 64);
           for (int a = 0; a < 2; ++a) tma_load_2d_2cta(b_st + a * ATOM_BYTES, tb, full_leader, n0 + a * 64, kb * 64);
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == NSTAGE) { s = 0; ph ^= 1; }
       }
     } else if (warp == 5) {
-      if (lane == 0 && leader) {
+      if (leader) {
         const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
         const uint32_t idesc_b = make_idesc_f16(256, 16, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
         const uint32_t ones = base + OFF_ONES;
@@ -116,19 +118,23 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after_sync();
-          const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
+          if (lane == 0) {
+            const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            const uint64_t ad = make_sdesc_sw128(a_st + k16 * 2048, ATOM_BYTES, 1024);
-            const uint32_t accum = (kb > kb0 || k16 > 0) ? 1u : 0u;
-            umma_f16_ss_2cta(tmem_base, ad, make_sdesc_sw128(b_st + k16 * 2048, ATOM_BYTES, 1024), idesc, accum);
-            if (with_bias)
-              umma_f16_ss_2cta(tmem_base + 256, ad, make_sdesc_sw128(ones + k16 * 2048, ATOM_BYTES, 1024), idesc_b, accum);
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const uint64_t ad = make_sdesc_sw128(a_st + k16 * 2048, ATOM_BYTES, 1024);
+              const uint32_t accum = (kb > kb0 || k16 > 0) ? 1u : 0u;
+              umma_f16_ss_2cta(tmem_base, ad, make_sdesc_sw128(b_st + k16 * 2048, ATOM_BYTES, 1024), idesc, accum);
+              if (with_bias)
+                umma_f16_ss_2cta(tmem_base + 256, ad, make_sdesc_sw128(ones + k16 * 2048, ATOM_BYTES, 1024), idesc_b, accum);
+            }
+            umma_commit_2cta(bar_empty + 8 * s, PAIR_MASK);
           }
-          umma_commit_2cta(bar_empty + 8 * s, PAIR_MASK);
+          __syncwarp();
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
-        umma_commit_2cta(bar_acc, PAIR_MASK);
+        if (lane == 0) umma_commit_2cta(bar_acc, PAIR_MASK);
+        __syncwarp();
       }
     } else {
       // epilogue warps 0..3 (control warps 4,5 have the highest ids = scheduling priority): TMEM lane quadrant = warp; this CTA owns dW rows m0.., all 256 columns of the tile
