@@ -175,6 +175,7 @@ class FusedTrainStep:
         self.sums = self.scalars[0:4]
         self.absmax_bits = self.scalars[4:5]
         self.scale = torch.ones(1, device=dev)
+        self._side = torch.cuda.Stream(device=self.device)
         self._bind()
         self.repack()
 
@@ -253,10 +254,17 @@ class FusedTrainStep:
                          self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2))
         ops.sine_mlp_wgrad(self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
                            [self.ab[i].grad for i in (1, 2, 3)])
+        # the HBM-bound head wgrad and the FMA-bound blur backward are independent: run them side by side
+        main = torch.cuda.current_stream(self.device)
+        if self.has_blur:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
+                             self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw,
+                             self.duv)
         ops.sine_mlp_head_wgrad(self.act16, dyf, self.aw[4].grad)
         if self.has_blur:
-            ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
-                         self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw, self.duv)
+            main.wait_stream(self._side)
 
     def reduce_gradients(self):
         """The step's only collective: SUM of the flat gradient buffer across the data-parallel ranks."""
