@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NEUCAM_ABI_VERSION 2
+#define NEUCAM_ABI_VERSION 3
 
 #define NEUCAM_ERR_BAD_ARG (-1)
 #define NEUCAM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point unavailable */
@@ -130,6 +130,15 @@ int neucam_psf_crf_loss(const float* y, const float* kout, const int64_t* coord_
                         int64_t global_count, float* dy, float* dkw, float* dexps, float* db4, float* sums,
                         uint32_t* dy_absmax_bits, float scale_target, float* scale_out, float* ldr_out,
                         void* stream);
+
+/* neucam_sample_batch (replaces dataio.Implicit3DWrapper.__getitem__, dataio.py:356-393,
+ *   for a video resident in HBM): data [N*H*W,3] (= img*2-1), optional gamma_w_all / mask_w_all [N*H*W].
+ *   Draws B pixel indices with replacement (Philox-4x32-10, key = seed, counter = (pixel, step)) or uses
+ *   idx_in [B] when given (index injection for parity runs); writes coords [B,3] (get_mgrid formula,
+ *   dataio.py:24-45), coord_idx [B], img [B,3] and the gathered per-pixel weights. */
+int neucam_sample_batch(const float* data, const float* gamma_w_all, const float* mask_w_all, const int64_t* idx_in,
+                        int N, int H, int W, int B, uint64_t seed, uint64_t step, float* coords, int64_t* coord_idx,
+                        float* img, float* gamma_w, float* mask_w, void* stream);
 
 /* ---- optimizer (torch.optim.Adam as constructed at training.py:51) --------------------------------------
  * state = device float[4]: {step count, 1-beta1^t, 1-beta2^t, unused}.  neucam_adam_tick advances it once

@@ -556,6 +556,73 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// on-device batch sampler / gather (replaces Implicit3DWrapper.__getitem__, dataio.py:356-393, for a video
+// that is resident in HBM): B indices drawn WITH replacement (Philox-4x32-10 keyed by seed, counter = step,
+// pixel) or taken from `idx_in`; coords recomputed from the index exactly like get_mgrid (dataio.py:24-45:
+// float64 i/(dim-1), -0.5, *2, then float32; t uses max(N-1,1)); data / per-pixel weights gathered.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+
+__global__ void __launch_bounds__(256)
+sample_batch_kernel(const float* __restrict__ data, const float* __restrict__ gamma_w_all,
+                    const float* __restrict__ mask_w_all, const long long* __restrict__ idx_in, int N, int H, int W,
+                    int B, unsigned long long seed, unsigned long long step, float* __restrict__ coords,
+                    long long* __restrict__ coord_idx, float* __restrict__ img, float* __restrict__ gamma_w,
+                    float* __restrict__ mask_w) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B) return;
+  const unsigned long long total = (unsigned long long)N * H * W;
+  unsigned long long idx;
+  if (idx_in != nullptr) {
+    idx = (unsigned long long)idx_in[p];
+  } else {
+    uint32_t c[4] = {(uint32_t)p, (uint32_t)step, (uint32_t)(step >> 32), 0x4E435553u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    const unsigned long long r64 = ((unsigned long long)c[0] << 32) | c[1];
+    idx = __umul64hi(r64, total);   // floor(r64 * total / 2^64): unbiased to 2^-64 * total
+  }
+  const int hw = H * W;
+  const int f = (int)(idx / hw), rem = (int)(idx % hw), yy = rem / W, xx = rem % W;
+  const int nt = N - 1 > 1 ? N - 1 : 1;
+  coords[3 * p + 0] = (float)(((double)f / nt - 0.5) * 2.0);
+  coords[3 * p + 1] = (float)(((double)yy / (H - 1) - 0.5) * 2.0);
+  coords[3 * p + 2] = (float)(((double)xx / (W - 1) - 0.5) * 2.0);
+  coord_idx[p] = (long long)idx;
+  img[3 * p + 0] = data[3 * idx + 0];
+  img[3 * p + 1] = data[3 * idx + 1];
+  img[3 * p + 2] = data[3 * idx + 2];
+  if (gamma_w != nullptr && gamma_w_all != nullptr) gamma_w[p] = gamma_w_all[idx];
+  if (mask_w != nullptr && mask_w_all != nullptr) mask_w[p] = mask_w_all[idx];
+}
+
+}  // namespace
+
+extern "C" int neucam_sample_batch(const float* data, const float* gamma_w_all, const float* mask_w_all,
+                                   const int64_t* idx_in, int N, int H, int W, int B, uint64_t seed, uint64_t step,
+                                   float* coords, int64_t* coord_idx, float* img, float* gamma_w, float* mask_w,
+                                   void* stream) {
+  NC_CHECK_ARG(data && coords && coord_idx && img && N > 0 && H > 1 && W > 1 && B > 0);
+  sample_batch_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      data, gamma_w_all, mask_w_all, (const long long*)idx_in, N, H, W, B, (unsigned long long)seed,
+      (unsigned long long)step, coords, (long long*)coord_idx, img, gamma_w, mask_w);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------

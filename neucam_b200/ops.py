@@ -149,3 +149,14 @@ def adam_step(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scal
                                      _lib.ptr(state), ctypes.c_float(lr), ctypes.c_float(beta1), ctypes.c_float(beta2),
                                      ctypes.c_float(eps), ctypes.c_float(grad_scale), _lib.cur_stream())
     _lib.check(rc, "neucam_adam_step")
+
+
+def sample_batch(data, gamma_w_all, mask_w_all, idx_in, shape, seed, step, coords, coord_idx, img, gamma_w, mask_w):
+    """On-device sampler / gather for a resident video (see neucam_sample_batch in the header)."""
+    _chk_cuda(data, gamma_w_all, mask_w_all, idx_in, coords, coord_idx, img, gamma_w, mask_w)
+    N, H, W = shape
+    rc = _lib.lib().neucam_sample_batch(
+        _lib.ptr(data), _lib.ptr(gamma_w_all), _lib.ptr(mask_w_all), _lib.ptr(idx_in), N, H, W, coords.shape[0],
+        ctypes.c_uint64(seed), ctypes.c_uint64(step), _lib.ptr(coords), _lib.ptr(coord_idx), _lib.ptr(img),
+        _lib.ptr(gamma_w), _lib.ptr(mask_w), _lib.cur_stream())
+    _lib.check(rc, "neucam_sample_batch")

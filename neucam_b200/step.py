@@ -221,6 +221,28 @@ class FusedTrainStep:
         if "weights" in model_input:
             self.mask_w.copy_(model_input["weights"].reshape(-1), non_blocking=non_blocking)
 
+    def attach_dataset(self, data, gamma_weights=None, mask_weights=None):
+        """Makes the video resident in HBM (data [N*H*W,3] = img*2-1, dataio.py:349) so that batches are formed on
+        the device by sample_resident() instead of the CPU DataLoader."""
+        dev = self.device
+        self.ds_data = data.reshape(-1, 3).to(dev, torch.float32).contiguous()
+        self.ds_gamma = None if gamma_weights is None else gamma_weights.reshape(-1).to(dev, torch.float32).contiguous()
+        self.ds_mask = None if mask_weights is None else mask_weights.reshape(-1).to(dev, torch.float32).contiguous()
+        self.idx_in = torch.zeros(self.B, dtype=torch.int64, device=dev)
+
+    def sample_resident(self, seed=0, step=0, indices=None, gamma=None):
+        """Forms the step's batch on the device: Philox-sampled (seed, step) or from injected `indices`
+        (host or device int64 [B]; only 8 B/pixel cross the bus)."""
+        idx = None
+        if indices is not None:
+            self.idx_in.copy_(indices.reshape(-1), non_blocking=True)
+            idx = self.idx_in
+        ops.sample_batch(self.ds_data, self.ds_gamma, self.ds_mask, idx, self.shape, seed, step, self.coords,
+                         self.coord_idx, self.img, self.gamma_w if self.ds_gamma is not None else None,
+                         self.mask_w if self.ds_mask is not None else None)
+        if self.opt.use_random_gamma and gamma is not None:
+            self.gamma.copy_(torch.as_tensor(gamma, dtype=torch.float32).reshape(1), non_blocking=True)
+
     def h2d_bytes(self):
         n = self.B * (3 * 4 + 8 + 3 * 4)
         if self.opt.use_random_gamma:
@@ -272,13 +294,24 @@ class FusedTrainStep:
             from .dist import allreduce_flat_gradients
             allreduce_flat_gradients(self.params.grad, self.pg)
 
-    def optimizer_step(self, lr=None, reduce=True):
-        """Gradient all-reduce (when distributed) + fused Adam + operand re-pack."""
+    def optimizer_step(self, lr=None, reduce=True, lr_groups=None):
+        """Gradient all-reduce (when distributed) + fused Adam + operand re-pack.
+
+        lr_groups: optional {slot: lr or None}; None freezes the slot (the post-freeze optimizer of
+        training.py:300-313 drops tm / exp / focal and gives the blur net its own rate).  Default: one launch
+        over the whole flat buffer at `lr` (all groups identical, training.py:51)."""
         P = self.params
         if reduce:
             self.reduce_gradients()
         ops.adam_tick(P.adam_state)
-        ops.adam_step(P.flat, P.grad, P.exp_avg, P.exp_avg_sq, P.adam_state, self.opt.lr if lr is None else lr)
+        if lr_groups is None:
+            ops.adam_step(P.flat, P.grad, P.exp_avg, P.exp_avg_sq, P.adam_state, self.opt.lr if lr is None else lr)
+        else:
+            for slot, (lo, hi) in P.slot_ranges.items():
+                g_lr = lr_groups.get(slot, self.opt.lr)
+                if g_lr is None or hi == lo:
+                    continue
+                ops.adam_step(P.flat[lo:hi], P.grad[lo:hi], P.exp_avg[lo:hi], P.exp_avg_sq[lo:hi], P.adam_state, g_lr)
         self.repack()
 
     def losses(self):

@@ -1,0 +1,65 @@
+"""`train()` with the reference's signature (training.py:18) driving the fused CUDA step.
+
+Mirrors the cadence of the reference loop: per-step pipeline (training.py:95-271) = FusedTrainStep; the freeze
+schedule at `opt.start_freeze_tm` (training.py:300-314: a FRESH Adam with lr 1e-5, blur lr 1e-6, tm / exp /
+focal no longer updated, mask weights switched on); checkpoints under the reference's keys every
+`epochs_til_ckpt` epochs and at the end (training.py:86-87, 317).  What it does not reproduce: TensorBoard
+writes and the summary renderer's image dumps (offline visualisation) -- `summary_fn`
+is still called at the reference's cadence if given.  Losses stay on the device; `.item()` only happens when a
+step is logged (the reference syncs once per loss per step, training.py:256-267).
+"""
+import os
+
+import torch
+
+from . import utils as nutils
+from .step import FusedTrainStep, StepOptions
+
+
+def lr_groups_after_freeze():
+    """training.py:300-313: atlas / uv / alpha at 1e-5, blur at 1e-6, tm / exp / focal frozen."""
+    return {"atlas_b": 1e-5, "uv_b": 1e-5, "uv_f": 1e-5, "atlas_f": 1e-5, "alpha": 1e-5, "blur": 1e-6,
+            "tm": None, "exp": None, "focal": None, "noise": None, "depth": None}
+
+
+def train(models, train_dataloader, model_dir, loss_fn=None, summary_fn=None, val_dataloader=None,
+          loss_schedules=None, video_shape=None, opt=None, log_every=None, process_group=None):
+    if loss_schedules is not None or val_dataloader is not None:
+        raise NotImplementedError("loss_schedules / val_dataloader are unused by every NeuCam config")
+    epochs = opt.num_epochs
+    steps_til_summary = getattr(opt, "steps_til_summary", 1000)
+    epochs_til_ckpt = getattr(opt, "epochs_til_ckpt", 1000)
+    start_freeze = getattr(opt, "start_freeze_tm", -1)
+    log_every = steps_til_summary if log_every is None else log_every
+
+    os.makedirs(os.path.join(model_dir, "checkpoints"), exist_ok=True)
+    first_in, _ = next(iter(train_dataloader))
+    B = first_in["coords"].reshape(-1, 3).shape[0]
+    step = FusedTrainStep(models, video_shape, StepOptions.from_opt(opt), B, process_group=process_group)
+
+    use_mask = False
+    lr_groups = None
+    total_steps = 0
+    history = []
+    for epoch in range(epochs):
+        if epoch and not epoch % epochs_til_ckpt:
+            nutils.save_model(models, os.path.join(model_dir, "checkpoints", "model_epoch_%04d.pth" % epoch))
+        for model_input, gt in train_dataloader:
+            gamma = (torch.rand(1) * 100 + 1.0) if step.opt.use_random_gamma else None     # training.py:181
+            step.load_batch(model_input, gt, gamma)
+            step.forward_backward(use_mask=use_mask)
+            step.optimizer_step(lr_groups=lr_groups)
+            if not total_steps % log_every:
+                losses = {k: float(v) for k, v in step.losses().items()}
+                history.append((total_steps, losses))
+                if not total_steps % steps_til_summary:
+                    nutils.save_model(models, os.path.join(model_dir, "checkpoints", "model_current.pth"))
+                    if summary_fn is not None:
+                        summary_fn(model_dir, models, gt, None, None, total_steps, opt)
+            if total_steps == start_freeze:
+                step.params.reset_optimizer()
+                lr_groups = lr_groups_after_freeze()
+                use_mask = True
+            total_steps += 1
+    nutils.save_model(models, os.path.join(model_dir, "checkpoints", "model_final.pth"))
+    return history
