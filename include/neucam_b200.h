@@ -71,7 +71,7 @@ int neucam_debug_set_chain_flags(int flags);
 /* neucam_sine_mlp_bwd:  given dy[Q,out_dim] computes duv[Q,2], ACCUMULATES the first layer's
  *   gradients into dw0 [512,2] / db0 [512] and writes dz16 = fp16 [3,Q,512] holding
  *   (*scale_dev) * dL/dz_l for l = 1..3 (consumed by neucam_sine_mlp_wgrad).
- *   wT_hid16 : fp16 [3*512,512], the hidden weights stacked and TRANSPOSED ([in,out] row-major).
+ *   wT_hid16 : fp16 [3*512,512], 30 * the hidden weights stacked and TRANSPOSED ([in,out] row-major).
  *   scale_dev: device pointer to one float, a power-of-two loss scale chosen so that the scaled
  *              gradients sit in fp16's normal range (neucam_b200/step.py derives it from max|dy|).
  */
@@ -149,7 +149,8 @@ int neucam_adam_step(float* p, const float* g, float* m, float* v, int64_t n, co
                      float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* Re-emits the fp16 operand copies of the three atlas hidden matrices (fp32 [512,512] each):
- * w16 = [3*512,512] row-major [out,in]; wT16 = [3*512,512] transposed ([in,out]). */
+ * w16 = [3*512,512] row-major [out,in]; wT16 = [3*512,512] = 30 * W transposed ([in,out]; the dgrad chain's
+ * 30*cos(.) factor is folded into the operand). */
 int neucam_pack_hidden_weights(const float* w1, const float* w2, const float* w3, void* w16, void* wT16,
                                void* stream);
 

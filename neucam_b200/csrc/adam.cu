@@ -56,7 +56,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
-// w: fp32 [512,512] row-major ([out,in]).  Writes fp16 copies: plain and transposed (32x32 smem tiles).
+// w: fp32 [512,512] row-major ([out,in]).  Writes fp16 copies: plain, and transposed * 30 (32x32 smem tiles).
 __global__ void __launch_bounds__(256)
 pack_hidden_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
                    __half* __restrict__ w16, __half* __restrict__ wT16) {
@@ -77,7 +77,8 @@ pack_hidden_kernel(const float* __restrict__ w1, const float* __restrict__ w2, c
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = c0 + ty + 8 * j;
-    oT[(size_t)c * 512 + r0 + tx] = __float2half_rn(tile[tx][ty + 8 * j]);
+    // the transposed copy feeds the dgrad chain, whose epilogue multiplies by 30 cos(.): the 30 is folded in here
+    oT[(size_t)c * 512 + r0 + tx] = __float2half_rn(30.f * tile[tx][ty + 8 * j]);
   }
 }
 

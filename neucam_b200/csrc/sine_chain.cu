@@ -19,7 +19,7 @@
 //     cos(30 z_l) with one MUFU (tile-blocked layout so the per-row threads store/load coalesced).
 //   backward (autograd of the same, training.py:270):
 //       dz3 = (dy W4) * 30 cos(30 z3)          SIMT prologue
-//       dz_{l-1} = (dz_l W_l) * 30 cos(30 z_{l-1})   l = 3..1, tcgen05 + epilogue
+//       dz_{l-1} = (dz_l 30 W_l) * cos(30 z_{l-1})   l = 3..1, tcgen05 + epilogue (30 folded into the fp16 W^T)
 //       duv = dz0 W0                           SIMT, fused in the last epilogue
 //       dW0 = dz0^T uv, db0 = sum dz0          column pass over the dz0 tile while it is still in smem
 //     dz1..dz3 are TMA-stored for the weight-gradient kernel (wgrad.cu).  All dz carry a power-of-two
@@ -559,12 +559,12 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                     const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
                     c0v = __cosf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
                     c1v = __cosf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
-                    const float z0 = __uint_as_float(r[i]) * 30.f * c0v;
-                    const float z1 = __uint_as_float(r[i + 1]) * 30.f * c1v;
+                    const float z0 = __uint_as_float(r[i]) * c0v;   // the operand W^T carries the factor 30
+                    const float z1 = __uint_as_float(r[i + 1]) * c1v;
                     acc0 = fmaf(z0, q0.x, fmaf(z1, q1.x, acc0));
                     acc1 = fmaf(z0, q0.y, fmaf(z1, q1.y, acc1));
                   }
-                  w[q * 4 + jj] = pack_h2_sat(__uint_as_float(r[i]) * 30.f * c0v, __uint_as_float(r[i + 1]) * 30.f * c1v);
+                  w[q * 4 + jj] = pack_h2_sat(__uint_as_float(r[i]) * c0v, __uint_as_float(r[i + 1]) * c1v);
                 }
               }
             }

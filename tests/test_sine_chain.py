@@ -38,7 +38,7 @@ def to_dev(sd):
     w4 = sd["net.net.4.0.weight"].cuda().contiguous()
     b4 = sd["net.net.4.0.bias"].cuda().contiguous()
     w16 = wh.half().reshape(3 * 512, 512).contiguous()
-    wT16 = wh.transpose(1, 2).half().reshape(3 * 512, 512).contiguous()
+    wT16 = (30.0 * wh.transpose(1, 2)).half().reshape(3 * 512, 512).contiguous()
     return w0, b0, w16, wT16, bh, w4, b4
 
 

@@ -18,7 +18,7 @@ def main():
     w4 = ((torch.rand(3, 512, generator=g) * 2 - 1) * math.sqrt(6 / 512) / 30).to(dev)
     b4 = torch.zeros(3, device=dev)
     w16 = wh.half().reshape(1536, 512).contiguous()
-    wT16 = wh.transpose(1, 2).half().reshape(1536, 512).contiguous()
+    wT16 = (30.0 * wh.transpose(1, 2)).half().reshape(1536, 512).contiguous()
     uv = (torch.rand(Q, 2, device=dev) * 2 - 1)
     dy = torch.randn(Q, 3, device=dev) * 1e-5
     act, cos, dz = ops.alloc_chain_workspace(Q, dev)
