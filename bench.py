@@ -249,7 +249,7 @@ def run_ours(args, cfg):
             "sine_chain_fwd": lambda: ops.sine_mlp_fwd(uv, step.aw[0].data, step.ab[0].data, step.w16, step.b_hid,
                                                        step.aw[4].data, step.ab[4].data, y=step.y.view(-1, 3),
                                                        act16=step.act16, phase16=step.phase16),
-            "sine_chain_bwd": lambda: ops.sine_mlp_bwd(uv, step.aw[0].data, step.ab[0].data, step.wT16, step.aw[4].data,
+            "sine_chain_bwd": lambda: ops.sine_mlp_bwd(uv, step.aw[0].data, step.ab[0].data, step.wT16, step.w4T16,
                                                        dyf, step.phase16, step.scale, step.dz16, step.aw[0].grad,
                                                        step.ab[0].grad, duv=step.duv.view(-1, 2)),
             "hidden_wgrad": lambda: ops.sine_mlp_wgrad(step.dz16, step.act16, step.scale,

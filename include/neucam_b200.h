@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NEUCAM_ABI_VERSION 3
+#define NEUCAM_ABI_VERSION 4
 
 #define NEUCAM_ERR_BAD_ARG (-1)
 #define NEUCAM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point unavailable */
@@ -72,11 +72,13 @@ int neucam_debug_set_chain_flags(int flags);
  *   gradients into dw0 [512,2] / db0 [512] and writes dz16 = fp16 [3,Q,512] holding
  *   (*scale_dev) * dL/dz_l for l = 1..3 (consumed by neucam_sine_mlp_wgrad).
  *   wT_hid16 : fp16 [3*512,512], 30 * the hidden weights stacked and TRANSPOSED ([in,out] row-major).
+ *   w4T16    : fp16 [512,64], the head weights transposed and zero-padded (neucam_pack_head_weights): the head
+ *              dgrad dy W4 runs as one K = 16 tensor-core step.
  *   scale_dev: device pointer to one float, a power-of-two loss scale chosen so that the scaled
  *              gradients sit in fp16's normal range (neucam_b200/step.py derives it from max|dy|).
  */
 int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0, const void* wT_hid16,
-                        const float* w4, int out_dim, const float* dy, const void* phase16,
+                        const void* w4T16, int out_dim, const float* dy, const void* phase16,
                         const float* scale_dev, void* dz16, float* duv, float* dw0, float* db0, void* stream);
 
 /* neucam_sine_mlp_wgrad: ACCUMULATES dW_l [512,512] += dz_l^T a_l / scale and db_l [512] += colsum(dz_l) / scale
@@ -153,6 +155,8 @@ int neucam_adam_step(float* p, const float* g, float* m, float* v, int64_t n, co
  * 30*cos(.) factor is folded into the operand). */
 int neucam_pack_hidden_weights(const float* w1, const float* w2, const float* w3, void* w16, void* wT16,
                                void* stream);
+/* w4 fp32 [out_dim,512] -> w4T16 fp16 [512,64] (row j = W4[0..out_dim-1][j], zero padded). */
+int neucam_pack_head_weights(const float* w4, int out_dim, void* w4T16, void* stream);
 
 #ifdef __cplusplus
 }

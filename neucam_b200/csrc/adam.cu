@@ -82,7 +82,23 @@ pack_hidden_kernel(const float* __restrict__ w1, const float* __restrict__ w2, c
   }
 }
 
+// head weights W4 [out_dim,512] -> fp16 [512,64]: row j = (W4[0][j], .., W4[out_dim-1][j], 0, ...): the K-major,
+// zero-padded B operand of the backward's head dgrad (one K = 16 tensor-core step)
+__global__ void pack_head_kernel(const float* __restrict__ w4, int out_dim, __half* __restrict__ w4t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 512 * 64
+  if (i >= 512 * 64) return;
+  const int j = i >> 6, c = i & 63;
+  w4t[i] = __float2half_rn(c < out_dim ? w4[c * 512 + j] : 0.f);
+}
+
 }  // namespace
+
+extern "C" int neucam_pack_head_weights(const float* w4, int out_dim, void* w4T16, void* stream) {
+  NC_CHECK_ARG(w4 && w4T16 && out_dim >= 1 && out_dim <= 4);
+  pack_head_kernel<<<128, 256, 0, (cudaStream_t)stream>>>(w4, out_dim, (__half*)w4T16);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int neucam_adam_tick(float* state, float beta1, float beta2, void* stream) {
   NC_CHECK_ARG(state != nullptr);

@@ -18,7 +18,7 @@
 //     of 30 z_l (l = 1..3) as 16-bit fixed point in revolutions, from which the backward regenerates
 //     cos(30 z_l) with one MUFU (tile-blocked layout so the per-row threads store/load coalesced).
 //   backward (autograd of the same, training.py:270):
-//       dz3 = (dy W4) * 30 cos(30 z3)          SIMT prologue
+//       dz3 = (dy W4) * 30 cos(30 z3)          tcgen05 (one K = 16 step on a zero-padded fp16 dy / W4^T pair) + epilogue
 //       dz_{l-1} = (dz_l 30 W_l) * cos(30 z_{l-1})   l = 3..1, tcgen05 + epilogue (30 folded into the fp16 W^T)
 //       duv = dz0 W0                           SIMT, fused in the last epilogue
 //       dW0 = dz0^T uv, db0 = sum dz0          column pass over the dz0 tile while it is still in smem
@@ -76,7 +76,9 @@ static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory li
 // mbarrier slots
 constexpr uint32_t BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_KFREE = 12, BAR_AREADY = 20, BAR_STORED = 28,
                    BAR_PEER = 36,   // leader only: the peer CTA's operand k-block kb is ready
-                   BAR_AOUT = 44;   // k-block kb of the tile's LAST output (a4 / dz0) is written (store warp only)
+                   BAR_AOUT = 44,   // k-block kb of the tile's LAST output (a4 / dz0) is written (store warp only)
+                   BAR_DYR = 52,    // backward: the tile's scaled output-gradient operand (dy, K = 16) is written
+                   BAR_PEERDY = 53; // leader only: same, for the peer CTA
 // a_ready / peer count the MMA-visible operand events only (prologue + first two layers = 3 per tile): every
 // such event needs MMA progress on the previous one, so no waiter can be lapped by a full barrier phase.
 
@@ -109,7 +111,7 @@ struct ChainParams {
 // trace layout: [role 0=mma,1=epi half0,2=epi half1 | +3 for the peer CTA][tile 0..1][g 0..2][step 0..7][4 stamps]
 // (globaltimer so that the two SMs of the pair share a time base)
 __device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i, int g, int step, int k) {
-  if (tr != nullptr && blockIdx.x < 2 && tile_i < 2) {
+  if (tr != nullptr && blockIdx.x < 2 && tile_i < 2 && g >= 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     tr[((((role + 3 * (int)blockIdx.x) * 2 + tile_i) * 3 + g) * 8 + step) * 4 + k] = (long long)t;
@@ -119,6 +121,7 @@ __device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i,
 struct ChainMaps {
   CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T), box 64 x 128
   CUtensorMap act[4];    // forward: a1..a4 ; backward: dz3, dz2, dz1, (unused)   ([Q,512] fp16, box 64x128)
+  CUtensorMap w4t;       // backward: head weights transposed + zero-padded, fp16 [512, 64], box 64 x 128
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -184,10 +187,10 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   // ---- one-time setup -------------------------------------------------------------------------
   for (int j = tid; j < HID; j += NTHREADS) {
     s_p0[j] = make_float4(30.f * p.w0[2 * j], 30.f * p.w0[2 * j + 1], 30.f * p.b0[j], 0.f);
-    float w4v[4];
-    for (int c = 0; c < 4; ++c) w4v[c] = (c < p.out_dim) ? p.w4[c * HID + j] : 0.f;
-    s_w4[j] = make_float4(w4v[0], w4v[1], w4v[2], w4v[3]);
     if (!BWD) {
+      float w4v[4];
+      for (int c = 0; c < 4; ++c) w4v[c] = (c < p.out_dim) ? p.w4[c * HID + j] : 0.f;
+      s_w4[j] = make_float4(w4v[0], w4v[1], w4v[2], w4v[3]);
       for (int l = 0; l < 3; ++l) {
         const float b30 = 30.f * p.b_hid[l * HID + j];
         s_b30[l * HID + j] = b30;
@@ -207,6 +210,8 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       mbar_init(bar(BAR_PEER + k), 1);
       mbar_init(bar(BAR_AOUT + k), 256);
     }
+    mbar_init(bar(BAR_DYR), 128);
+    mbar_init(bar(BAR_PEERDY), 1);
     mbar_fence_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -235,6 +240,18 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       uint32_t full_bar[NSTAGE];   // the leader's w_full barriers (shared::cluster addresses)
       for (uint32_t k = 0; k < NSTAGE; ++k) full_bar[k] = mapa_shared(bar(BAR_WFULL + k), 0);
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
+        if (BWD) {
+          // head dgrad dh4 = dy W4 runs on the tensor cores too: one K = 16 step per 256-column half
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar(BAR_WEMPTY + s), ph ^ 1);
+            if (lane == 0) {
+              if (leader) mbar_arrive_expect_tx(bar(BAR_WFULL + s), 2 * STAGE_BYTES);
+              tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w4t, full_bar[s], 0, h * 256 + (int)crank * 128);
+            }
+            __syncwarp();
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+        }
         for (int g = 0; g < 3; ++g) {
           const int wl = BWD ? (2 - g) : g;
           for (int h = 0; h < 2; ++h) {
@@ -264,7 +281,31 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       uint32_t s = 0, ph = 0, ev = 0;   // ev = operand-write event counter (a_ready parity)
       long long* trm = (lane == 0) ? p.trace : nullptr;
       int tile_i = 0;
+      uint32_t dyp = 0;   // parity of the dy-operand barriers (one phase per tile)
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
+        if (BWD) {
+          mbar_wait(bar(BAR_DYR), dyp);
+          mbar_wait(bar(BAR_PEERDY), dyp);
+          dyp ^= 1;
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar(BAR_WFULL + s), ph);
+            tc_fence_after_sync();
+            if (lane == 0) {
+              // A = the dy operand in k-block slot 7 (columns 0..15), B = this half of W4^T: a single K = 16 MMA
+              umma_f16_ss_2cta(tmem_base + h * 256, make_sdesc_sw128(base + OFF_A + 7 * A_BLOCK_BYTES, 0, 1024),
+                               make_sdesc_sw128(base + OFF_W + s * STAGE_BYTES, 0, 1024), idesc, 0u);
+              umma_commit_2cta(bar(BAR_WEMPTY + s), PAIR_MASK);
+              if (h == 1) {
+                umma_commit_2cta(bar(BAR_KFREE + 0), PAIR_MASK);
+                umma_commit_2cta(bar(BAR_KFREE + 1), PAIR_MASK);
+              }
+              umma_commit_2cta(bar(BAR_ACC + 2 * h), PAIR_MASK);
+              umma_commit_2cta(bar(BAR_ACC + 2 * h + 1), PAIR_MASK);
+            }
+            __syncwarp();
+            if (++s == NSTAGE) { s = 0; ph ^= 1; }
+          }
+        }
         for (int g = 0; g < 3; ++g) {
           for (int h = 0; h < 2; ++h) {
             trace_stamp(trm, 0, tile_i, g, 2 * h, 0);
@@ -321,7 +362,15 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       for (uint32_t k = 0; k < 8; ++k) peer_bar[k] = mapa_shared(bar(BAR_PEER + k), 0);
       long long* trm = (lane == 0) ? p.trace : nullptr;
       int tile_i = 0;
+      const uint32_t peer_dy = mapa_shared(bar(BAR_PEERDY), 0);
+      uint32_t dyp = 0;
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
+        if (BWD) {
+          mbar_wait(bar(BAR_DYR), dyp);
+          dyp ^= 1;
+          if (lane == 0) mbar_arrive_cluster(peer_dy);
+          __syncwarp();
+        }
         for (int e3 = 0; e3 < 3; ++e3) {
           for (int kb = 0; kb < 8; ++kb) {
             mbar_wait(bar(BAR_AREADY + kb), ev & 1);
@@ -402,20 +451,11 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       const size_t ph_row_off = ((size_t)tile * 64 * TILE_M + row) * 8;   // + chunk8 * 128 * 8
       const bool store_ph = tile_ok && p.store_act != 0;
 
-      // ---------------- prologue: first operand tile ----------------
+      // ---------------- prologue ----------------
+      // forward: first operand tile a1 = sin(30 (uv W0^T + b0)) (SIMT, K = 2)
+      // backward: only the K = 16 operand of the head dgrad (dy scaled by 30 * loss scale, fp16); dz3 is then
+      //           produced by the regular chunked epilogue of a tensor-core "layer -1"
       trace_stamp(tr, role, tile_i, 0, 7, 0);
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-      if (BWD) {
-        if (sub == 0) s_uv[row] = make_float2(u, v);
-        if (valid) {
-          const float* dyr = p.dy + (size_t)grow * p.out_dim;
-          const float sc = gscale * 30.f;
-          d0 = dyr[0] * sc;
-          d1 = dyr[1] * sc;
-          d2 = dyr[2] * sc;
-          if (p.out_dim > 3) d3 = dyr[3] * sc;
-        }
-      }
       if (!BWD) {
 #pragma unroll 1
         for (uint32_t c = 0; c < 4; ++c) {
@@ -432,54 +472,33 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           fence_proxy_async_smem();
           mbar_arrive(bar(BAR_AREADY + kb));
         }
-      } else {
-        // the layer-3 phases come from HBM: keep the next chunk's 4 loads in flight while this one is computed
-        const uint16_t* ph3 = p.phase + 2 * ph_layer_stride + ph_row_off + (size_t)((sub * 32) >> 3) * (TILE_M * 8);
-        uint4 pvn[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          pvn[q] = tile_ok ? *reinterpret_cast<const uint4*>(ph3 + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (uint32_t c = 0; c < 4; ++c) {
-          const uint32_t col = c * 128 + sub * 32;
-          const uint32_t kb = col >> 6;
-          uint4 pv[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) pv[q] = pvn[q];
-          if (c < 3) {
-            const uint16_t* nxt = ph3 + (size_t)((c + 1) * 16) * (TILE_M * 8);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              pvn[q] = tile_ok ? *reinterpret_cast<const uint4*>(nxt + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
-          }
-          uint32_t w[16];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = col + q * 8 + jj * 2;
-              const float4 wa = s_w4[j], wb = s_w4[j + 1];
-              const float g0 = fmaf(d0, wa.x, fmaf(d1, wa.y, fmaf(d2, wa.z, d3 * wa.w)));
-              const float g1 = fmaf(d0, wb.x, fmaf(d1, wb.y, fmaf(d2, wb.z, d3 * wb.w)));
-              w[q * 4 + jj] = pack_h2_sat(g0 * cos_of_phase(pw[jj] & 0xFFFFu), g1 * cos_of_phase(pw[jj] >> 16));
-            }
-          }
-          if (ev > 0) mbar_wait(bar(BAR_STORED + kb), (ev - 1) & 1);
-          write_a_half_row(a_base, kb, row, qb, w);
-          fence_proxy_async_smem();
-          mbar_arrive(bar(BAR_AREADY + kb));
+        ++ev;
+      } else if (sub == 0) {
+        s_uv[row] = make_float2(u, v);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        if (valid) {
+          const float* dyr = p.dy + (size_t)grow * p.out_dim;
+          const float sc = gscale * 30.f;
+          d0 = dyr[0] * sc;
+          d1 = dyr[1] * sc;
+          d2 = dyr[2] * sc;
+          if (p.out_dim > 3) d3 = dyr[3] * sc;
         }
+        // k-block slot 7 is free here: the previous tile's column pass over dz0 ended with epi_bar_sync
+        const uint32_t blk7 = a_base + 7 * A_BLOCK_BYTES;
+        st_shared_v4(blk7 + sw128_offset(row, 0), pack_h2_sat(d0, d1), pack_h2_sat(d2, d3), 0u, 0u);
+        st_shared_v4(blk7 + sw128_offset(row, 1), 0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+        mbar_arrive(bar(BAR_DYR));
       }
-      ++ev;
       trace_stamp(tr, role, tile_i, 0, 7, 1);
 
-      // ---------------- three tensor-core layers ----------------
+      // ---------------- tensor-core layers (backward: g = -1 is the head dgrad) ----------------
 #pragma unroll 1
-      for (int g = 0; g < 3; ++g) {
+      for (int g = BWD ? -1 : 0; g < 3; ++g) {
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // head (fwd) / duv (bwd) partials
-        const float* b30 = s_b30 + g * HID;
-        uint16_t* ph_out = p.phase + (size_t)g * ph_layer_stride + ph_row_off;
+        const float* b30 = s_b30 + (g < 0 ? 0 : g) * HID;
+        uint16_t* ph_out = p.phase + (size_t)(g < 0 ? 0 : g) * ph_layer_stride + ph_row_off;
         const uint16_t* ph_in = p.phase + (size_t)(g < 2 ? 1 - g : 0) * ph_layer_stride + ph_row_off;
 
         // order: A(0) A(1) B(0) B(1) A(2) A(3)   (A = drain + math, B = parked result -> operand).
@@ -654,9 +673,16 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   if (warp == WARP_ALLOC) tmem_dealloc_2cta(tmem_base, 512);
 }
 
-int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, bool need_act) {
+int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, bool need_act,
+               const void* w4t16 = nullptr) {
   int rc = nchost::make_tmap_16b(&m->w, w16, 3 * HID, HID, HID, 128, 64);
   if (rc) return rc;
+  if (w4t16 != nullptr) {
+    rc = nchost::make_tmap_16b(&m->w4t, w4t16, HID, 64, 64, 128, 64);
+    if (rc) return rc;
+  } else {
+    m->w4t = m->w;   // never dereferenced (forward)
+  }
   for (int i = 0; i < 4; ++i) {
     if (!need_act) {
       m->act[i] = m->w;   // never dereferenced
@@ -728,10 +754,10 @@ extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, 
 }
 
 extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0,
-                                   const void* wT_hid16, const float* w4, int out_dim, const float* dy,
+                                   const void* wT_hid16, const void* w4T16, int out_dim, const float* dy,
                                    const void* phase16, const float* scale_dev, void* dz16, float* duv,
                                    float* dw0, float* db0, void* stream) {
-  NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4 && dy && phase16 && scale_dev && dz16 && duv && dw0 && db0);
+  NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4T16 && dy && phase16 && scale_dev && dz16 && duv && dw0 && db0);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - TILE_M);
   NC_CHECK_ARG(out_dim == 3 || out_dim == 4);
   ChainParams p{};
@@ -739,7 +765,7 @@ extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, 
   p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
   p.out_dim = out_dim;
   p.store_act = 1;
-  p.uv = uv; p.w0 = w0; p.b0 = b0; p.w4 = w4;
+  p.uv = uv; p.w0 = w0; p.b0 = b0; p.w4 = nullptr;
   p.phase = reinterpret_cast<uint16_t*>(const_cast<void*>(phase16));
   p.dy = dy; p.duv = duv; p.scale = scale_dev; p.dw0 = dw0; p.db0 = db0;
   p.trace = g_trace;
@@ -751,7 +777,7 @@ extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, 
   void* act[4];
   for (int i = 0; i < 3; ++i) act[i] = (void*)((__half*)dz16 + (size_t)(2 - i) * Q * HID);
   act[3] = act[2];
-  int rc = build_maps(&maps, wT_hid16, act, Q, true);
+  int rc = build_maps(&maps, wT_hid16, act, Q, true, w4T16);
   if (rc) return rc;
   return launch<true>(maps, p, (cudaStream_t)stream);
 }

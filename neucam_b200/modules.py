@@ -134,7 +134,9 @@ class _SineMLPFunction(torch.autograd.Function):
         if need_grad:
             act, cos, dz = ops.alloc_chain_workspace(Q, dev)
             y = ops.sine_mlp_fwd(uvc, w0c, b0c, w16, b_hid, w4c, b4c, act16=act, phase16=cos)
-            ctx.save_for_backward(uvc, w0c, b0c, w4c, wT16, act, cos)
+            w4T16 = torch.empty((HID, 64), dtype=torch.float16, device=dev)
+            ops.pack_head_weights(w4c, w4T16)
+            ctx.save_for_backward(uvc, w0c, b0c, w4c, wT16, act, cos, w4T16)
             ctx.dz = dz
         else:
             y = ops.sine_mlp_fwd(uvc, w0c, b0c, w16, b_hid, w4c, b4c)
@@ -142,7 +144,7 @@ class _SineMLPFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        uv, w0, b0, w4, wT16, act, cos = ctx.saved_tensors
+        uv, w0, b0, w4, wT16, act, cos, w4T16 = ctx.saved_tensors
         dz = ctx.dz
         dev = uv.device
         dy = dy.contiguous().float()
@@ -152,7 +154,7 @@ class _SineMLPFunction(torch.autograd.Function):
         dws = [torch.zeros((HID, HID), dtype=torch.float32, device=dev) for _ in range(3)]
         dbs = [torch.zeros((HID,), dtype=torch.float32, device=dev) for _ in range(3)]
         dw4 = torch.zeros_like(w4)
-        duv = ops.sine_mlp_bwd(uv, w0, b0, wT16, w4, dy, cos, scale, dz, dw0, db0)
+        duv = ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, cos, scale, dz, dw0, db0)
         ops.sine_mlp_wgrad(dz, act, scale, dws, dbs)
         ops.sine_mlp_head_wgrad(act, dy, dw4)
         db4 = dy.sum(0)

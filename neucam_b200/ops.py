@@ -43,15 +43,23 @@ def sine_mlp_fwd(uv, w0, b0, w_hid16, b_hid, w4, b4, y=None, act16=None, phase16
     return y
 
 
-def sine_mlp_bwd(uv, w0, b0, wT_hid16, w4, dy, phase16, scale, dz16, dw0, db0, duv=None):
-    """dy [Q,out_dim] -> duv [Q,2]; accumulates dW0/db0; fills dz16 [3,Q,512] with scale * dL/dz_l, l=1..3."""
-    _chk_cuda(uv, w0, b0, wT_hid16, w4, dy, phase16, scale, dz16, duv, dw0, db0)
+def pack_head_weights(w4, w4T16):
+    """fp32 [out_dim,512] -> fp16 [512,64] zero-padded transposed operand of the head dgrad."""
+    _chk_cuda(w4, w4T16)
+    rc = _lib.lib().neucam_pack_head_weights(_lib.ptr(w4), w4.shape[0], _lib.ptr(w4T16), _lib.cur_stream())
+    _lib.check(rc, "neucam_pack_head_weights")
+
+
+def sine_mlp_bwd(uv, w0, b0, wT_hid16, w4T16, dy, phase16, scale, dz16, dw0, db0, duv=None):
+    """dy [Q,out_dim] -> duv [Q,2]; accumulates dW0/db0; fills dz16 [3,Q,512] with scale * dL/dz_l, l=1..3.
+    w4T16: fp16 [512,64] from pack_head_weights."""
+    _chk_cuda(uv, w0, b0, wT_hid16, w4T16, dy, phase16, scale, dz16, duv, dw0, db0)
     Q = uv.shape[0]
     if duv is None:
         duv = torch.empty((Q, 2), dtype=torch.float32, device=uv.device)
     rc = _lib.lib().neucam_sine_mlp_bwd(
-        _lib.ptr(uv), ctypes.c_int64(Q), _lib.ptr(w0), _lib.ptr(b0), _lib.ptr(wT_hid16), _lib.ptr(w4),
-        w4.shape[0], _lib.ptr(dy), _lib.ptr(phase16), _lib.ptr(scale), _lib.ptr(dz16), _lib.ptr(duv),
+        _lib.ptr(uv), ctypes.c_int64(Q), _lib.ptr(w0), _lib.ptr(b0), _lib.ptr(wT_hid16), _lib.ptr(w4T16),
+        dy.shape[1], _lib.ptr(dy), _lib.ptr(phase16), _lib.ptr(scale), _lib.ptr(dz16), _lib.ptr(duv),
         _lib.ptr(dw0), _lib.ptr(db0), _lib.cur_stream())
     _lib.check(rc, "neucam_sine_mlp_bwd")
     return duv

@@ -170,6 +170,7 @@ class FusedTrainStep:
         self.act16, self.phase16, self.dz16 = ops.alloc_chain_workspace(Q, dev)
         self.w16 = torch.empty(3 * ops.HID, ops.HID, dtype=torch.float16, device=dev)
         self.wT16 = torch.empty(3 * ops.HID, ops.HID, dtype=torch.float16, device=dev)
+        self.w4T16 = torch.empty(ops.HID, 64, dtype=torch.float16, device=dev)
         # scalars: sums[0..3] | absmax bits | scale
         self.scalars = torch.zeros(8, device=dev)
         self.sums = self.scalars[0:4]
@@ -206,6 +207,7 @@ class FusedTrainStep:
     def repack(self):
         """fp16 tensor-core operand copies of the atlas hidden weights (+ packed hidden biases)."""
         ops.pack_hidden_weights(self.aw[1].data, self.aw[2].data, self.aw[3].data, self.w16, self.wT16)
+        ops.pack_head_weights(self.aw[4].data, self.w4T16)
         for i in range(3):
             self.b_hid[i].copy_(self.ab[i + 1].data)
 
@@ -272,7 +274,7 @@ class FusedTrainStep:
                          3 * self.global_pixels, self.dy, self.dkw if self.has_blur else None, self.exps.grad,
                          self.ab[4].grad, self.sums, self.absmax_bits.view(torch.int32), self.scale)
         dyf = self.dy.view(-1, self.out_dim)
-        ops.sine_mlp_bwd(uv, self.aw[0].data, self.ab[0].data, self.wT16, self.aw[4].data, dyf, self.phase16, self.scale,
+        ops.sine_mlp_bwd(uv, self.aw[0].data, self.ab[0].data, self.wT16, self.w4T16, dyf, self.phase16, self.scale,
                          self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2))
         ops.sine_mlp_wgrad(self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
                            [self.ab[i].grad for i in (1, 2, 3)])

@@ -96,7 +96,9 @@ def test_backward_parity(Q, gain, out_dim):
     dbs = [torch.zeros(512, device="cuda") for _ in range(3)]
     dw4 = torch.zeros(out_dim, 512, device="cuda")
     dyc = dy.cuda()
-    duv = ops.sine_mlp_bwd(uv.cuda(), w0, b0, wT16, w4, dyc, cos, scale, dz, dw0, db0)
+    w4T16 = torch.empty(512, 64, dtype=torch.float16, device="cuda")
+    ops.pack_head_weights(w4, w4T16)
+    duv = ops.sine_mlp_bwd(uv.cuda(), w0, b0, wT16, w4T16, dyc, cos, scale, dz, dw0, db0)
     ops.sine_mlp_wgrad(dz, act, scale, dws, dbs)
     ops.sine_mlp_head_wgrad(act, dyc, dw4)
     torch.cuda.synchronize()

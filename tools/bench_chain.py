@@ -19,6 +19,8 @@ def main():
     b4 = torch.zeros(3, device=dev)
     w16 = wh.half().reshape(1536, 512).contiguous()
     wT16 = (30.0 * wh.transpose(1, 2)).half().reshape(1536, 512).contiguous()
+    w4T16 = torch.empty(512, 64, dtype=torch.float16, device=dev)
+    ops.pack_head_weights(w4, w4T16)
     uv = (torch.rand(Q, 2, device=dev) * 2 - 1)
     dy = torch.randn(Q, 3, device=dev) * 1e-5
     act, cos, dz = ops.alloc_chain_workspace(Q, dev)
@@ -33,7 +35,7 @@ def main():
     fns = {
         "fwd(train)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, phase16=cos),
         "fwd(infer)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y),
-        "bwd": lambda: ops.sine_mlp_bwd(uv, w0, b0, wT16, w4, dy, cos, scale, dz, dw0, db0, duv=duv),
+        "bwd": lambda: ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, cos, scale, dz, dw0, db0, duv=duv),
         "wgrad": lambda: ops.sine_mlp_wgrad(dz, act, scale, dws, dbs),
         "head_wgrad": lambda: ops.sine_mlp_head_wgrad(act, dy, dw4),
     }

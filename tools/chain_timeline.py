@@ -15,6 +15,8 @@ def run(bwd, Q=148 * 128 * 4):
     b4 = torch.zeros(3, device=dev)
     w16 = wh.half().reshape(1536, 512).contiguous()
     wT16 = (30.0 * wh.transpose(1, 2)).half().reshape(1536, 512).contiguous()
+    w4T16 = torch.empty(512, 64, dtype=torch.float16, device=dev)
+    ops.pack_head_weights(w4, w4T16)
     uv = (torch.rand(Q, 2, device=dev) * 2 - 1)
     dy = torch.randn(Q, 3, device=dev) * 1e-5
     act, ph, dz = ops.alloc_chain_workspace(Q, dev)
@@ -30,9 +32,9 @@ def run(bwd, Q=148 * 128 * 4):
         lib.neucam_debug_set_chain_trace(ctypes.c_void_p(trace.data_ptr()))
         ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, phase16=ph)
     else:
-        ops.sine_mlp_bwd(uv, w0, b0, wT16, w4, dy, ph, scale, dz, dw0, db0)
+        ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, ph, scale, dz, dw0, db0)
         lib.neucam_debug_set_chain_trace(ctypes.c_void_p(trace.data_ptr()))
-        ops.sine_mlp_bwd(uv, w0, b0, wT16, w4, dy, ph, scale, dz, dw0, db0)
+        ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, ph, scale, dz, dw0, db0)
     lib.neucam_debug_set_chain_trace(ctypes.c_void_p(0))
     torch.cuda.synchronize()
     t = trace.cpu().view(6, 2, 3, 8, 4)
