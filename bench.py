@@ -299,7 +299,7 @@ def run_ours(args, cfg):
             "frac_of_tensor_peak_whole_step": value / world * FLOP_PER_SAMPLE_FWD_BWD / 1e12 / peaks["bf16_tflops_sustained"],
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": step.h2d_bytes(), "d2h_bytes_per_step": 4},
-            "gpu_launches": 11 * args.steps,
+            "gpu_launches": 12 * args.steps,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": kern[dom]["tflops"], "peak": peak,
                          "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak, "traffic": traffic,

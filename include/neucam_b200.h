@@ -133,6 +133,13 @@ int neucam_psf_crf_loss(const float* y, const float* kout, const int64_t* coord_
                         uint32_t* dy_absmax_bits, float scale_target, float* scale_out, float* ldr_out,
                         void* stream);
 
+/* neucam_tm_min_slope: the VALUE-ONLY CRF gradient regulariser of training.py:248-252 (TonemapNet.forward with
+ *   output_grads=True, modules.py:249-251): min over M points of d mean(ldr)/d lnx for rad [M,3], expo [M,1].
+ *   *min_bits receives an order-preserving uint32 encoding of the float minimum (decode: b & 0x80000000 ?
+ *   b & 0x7fffffff : ~b).  grad_loss = relu(-min) * 1e6 contributes no gradient in the reference. */
+int neucam_tm_min_slope(const float* const* tm_params, const float* rad, const float* expo, int M,
+                        uint32_t* min_bits, void* stream);
+
 /* neucam_sample_batch (replaces dataio.Implicit3DWrapper.__getitem__, dataio.py:356-393,
  *   for a video resident in HBM): data [N*H*W,3] (= img*2-1), optional gamma_w_all / mask_w_all [N*H*W].
  *   Draws B pixel indices with replacement (Philox-4x32-10, key = seed, counter = (pixel, step)) or uses

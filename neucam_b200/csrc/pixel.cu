@@ -608,6 +608,69 @@ sample_batch_kernel(const float* __restrict__ data, const float* __restrict__ ga
   if (mask_w != nullptr && mask_w_all != nullptr) mask_w[p] = mask_w_all[idx];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// value-only gradient regulariser of the CRF (training.py:248-252 with modules.py:249-251): the minimum over M
+// random (radiance, exposure) points of d mean(ldr) / d lnx.  The reference computes it with autograd.grad and no
+// create_graph, so it is a constant w.r.t. the parameters: it only shows up in the logged loss.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tm_min_slope_kernel(TmParams tm, const float* __restrict__ rad, const float* __restrict__ expo, int M,
+                    unsigned int* __restrict__ min_bits /* order-preserving encoding of the float minimum */) {
+  __shared__ float s_u[3][TMW], s_a[3][TMW], s_v[3][TMW];
+  const int tid = threadIdx.x;
+  if (tid < TMW)
+    for (int c = 0; c < 3; ++c) {
+      s_u[c][tid] = tm.u[c][tid];
+      s_a[c][tid] = tm.a[c][tid];
+      s_v[c][tid] = tm.v[c][tid];
+    }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + tid;
+  float mn = 3.4e38f;
+  if (i < M) {
+    const float e = LN2 * expo[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = rad[3 * i + c] + e;
+      float o = tm.d[c][0], sl = 0.f;
+      for (int k = 0; k < TMW; ++k) {
+        const float pre = fmaf(s_u[c][k], x, s_a[c][k]);
+        if (pre > 0.f) {
+          o = fmaf(s_v[c][k], pre, o);
+          sl = fmaf(s_v[c][k], s_u[c][k], sl);
+        }
+      }
+      const float t = tanhf(o);
+      mn = fminf(mn, (1.f - t * t) * sl / (3.f * (float)M));   // d mean(ldr) / d lnx[i,c]
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((tid & 31) == 0) {
+    unsigned int b = __float_as_uint(mn);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // monotone float -> uint
+    atomicMin(min_bits, b);
+  }
+}
+
+}  // namespace
+
+extern "C" int neucam_tm_min_slope(const float* const* tm_params, const float* rad, const float* expo, int M,
+                                   uint32_t* min_bits, void* stream) {
+  NC_CHECK_ARG(tm_params && rad && expo && min_bits && M > 0);
+  TmParams tm{};
+  for (int c = 0; c < 3; ++c) {
+    tm.u[c] = tm_params[4 * c + 0]; tm.a[c] = tm_params[4 * c + 1];
+    tm.v[c] = tm_params[4 * c + 2]; tm.d[c] = tm_params[4 * c + 3];
+  }
+  NC_CHECK_CUDA(cudaMemsetAsync(min_bits, 0xFF, 4, (cudaStream_t)stream));
+  tm_min_slope_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tm, rad, expo, M, min_bits);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace {
 }  // namespace
 
 extern "C" int neucam_sample_batch(const float* data, const float* gamma_w_all, const float* mask_w_all,

@@ -168,3 +168,15 @@ def sample_batch(data, gamma_w_all, mask_w_all, idx_in, shape, seed, step, coord
         ctypes.c_uint64(seed), ctypes.c_uint64(step), _lib.ptr(coords), _lib.ptr(coord_idx), _lib.ptr(img),
         _lib.ptr(gamma_w), _lib.ptr(mask_w), _lib.cur_stream())
     _lib.check(rc, "neucam_sample_batch")
+
+
+def tm_min_slope(tm_params, rad, expo):
+    """min over points of d mean(ldr)/d lnx (value-only grad_loss input, training.py:248-252) -> device scalar."""
+    _chk_cuda(rad, expo, *tm_params)
+    bits = torch.empty(1, dtype=torch.int32, device=rad.device)
+    rc = _lib.lib().neucam_tm_min_slope(_ptr_array(tm_params), _lib.ptr(rad), _lib.ptr(expo), rad.shape[0],
+                                        _lib.ptr(bits), _lib.cur_stream())
+    _lib.check(rc, "neucam_tm_min_slope")
+    b = bits.to(torch.int64) & 0xFFFFFFFF
+    dec = torch.where((b & 0x80000000) != 0, b & 0x7FFFFFFF, (~b) & 0xFFFFFFFF)
+    return dec.to(torch.int32).view(torch.float32).reshape(())

@@ -316,6 +316,16 @@ class FusedTrainStep:
                 ops.adam_step(P.flat[lo:hi], P.grad[lo:hi], P.exp_avg[lo:hi], P.exp_avg_sq[lo:hi], P.adam_state, g_lr)
         self.repack()
 
+    def grad_loss(self, rand_radiance=None, rand_exposure=None):
+        """The reference's logged-only `grad_loss` = relu(-min slope of the CRF) * 1e6 over 10000 random points
+        (training.py:248-252; drawn on the host like the reference when not given).  No gradient flows from it."""
+        if rand_radiance is None:
+            rand_radiance = torch.rand(10000, 3) * 5
+            rand_exposure = torch.rand(10000, 1) * 6 - 3.0
+        slope = ops.tm_min_slope([p.data for p in self.tm_p], rand_radiance.to(self.device).contiguous(),
+                                 rand_exposure.to(self.device).contiguous())
+        return torch.relu(-slope) * 1e6
+
     def losses(self):
         """Device scalars: img_loss (this rank's share of the global mean), ue_loss, total."""
         img = self.sums[0] / float(3 * self.global_pixels)

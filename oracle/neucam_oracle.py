@@ -222,7 +222,10 @@ def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_int
         fake = fake + gamma_map(ldr, g) * gw
         real = real + gamma_map(batch["img"], g) * gw
     losses = OrderedDict()
-    losses["img_loss"] = ((fake - real) ** 2).mean()                                # loss_functions.py:12
+    if "weights" in batch and batch.get("use_mask", False):
+        losses["img_loss"] = (batch["weights"] * (fake - real) ** 2).mean()         # loss_functions.py:10 (after freeze)
+    else:
+        losses["img_loss"] = ((fake - real) ** 2).mean()                            # loss_functions.py:12
 
     z3, z1 = torch.zeros(1, 3, device=coords.device), torch.zeros(1, 1, device=coords.device)
     ue, _ = tonemap(state["tm"], z3, z1)

@@ -140,3 +140,36 @@ def test_cuda_graph_replay_equals_eager_steps():
     # atomics make gradient summation order non-deterministic; Adam's early steps are sign-like, so compare loosely
     assert (p0 - p1).abs().max().item() <= 2.5e-4
     assert rel(p1, p0) <= 1e-4
+
+
+def test_mask_weights_and_value_only_grad_loss():
+    """After start_freeze_tm the reference weights the squared error with per-pixel mask weights
+    (loss_functions.py:10); and it logs a value-only grad_loss (training.py:248-252)."""
+    shape, focal, B = (3, 30, 40), [-1.0, 0.0, 1.0], 800
+    models0 = harness.build_static_models(shape, focal, hidden=512, seed=4)
+    with torch.no_grad():
+        models0["tm"].layers_g[2].weight.mul_(-1.0)      # make some CRF slopes negative so grad_loss is non-zero
+    state = {s: {k: v.detach().clone() for k, v in m.state_dict().items()} for s, m in models0.items() if m is not None}
+    scene = harness.SyntheticScene(shape, focal, seed=5)
+    gen = torch.Generator().manual_seed(9)
+    inp, gt = scene.sample(B, gen)
+    inp["weights"] = torch.rand(1, B, 1, generator=gen) + 0.2
+    step, models = make_step(dict(shape=shape, focal_list=focal), state, B, False)
+    step.load_batch(inp, gt)
+    step.forward_backward(use_mask=True)
+    torch.cuda.synchronize()
+    batch = dict(inp)
+    batch["img"] = gt["img"]
+    batch["use_mask"] = True
+    rad, expo = torch.rand(10000, 3, generator=gen) * 5, torch.rand(10000, 1, generator=gen) * 6 - 3.0
+    cfg = orc.StepConfig(shape, with_grad_loss=True)
+    losses, grads = orc.step_grads(state, batch, cfg, None, (rad, expo))
+    assert step.losses()["img_loss"].item() == pytest.approx(losses["img_loss"].item(), rel=1e-3)
+    g = grads_of(models)
+    for slot in ("atlas_b", "tm", "blur", "exp"):
+        for k, gr in grads[slot].items():
+            if gr.abs().max() > 0:
+                assert rel(g[slot][k], gr) <= 1e-2, (slot, k)
+    gl = step.grad_loss(rad, expo).item()
+    assert losses["grad_loss"].item() > 0
+    assert gl == pytest.approx(losses["grad_loss"].item(), rel=2e-3)
