@@ -157,7 +157,8 @@ class StepConfig:
     """The subset of the reference's `opt` namespace (configs.py) the hot path reads."""
 
     def __init__(self, shape, patch_size=9, offset_size=5, use_random_gamma=False, fixed_value=0.0,
-                 lr=1e-4, with_grad_loss=True):
+                 lr=1e-4, with_grad_loss=True, uv_mapping_scale=1.0, rigidity_loss_w=None, sparsity_loss_w=None,
+                 alpha_loss_w=None, nets=None):
         self.shape = tuple(shape)  # (N, H, W)  == video_shape
         self.patch_size = patch_size
         self.offset_size = offset_size
@@ -165,13 +166,49 @@ class StepConfig:
         self.fixed_value = fixed_value
         self.lr = lr
         self.with_grad_loss = with_grad_loss
+        self.uv_mapping_scale = uv_mapping_scale
+        self.rigidity_loss_w = rigidity_loss_w     # None = rigidity loss off (opt.rigidity_loss / steps window)
+        self.sparsity_loss_w = sparsity_loss_w     # None = sparsity loss off
+        self.alpha_loss_w = alpha_loss_w           # None = alpha loss off
+        # per-slot SimpleMLP hyper-parameters that are not recoverable from a state_dict:
+        # {'uv_b': dict(last='tanh', skip=(4,), num_frequencies=None), ...}
+        self.nets = nets or {}
+
+
+def _mlp(state, cfg, slot, x, in_dim=3):
+    h = cfg.nets.get(slot, {})
+    return simple_mlp(state[slot], x, h.get("last", "tanh"), in_dim, tuple(h.get("skip", (4,))), h.get("num_frequencies"))
+
+
+def rigidity_loss(state, cfg, slot, coords, src_uv, mask=1.0):
+    """utils.get_rigidity_loss (utils.py:402-454), derivative_amount = 1: finite-difference Jacobian of the
+    (t,y,x) -> (u,v) mapping against the pixel one step up / one step left, pushed towards a rotation.
+    NB the reference scales BOTH u differences by (H-1)/2 and BOTH v differences by (W-1)/2 (utils.py:425-428)."""
+    N, H, W = cfg.shape
+    sy, sx = 2 / (H - 1), 2 / (W - 1)
+    t, y, x = coords[:, :, 0:1], coords[:, :, 1:2], coords[:, :, 2:3]
+    tyx_p = torch.cat((torch.cat((t, t), 1), torch.cat((y - sy, y), 1), torch.cat((x, x - sx), 1)), -1).squeeze(0)
+    uv_p = (_mlp(state, cfg, slot, tyx_p) + tyx_p[:, 1:3]) / 2
+    u_p, v_p = uv_p[:, 0].view(2, -1), uv_p[:, 1].view(2, -1)
+    src_uv = src_uv.reshape(-1, 2)
+    du, dv = src_uv[:, 0].unsqueeze(0) - u_p, src_uv[:, 1].unsqueeze(0) - v_p
+    du_dx, du_dy = du[1] * (H - 1) / 2, du[0] * (H - 1) / 2
+    dv_dy, dv_dx = dv[0] * (W - 1) / 2, dv[1] * (W - 1) / 2
+    J = torch.stack((torch.stack((du_dx, du_dy), -1), torch.stack((dv_dx, dv_dy), -1)), 1) / cfg.uv_mapping_scale
+    JtJ = J.transpose(1, 2) @ J
+    a, b = JtJ[:, 0, 0] + 0.001, JtJ[:, 0, 1]
+    c, d = JtJ[:, 1, 0], JtJ[:, 1, 1] + 0.001
+    inv = torch.stack((torch.stack((d, -b), -1), torch.stack((-c, a), -1)), 1) / (a * d - b * c).view(-1, 1, 1)
+    loss = (JtJ ** 2).sum((1, 2)).sqrt() + (inv ** 2).sum((1, 2)).sqrt()
+    return (loss * mask).mean()
 
 
 def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_intermediates=False,
                 img_weight=1.0, ue_weight=1.0):
     """One forward pass of the 'Main Pipeline' + 'Loss Function' blocks of training.train
-    (training.py:95-267) for the static multi-focus / multi-exposure configuration: blur MLP + focus,
-    atlas_b, PSF sum, learned exposure, CRF, image_mse (+ random gamma), ue_loss, value-only grad_loss.
+    (training.py:95-267): optional blur MLP + focus, optional uv-mapping MLPs / foreground atlas / alpha MLP and
+    layer blend, atlas_b, PSF sum, learned or given exposure, CRF, image_mse (+ random gamma / mask), rigidity,
+    sparsity and alpha losses, ue_loss, value-only grad_loss -- i.e. every branch the five shipped configs take.
 
     batch: {'coords' [1,B,3], 'coord_idx' [1,B] int64, 'img' [1,B,3], optional 'gamma_weights' [1,B,1]}
     gamma: the per-step random gamma scalar (injected; the reference draws it from the CPU RNG, 181).
@@ -203,15 +240,33 @@ def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_int
         patch = coords
         K = 1
         weights = None
-    uv = patch[..., 1:]                                                             # 128-129
+    src_uv = patch[..., 1:]                                                         # 128-129
+    has = lambda slot: state.get(slot) is not None
+    uv = src_uv
+    if has("uv_b"):                                                                 # 131-133
+        uv = (_mlp(state, cfg, "uv_b", patch).view(K, -1, 2) + src_uv) / 2
     inter["uv"] = uv
     rgb = sine_mlp(state["atlas_b"], uv)                                            # 141
     inter["atlas_out"] = rgb
+    alpha = None
+    if has("uv_f"):                                                                 # 135-153
+        uv_f = (_mlp(state, cfg, "uv_f", patch).view(K, -1, 2) + src_uv) / 2
+        rgb_f = sine_mlp(state["atlas_f"], uv_f)
+        if has("alpha"):
+            alpha = _mlp(state, cfg, "alpha", patch).view(K, -1, 1)
+        else:
+            alpha = torch.sigmoid(rgb_f[..., -1:])
+        rgb = (1 - alpha) * rgb + alpha * rgb_f[..., 0:3]
+        alpha = alpha[K // 2].unsqueeze(0)
+        inter["uv_f"], inter["atlas_f_out"] = uv_f, rgb_f
     if has_blur:
         rgb = torch.sum(weights * rgb, 0, keepdim=True)                             # 157
     inter["hdr"] = rgb
 
-    exps = per_frame_gather(3.0 * torch.tanh(state["exp"]["exps"]), idx, H, W)      # 161-166, modules.py:407-408
+    if has("exp"):
+        exps = per_frame_gather(3.0 * torch.tanh(state["exp"]["exps"]), idx, H, W)  # 161-166, modules.py:407-408
+    else:
+        exps = batch["exps"].view(-1, 1)                                            # 168
     ldr, _ = tonemap(state["tm"], rgb.view(-1, 3), exps)                            # 171
     inter["ldr"] = ldr
 
@@ -227,6 +282,21 @@ def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_int
     else:
         losses["img_loss"] = ((fake - real) ** 2).mean()                            # loss_functions.py:12
 
+    ref = K // 2
+    if cfg.rigidity_loss_w is not None:                                             # 203-217
+        mask = batch["weights"] if ("weights" in batch and batch.get("use_mask", False)) else 1.0
+        rig = rigidity_loss(state, cfg, "uv_b", coords, uv[ref], mask)
+        if has("uv_f"):
+            rig = rig + rigidity_loss(state, cfg, "uv_f", coords, inter["uv_f"][ref], mask)
+        losses["rigidity_loss"] = rig * cfg.rigidity_loss_w
+    if has("uv_f"):                                                                 # 220-234
+        if cfg.sparsity_loss_w is not None:
+            not_dyn = (1 - alpha) * torch.exp(inter["atlas_f_out"])
+            losses["sparsity_loss1"] = (torch.norm(not_dyn, dim=-1) ** 2).mean() * cfg.sparsity_loss_w
+            # the reference multiplies by the BOOLEAN flag opt.sparsity_loss, i.e. by 1 (training.py:227)
+            losses["sparsity_loss2"] = torch.mean(-1 / (torch.log(alpha + 1e-24) + torch.log(1 - alpha + 1e-24)))
+        if cfg.alpha_loss_w is not None:
+            losses["alpha_loss"] = torch.mean(alpha) * cfg.alpha_loss_w
     z3, z1 = torch.zeros(1, 3, device=coords.device), torch.zeros(1, 1, device=coords.device)
     ue, _ = tonemap(state["tm"], z3, z1)
     losses["ue_loss"] = torch.mean(torch.abs(ue - cfg.fixed_value))                 # 244-245

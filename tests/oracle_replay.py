@@ -30,7 +30,10 @@ def replay_rng(fx, step):
 def cfg_of(fx):
     return orc.StepConfig(fx["shape"], patch_size=fx["opt"]["patch_size"], offset_size=fx["opt"]["offset_size"],
                           use_random_gamma=fx["use_random_gamma"], fixed_value=fx["opt"]["fixed_value"],
-                          lr=fx["opt"]["lr"])
+                          lr=fx["opt"]["lr"], uv_mapping_scale=fx["opt"].get("uv_mapping_scale", 1.0),
+                          rigidity_loss_w=fx["opt"].get("rigidity_loss_w"),
+                          sparsity_loss_w=fx["opt"].get("sparsity_loss_w"),
+                          alpha_loss_w=fx["opt"].get("alpha_loss_w"), nets=fx.get("nets"))
 
 
 def batch_of(fx, step):

@@ -6,7 +6,9 @@ import torch
 
 from oracle_replay import batch_of, cfg_of, load_fixture, orc, rel, replay_rng
 
-FULL = ["mf_static_small", "mfme_gamma_small"]
+# the last three take the uv-mapping / foreground-layer / alpha-MLP branches and the rigidity, sparsity and alpha
+# losses (configs me_dynamic, video_deblur, video_hdr)
+FULL = ["mf_static_small", "mfme_gamma_small", "me_dynamic_small", "video_deblur_small", "video_hdr_small"]
 
 
 @pytest.mark.parametrize("name", FULL)
@@ -24,6 +26,10 @@ def test_losses_grads_and_adam_match_reference(name):
         assert losses["ue_loss"].item() == pytest.approx(ref_l["loss/ue_loss"], rel=2e-5)
         assert losses["grad_loss"].item() == pytest.approx(ref_l["loss/grad_loss"], rel=1e-3, abs=1e-3)
         assert losses["total"].item() == pytest.approx(ref_l["loss/total_train_loss"], rel=1e-4)
+        for extra in ("rigidity_loss", "sparsity_loss1", "sparsity_loss2", "alpha_loss"):
+            assert (extra in losses) == ("loss/" + extra in ref_l), extra
+            if extra in losses:
+                assert losses[extra].item() == pytest.approx(ref_l["loss/" + extra], rel=5e-5), extra
         for slot, d in fx["grads"][step].items():
             for k, g_ref in d.items():
                 g = grads[slot][k]
@@ -37,7 +43,9 @@ def test_losses_grads_and_adam_match_reference(name):
                 p, mm, vv = orc.adam_update(d[k], grads[slot][k], m[slot][k], v2[slot][k], step + 1, cfg.lr)
                 d[k], m[slot][k], v2[slot][k] = p, mm, vv
                 p_ref = fx["params"][step][slot][k]
-                assert torch.allclose(p, p_ref, rtol=0, atol=2e-6), (step, slot, k, (p - p_ref).abs().max())
+                # the first Adam updates are lr * g / (|g| + eps): where |g| ~ eps = 1e-8 (the layered configs have
+                # such entries) a 1e-4 relative gradient difference moves the update by a few % of lr = 1e-4
+                assert torch.allclose(p, p_ref, rtol=0, atol=5e-6), (step, slot, k, (p - p_ref).abs().max())
 
 
 def test_full_width_network_digest():
