@@ -317,6 +317,161 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# the uv-mapping / two-layer workloads (SURVEY.md section 8f "next" rows): --config me_dynamic|video_deblur|video_hdr
+# ------------------------------------------------------------------------------------------------------
+def layered_host_batches(kind, B, n, seed, pin):
+    from neucam_b200 import harness
+    spec = harness.LAYERED_CONFIGS[kind]
+    N, H, W = spec["shape"]
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        idx = torch.randint(0, N * H * W, (B,), generator=gen)
+        t, rem = idx // (H * W), idx % (H * W)
+        tyx = torch.stack((t / max(N - 1, 1), (rem // W) / (H - 1), (rem % W) / (W - 1)), -1).float() * 2 - 1
+        b = {"coords": tyx[None].contiguous(), "coord_idx": idx[None].contiguous(),
+             "gamma_weights": torch.ones(1, B, 1), "img": torch.rand(1, B, 3, generator=gen) * 2 - 1,
+             "gamma": torch.rand(1, generator=gen) * 100 + 1.0}
+        out.append({k: v.pin_memory() for k, v in b.items()} if pin else b)
+    return out
+
+
+def layered_cpu_steps(kind, B_sample, steps, warmup, threads):
+    from neucam_b200 import harness
+    from oracle import neucam_oracle as orc
+    torch.set_num_threads(threads)
+    spec = harness.LAYERED_CONFIGS[kind]
+    models = harness.build_layered_models(kind, seed=0)
+    state = {s: {k: v.detach().clone() for k, v in m.state_dict().items()} for s, m in models.items() if m is not None}
+    nets = {s: dict(last=spec[s][3], skip=(4,), num_frequencies=spec[s][2] if spec[s][1] else None)
+            for s in ("uv_b", "uv_f", "alpha") if s in spec}
+    o = spec["options"]
+    ocfg = orc.StepConfig(spec["shape"], use_random_gamma=spec["use_random_gamma"], with_grad_loss=False,
+                          uv_mapping_scale=o["uv_mapping_scale"], rigidity_loss_w=o.get("rigidity_loss_w"),
+                          sparsity_loss_w=o.get("sparsity_loss_w"), alpha_loss_w=o.get("alpha_loss_w"), nets=nets)
+    mom = {s: {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in d.items()} for s, d in state.items()}
+    times = []
+    for i, b in enumerate(layered_host_batches(kind, B_sample, steps + warmup, 1, False)):
+        t0 = time.perf_counter()
+        _, grads = orc.step_grads(state, b, ocfg, b["gamma"] if spec["use_random_gamma"] else None)
+        for s, d in state.items():
+            for k in d:
+                p, m, v = orc.adam_update(d[k], grads[s][k], mom[s][k][0], mom[s][k][1], i + 1, 1e-4)
+                d[k], mom[s][k] = p, (m, v)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return B_sample * len(times) / sum(times), sum(times) / len(times) * 1e3
+
+
+def run_layered(args, kind):
+    import torch.distributed as dist
+    from neucam_b200 import harness
+    from neucam_b200.layered import LayeredTrainStep
+    from neucam_b200.step import StepOptions
+
+    spec = harness.LAYERED_CONFIGS[kind]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank == 0:
+            threads = os.cpu_count() or 1
+            B_sample = 2048
+            pps, ms = layered_cpu_steps(kind, B_sample, args.steps, max(args.warmup, 1), threads)
+            print(json.dumps({"impl": "reference", "metric": "train_pixels_per_second", "value": pps, "unit": "px/s",
+                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                              "data": "synthetic", "config": {"workload": kind, "sample": f"{B_sample} px/step"},
+                              "cpu_baseline": {"value": pps, "unit": "px/s", "cores": threads, "kind": "port",
+                                               "sample": f"{B_sample} px/step x {args.steps} steps, oracle port"},
+                              "e2e": {"value": pps, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    N, H, W = spec["shape"]
+    B = int(spec["sample_frac"] * N * H * W)
+    K = 9 if spec["deblur"] else 1
+    atlases = 2 if "uv_f" in spec else 1
+    models = harness.build_layered_models(kind, seed=0)
+    opts = StepOptions(patch_size=9, offset_size=5, use_random_gamma=spec["use_random_gamma"], lr=1e-4, **spec["options"])
+    step = LayeredTrainStep(models, spec["shape"], opts, device=dev, process_group=pg)
+    n_batches = min(args.steps + args.warmup, 8)
+    host = layered_host_batches(kind, B, n_batches, 100 + rank, True)
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    use_gamma = spec["use_random_gamma"]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    if not args.no_graph:
+        step.capture(resident[0], resident[0], resident[0]["gamma"] if use_gamma else None)
+
+    def one_step(i, src):
+        b = src[i % n_batches]
+        if args.no_graph:
+            return step.step(b, b, b["gamma"] if use_gamma else None)
+        step.load_resident(b, b, b["gamma"] if use_gamma else None)
+        return step.run_resident()
+
+    for i in range(args.warmup):
+        one_step(i, resident)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for i in range(args.steps):
+            one_step(args.warmup + i, resident)
+        e1.record()
+        sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    loss_now = step.losses()["total"].item()
+    # end to end: pinned host batch -> H2D -> step -> loss D2H
+    for i in range(2):
+        one_step(i, host)["total"].item()
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        _ = one_step(args.warmup + i, host)["total"].item()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    if rank == 0:
+        h2d = sum(v.numel() * v.element_size() for k, v in host[0].items() if k != "gamma" or use_gamma)
+        line = {"metric": "train_pixels_per_second", "value": world * B / (ms_step * 1e-3), "unit": "px/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 scene nets / f32 glue",
+                "data": "synthetic",
+                "config": {"workload": kind, "shape_NHW": [N, H, W], "pixels_per_step_per_gpu": B, "taps": K,
+                           "scene_networks": atlases, "scene_samples_per_step_per_gpu": K * B * atlases,
+                           "cuda_graph": not args.no_graph},
+                "scene_samples_per_s": world * K * B * atlases / (ms_step * 1e-3),
+                "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "px/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "clocks": clk.summary(), "loss": loss_now}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            pps, _ = layered_cpu_steps(kind, 2048, 10, 1, threads)
+            line["cpu_baseline"] = {"value": pps, "unit": "px/s", "cores": threads, "kind": "port",
+                                    "sample": "2048 px/step x 10 steps, oracle port on torch CPU fp32"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,6 +484,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from neucam_b200 import harness
+    if args.config in harness.LAYERED_CONFIGS:
+        return run_layered(args, args.config)
     cfg = harness.CONFIGS[args.config]
     if args.impl == "reference":
         run_reference_arm(args, cfg)

@@ -32,6 +32,54 @@ CONFIGS = {
 }
 
 
+# the uv-mapping / two-layer configs: configs/config_{me_dynamic,video_deblur,video_hdr}.txt.  Per SimpleMLP:
+# (num_layer, use_encoding, num_frequencies, last nonlinearity); hidden 256, in 3, skip [4] throughout.
+LAYERED_CONFIGS = {
+    "me_dynamic": dict(shape=(3, 448, 680), sample_frac=6e-2, use_random_gamma=True, deblur=False,
+                       uv_b=(4, False, None, "tanh"),
+                       options=dict(uv_mapping_scale=1.0, rigidity_loss_w=1.0, rigidity_loss_steps=50000)),
+    "video_deblur": dict(shape=(80, 360, 640), sample_frac=1e-3, use_random_gamma=False, deblur=True,
+                         uv_b=(4, True, 3, "tanh"), uv_f=(4, True, 3, "tanh"), alpha=(4, True, 4, "sigmoid"),
+                         options=dict(uv_mapping_scale=1.0, rigidity_loss_w=1e-2, rigidity_loss_steps=20000,
+                                      sparsity_loss_w=1e-3, alpha_loss_w=5e-2)),
+    "video_hdr": dict(shape=(80, 360, 640), sample_frac=1e-3, use_random_gamma=False, deblur=False,
+                      uv_b=(4, False, None, "tanh"), uv_f=(6, True, 3, "tanh"), alpha=(4, True, 3, "sigmoid"),
+                      options=dict(uv_mapping_scale=0.8, rigidity_loss_w=1e-2, rigidity_loss_steps=500000,
+                                   sparsity_loss_w=5e-2)),
+}
+
+
+def build_layered_models(kind, shape=None, hidden=512, mlp_hidden=256, seed=0):
+    """Model set of a uv-mapping config, constructed like train_video.py:27-122 does for it."""
+    spec = LAYERED_CONFIGS[kind]
+    torch.manual_seed(seed)
+    n, h, w = shape if shape is not None else spec["shape"]
+    m = OrderedDict((k, None) for k in SLOTS)
+
+    def mlp(hp, out_dim):
+        layers, enc, freqs, last = hp
+        return modules.SimpleMLP(hidden_dim=mlp_hidden, num_layer=layers, in_dim=3, out_dim=out_dim,
+                                 use_encoding=enc, num_frequencies=freqs, skip_layer=[4], nonlinear=last)
+
+    m["atlas_b"] = modules.SingleBVPNet(type="sine", mode="mlp", hidden_features=hidden, num_hidden_layers=3,
+                                        in_features=2, out_features=3, sidelength=(h, w), num_frequencies=7)
+    m["uv_b"] = mlp(spec["uv_b"], 2)
+    if "uv_f" in spec:
+        m["atlas_f"] = modules.SingleBVPNet(type="sine", mode="mlp", hidden_features=hidden, in_features=2,
+                                            out_features=3 if "alpha" in spec else 4, sidelength=(h, w),
+                                            num_frequencies=7)
+        m["uv_f"] = mlp(spec["uv_f"], 2)
+        if "alpha" in spec:
+            m["alpha"] = mlp(spec["alpha"], 1)
+    m["exp"] = modules.LearnExps(n)
+    if spec["deblur"]:
+        m["focal"] = modules.LearnFocal(n)
+        m["blur"] = modules.SimpleMLP(hidden_dim=64, num_layer=4, in_dim=3, out_dim=27, use_encoding=False,
+                                      num_frequencies=7, skip_layer=[4], nonlinear="both")
+    m["tm"] = modules.TonemapNet()
+    return m
+
+
 def pixels_per_step(cfg):
     n, h, w = cfg["shape"]
     return int(cfg["sample_frac"] * n * h * w)   # dataio.py:351

@@ -1,0 +1,280 @@
+"""The training step of the uv-mapping / two-layer configurations (config_me_dynamic, config_video_deblur,
+config_video_hdr): reference training.py:95-271 with `models['uv_b']`, and optionally `models['uv_f']` +
+`models['atlas_f']` + `models['alpha']`, in play.  SURVEY.md section 8f rows "next" 1 and 2.
+
+What runs where:
+  * both scene networks (atlas_b, atlas_f)     fused tcgen05 chains + split-K wgrad kernels, through
+                                               modules.SingleBVPNet -> _SineMLPFunction (forward, dgrad incl.
+                                               d/d(u,v), weight gradients)
+  * Adam over every model                      ONE fused launch over the flat parameter buffer (adam.cu)
+  * value-only grad_loss                       neucam_tm_min_slope
+  * uv / alpha / blur ReLU MLPs, layer blend,  torch ops on the device, differentiated by autograd (cuBLAS GEMMs:
+    PSF sum, CRF, the losses                   library code, the part of this path still to be hand-written)
+
+Nothing here has a CPU path: the scene networks raise on CPU tensors and the optimizer is the CUDA kernel.
+
+Data parallel: like FusedTrainStep, every rank takes a slice of the step's pixels; per-pixel means are
+weighted by B_local / B_global, the pixel-free ue_loss by 1 / world, and the flat gradient buffer is summed
+once per step.
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import _lib, ops
+from .step import FlatParameters, StepOptions, flat_adam  # noqa: F401  (StepOptions re-exported)
+
+_LAYER_SLOTS = ("uv_b", "uv_f", "atlas_f", "alpha")
+
+
+def needs_layered_step(models):
+    """True when the model set has any slot FusedTrainStep does not execute."""
+    return any(models.get(s) is not None for s in _LAYER_SLOTS) or models.get("blur") is None \
+        or models.get("exp") is None
+
+
+class LayeredTrainStep:
+    def __init__(self, models, video_shape, options, device=None, process_group=None, global_pixels=None,
+                 _host_logic_only=False):
+        # _host_logic_only: CPU unit tests of the glue above the kernels (tests/test_layered_cpu.py swap the scene
+        # networks for a stand-in); such an instance cannot run the optimizer and is not a product path
+        if not _host_logic_only:
+            _lib.check(_lib.lib().neucam_check_device(), "neucam_check_device (need an sm_100 GPU)")
+        for slot in ("noise", "depth"):
+            if models.get(slot) is not None:
+                raise NotImplementedError(f"model slot '{slot}' is not used by any shipped NeuCam config")
+        if models.get("atlas_b") is None or models.get("tm") is None:
+            raise NotImplementedError("the step needs at least atlas_b and tm (every shipped config has pre_hdr)")
+        if models.get("uv_f") is not None and models.get("atlas_f") is None:
+            raise ValueError("uv_f without atlas_f (train_video.py:48-58 builds atlas_f whenever split_layer and "
+                             "uv_mapping are both set)")
+        if (models.get("blur") is None) != (models.get("focal") is None):
+            raise ValueError("blur and focal come together (deblur + learn_focal)")
+        self.models = models
+        self.shape = tuple(int(s) for s in video_shape)
+        self.opt = options
+        if _host_logic_only:
+            self.device = torch.device("cpu")
+        else:
+            self.device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.global_pixels = global_pixels
+        self.params = None if _host_logic_only else FlatParameters(models, self.device)
+        n, h, w = self.shape
+        self.K = int(options.patch_size) if models.get("blur") is not None else 1
+        if self.K not in (1, 9, 25):
+            raise ValueError("patch_size must be 9 or 25 (utils.get_input_patch)")
+        side = {1: (0,), 9: (-1, 0, 1), 25: (-2, -1, 0, 1, 2)}[self.K]
+        # tap k = (row dy, column dx) of the neighbourhood, dy outer (utils.py:587-612)
+        self.tap_shift = torch.tensor([[0.0, dy * 2 / (h - 1), dx * 2 / (w - 1)] for dy in side for dx in side],
+                                      device=self.device).view(self.K, 1, 3)
+        # constants of the pipeline live on the device once (no host->device traffic inside a step / a graph)
+        self._one_row_up = torch.tensor([0.0, 2 / (h - 1), 0.0], device=self.device)
+        self._one_col_left = torch.tensor([0.0, 0.0, 2 / (w - 1)], device=self.device)
+        self._off_centre = torch.ones(self.K, 1, 1, device=self.device)
+        self._off_centre[self.K // 2] = 0.0      # the centre tap stays on the pixel (training.py:120)
+        self._black = (torch.zeros(1, 3, device=self.device), torch.zeros(1, 1, device=self.device))
+        self.step_index = 0
+        self._losses = None
+
+    # -- pieces of the pipeline ------------------------------------------------------------------------------
+    def _frame_value(self, per_frame, coord_idx):
+        n, h, w = self.shape
+        return per_frame.reshape(-1)[torch.div(coord_idx, h * w, rounding_mode="floor")].view(-1, 1)
+
+    def _taps(self, coords, coord_idx):
+        """[K,B,3] sample positions and [K,B,1] PSF weights (training.py:99-126)."""
+        if self.K == 1:
+            return coords, None
+        n, h, w = self.shape
+        K = self.K
+        focus = self._frame_value(self.models["focal"](), coord_idx)
+        kernel = self.models["blur"](torch.cat((focus, coords[0, :, 1:3]), -1))            # [B, 3K]
+        shift = torch.stack((torch.zeros_like(kernel[:, :K]),
+                             kernel[:, K:2 * K] * (2 / (h - 1) * self.opt.offset_size),
+                             kernel[:, 2 * K:] * (2 / (w - 1) * self.opt.offset_size)), -1)  # [B,K,3]
+        taps = coords + self.tap_shift + shift.permute(1, 0, 2) * self._off_centre
+        return taps, kernel[:, :K].t().unsqueeze(-1)
+
+    def _warp(self, slot, taps):
+        """(t,y,x) -> atlas (u,v): half-way between the MLP's output and the pixel position (training.py:131-137)."""
+        K = taps.shape[0]
+        return (self.models[slot](taps).view(K, -1, 2) + taps[..., 1:]) * 0.5
+
+    def _rigidity(self, slot, coords, uv_ref, mask):
+        """utils.get_rigidity_loss (utils.py:402-454) with derivative_amount 1, in closed form for the 2x2
+        algebra: J = d(u,v)/d(x,y) by backward differences, loss = |J^T J|_F + |(J^T J + 0.001 I)^-1|_F.
+        The reference converts BOTH u differences with (H-1)/2 and BOTH v differences with (W-1)/2 (utils.py:425-428)."""
+        n, h, w = self.shape
+        pts = coords[0]
+        moved = torch.cat((pts - self._one_row_up, pts - self._one_col_left), 0)
+        uv_moved = ((self.models[slot](moved) + moved[:, 1:3]) * 0.5).view(2, -1, 2)
+        d_up, d_left = uv_ref.reshape(-1, 2) - uv_moved[0], uv_ref.reshape(-1, 2) - uv_moved[1]
+        s = 1.0 / self.opt.uv_mapping_scale
+        a, b = d_left[:, 0] * ((h - 1) / 2 * s), d_up[:, 0] * ((h - 1) / 2 * s)      # du/dx, du/dy
+        c, d = d_left[:, 1] * ((w - 1) / 2 * s), d_up[:, 1] * ((w - 1) / 2 * s)      # dv/dx, dv/dy
+        p, q, r = a * a + c * c, a * b + c * d, b * b + d * d                         # J^T J = [[p,q],[q,r]]
+        pe, re = p + 0.001, r + 0.001
+        det = pe * re - q * q
+        loss = torch.sqrt(p * p + 2 * q * q + r * r) + torch.sqrt(pe * pe + 2 * q * q + re * re) / det
+        if mask is not None:
+            # the reference multiplies the [B] loss by the [1,B,1] weights, which broadcasts to [1,B,B]; the mean
+            # of that outer product is mean(loss) * mean(weights) (utils.py:452-453)
+            return loss.mean() * mask.mean()
+        return loss.mean()
+
+    # -- forward ----------------------------------------------------------------------------------------------
+    def forward(self, model_input, gt, gamma=None, use_mask=False):
+        """Losses of one step as an OrderedDict of device scalars (this rank's share), graph attached."""
+        m, opt = self.models, self.opt
+        dev = self.device
+        coords = model_input["coords"].to(dev, torch.float32).view(1, -1, 3)
+        coord_idx = model_input["coord_idx"].to(dev).view(-1)
+        target = gt["img"].to(dev, torch.float32).view(-1, 3)
+        B = coords.shape[1]
+        K = self.K
+        global_pixels = self.global_pixels if self.global_pixels is not None else B * self.world
+        share = B / float(global_pixels)
+
+        taps, psf = self._taps(coords, coord_idx)
+        uv_b = self._warp("uv_b", taps) if m.get("uv_b") is not None else taps[..., 1:]
+        radiance = m["atlas_b"]({"coords": uv_b})["model_out"]                             # [K,B,3] log radiance
+        alpha = front = uv_f = None
+        if m.get("uv_f") is not None:
+            uv_f = self._warp("uv_f", taps)
+            front = m["atlas_f"]({"coords": uv_f})["model_out"]
+        if m.get("atlas_f") is not None:
+            if front is None:
+                raise ValueError("atlas_f without uv_f: the reference would fail at training.py:149 as well")
+            alpha = m["alpha"](taps).view(K, -1, 1) if m.get("alpha") is not None else torch.sigmoid(front[..., -1:])
+            radiance = torch.lerp(radiance, front[..., 0:3], alpha)                        # training.py:152
+            alpha = alpha[K // 2].unsqueeze(0)
+        if psf is not None:
+            radiance = (psf * radiance).sum(0, keepdim=True)                               # training.py:157
+        if m.get("exp") is not None:
+            exposure = self._frame_value(m["exp"](), coord_idx)
+        else:
+            exposure = model_input["exps"].to(dev, torch.float32).view(-1, 1)
+        ldr = m["tm"](radiance.view(-1, 3), exposure, None)
+
+        fake, real = ldr, target
+        if opt.use_random_gamma:                                                           # training.py:180-183
+            g = torch.as_tensor(gamma, dtype=torch.float32).to(dev).view(1)
+            gw = model_input["gamma_weights"].to(dev, torch.float32).view(-1, 1)
+            log1pg = torch.log(g + 1.0)
+            curve = lambda x: torch.log((x * 0.5 + 0.5) * g + 1.0) / log1pg * 2.0 - 1.0    # utils.gamma_map
+            fake, real = fake + curve(ldr) * gw, real + curve(target) * gw
+        mask = model_input["weights"].to(dev, torch.float32).view(-1, 1) if use_mask else None
+        sq = (fake - real) ** 2
+        losses = OrderedDict()
+        losses["img_loss"] = (sq * mask if mask is not None else sq).mean() * share        # loss_functions.py:8-12
+
+        if opt.rigidity_loss_w is not None and self.step_index < opt.rigidity_loss_steps:  # training.py:203-217
+            rig = self._rigidity("uv_b", coords, uv_b[K // 2], mask)
+            if uv_f is not None:
+                rig = rig + self._rigidity("uv_f", coords, uv_f[K // 2], mask)
+            losses["rigidity_loss"] = rig * (opt.rigidity_loss_w * share)
+        if uv_f is not None:                                                               # training.py:220-234
+            if opt.sparsity_loss_w is not None:
+                hidden_front = (1 - alpha) * torch.exp(front)
+                losses["sparsity_loss1"] = hidden_front.square().sum(-1).mean() * (opt.sparsity_loss_w * share)
+                entropy = torch.log(alpha + 1e-24) + torch.log(1 - alpha + 1e-24)
+                losses["sparsity_loss2"] = (-1 / entropy).mean() * share
+            if opt.alpha_loss_w is not None:
+                losses["alpha_loss"] = alpha.mean() * (opt.alpha_loss_w * share)
+        black = m["tm"](*self._black)                                                      # training.py:244-245
+        losses["ue_loss"] = (black - opt.fixed_value).abs().mean() / self.world
+        losses["total"] = sum(losses.values())
+        return losses
+
+    # -- backward / optimizer ---------------------------------------------------------------------------------
+    def forward_backward(self, model_input, gt, gamma=None, use_mask=False):
+        if self.params is None:
+            raise _lib.NeucamNativeError("LayeredTrainStep was built for host-logic tests only; no optimizer state")
+        self.params.zero_grad()
+        losses = self.forward(model_input, gt, gamma, use_mask)
+        losses["total"].backward()
+        self._losses = OrderedDict((k, v.detach()) for k, v in losses.items())
+        return self._losses
+
+    def reduce_gradients(self):
+        if self.world > 1:
+            from .dist import allreduce_flat_gradients
+            allreduce_flat_gradients(self.params.grad, self.pg)
+
+    def optimizer_step(self, lr=None, reduce=True, lr_groups=None):
+        if reduce:
+            self.reduce_gradients()
+        flat_adam(self.params, self.opt.lr if lr is None else lr, lr_groups)
+
+    def grad_loss(self, rand_radiance=None, rand_exposure=None):
+        """Logged-only relu(-min CRF slope) * 1e6 over 10000 random points (training.py:248-252)."""
+        if rand_radiance is None:
+            rand_radiance = torch.rand(10000, 3) * 5
+            rand_exposure = torch.rand(10000, 1) * 6 - 3.0
+        slope = ops.tm_min_slope([p.data for p in self.models["tm"].parameters()],
+                                 rand_radiance.to(self.device).contiguous(), rand_exposure.to(self.device).contiguous())
+        return torch.relu(-slope) * 1e6
+
+    def losses(self):
+        return self._losses
+
+    # -- CUDA graph ---------------------------------------------------------------------------------------------
+    def capture(self, model_input, gt, gamma=None, use_mask=False):
+        """Captures forward + autograd backward + Adam over STATIC device copies of one batch into a CUDA graph
+        (two graphs around the eager gradient all-reduce when distributed); `run_resident()` replays it after
+        `load_resident()` refreshed the static buffers.  The rigidity window is decided at capture time."""
+        dev = self.device
+        self._static_in = {k: v.to(dev).clone() for k, v in model_input.items() if torch.is_tensor(v)}
+        self._static_gt = {"img": gt["img"].to(dev).clone()}
+        self._static_gamma = None if gamma is None else torch.as_tensor(gamma, dtype=torch.float32).to(dev).view(1).clone()
+        P = self.params
+        saved = [t.clone() for t in (P.flat, P.exp_avg, P.exp_avg_sq, P.adam_state)]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up off the capture stream (kernel attributes, cuBLAS handles)
+            for _ in range(2):
+                self.forward_backward(self._static_in, self._static_gt, self._static_gamma, use_mask)
+                self.optimizer_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for dst, src in zip((P.flat, P.exp_avg, P.exp_avg_sq, P.adam_state), saved):
+            dst.copy_(src)
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self.forward_backward(self._static_in, self._static_gt, self._static_gamma, use_mask)
+            if self.world == 1:
+                self.optimizer_step(reduce=False)
+        g2 = None
+        if self.world > 1:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self.optimizer_step(reduce=False)
+        self._graph = (g1, g2)
+        return self._graph
+
+    def load_resident(self, model_input, gt, gamma=None, non_blocking=True):
+        for k, dst in self._static_in.items():
+            dst.copy_(model_input[k], non_blocking=non_blocking)
+        self._static_gt["img"].copy_(gt["img"], non_blocking=non_blocking)
+        if self._static_gamma is not None:
+            self._static_gamma.copy_(torch.as_tensor(gamma, dtype=torch.float32).view(1), non_blocking=non_blocking)
+
+    def run_resident(self):
+        g1, g2 = self._graph
+        g1.replay()
+        if g2 is not None:
+            self.reduce_gradients()
+            g2.replay()
+        self.step_index += 1
+        return self._losses
+
+    def step(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None):
+        losses = self.forward_backward(model_input, gt, gamma, use_mask)
+        self.optimizer_step(lr_groups=lr_groups)
+        self.step_index += 1
+        return losses

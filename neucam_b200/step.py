@@ -78,24 +78,54 @@ class FlatParameters:
 class StepOptions:
     """The fields of the reference's `opt` namespace (configs.py) that the hot path reads."""
 
-    def __init__(self, patch_size=9, offset_size=5, use_random_gamma=False, fixed_value=0.0, lr=1e-4):
+    def __init__(self, patch_size=9, offset_size=5, use_random_gamma=False, fixed_value=0.0, lr=1e-4,
+                 uv_mapping_scale=1.0, rigidity_loss_w=None, rigidity_loss_steps=0, sparsity_loss_w=None,
+                 alpha_loss_w=None):
         self.patch_size = patch_size
         self.offset_size = offset_size
         self.use_random_gamma = use_random_gamma
         self.fixed_value = fixed_value
         self.lr = lr
+        # layered (uv-mapping) configs only; a weight of None means the loss is switched off
+        self.uv_mapping_scale = uv_mapping_scale
+        self.rigidity_loss_w = rigidity_loss_w
+        self.rigidity_loss_steps = rigidity_loss_steps
+        self.sparsity_loss_w = sparsity_loss_w
+        self.alpha_loss_w = alpha_loss_w
 
     @classmethod
     def from_opt(cls, opt):
+        on = lambda flag, w: float(getattr(opt, w)) if getattr(opt, flag, False) else None
         return cls(patch_size=getattr(opt, "patch_size", 9), offset_size=getattr(opt, "offset_size", 5),
                    use_random_gamma=bool(getattr(opt, "use_random_gamma", False)),
-                   fixed_value=float(getattr(opt, "fixed_value", 0.0)), lr=float(getattr(opt, "lr", 1e-4)))
+                   fixed_value=float(getattr(opt, "fixed_value", 0.0)), lr=float(getattr(opt, "lr", 1e-4)),
+                   uv_mapping_scale=float(getattr(opt, "uv_mapping_scale", 1.0)),
+                   rigidity_loss_w=on("rigidity_loss", "rigidity_loss_w"),
+                   rigidity_loss_steps=int(getattr(opt, "rigidity_loss_steps", 0) or 0),
+                   sparsity_loss_w=on("sparsity_loss", "sparsity_loss_w"),
+                   alpha_loss_w=on("alpha_loss", "alpha_loss_w"))
 
 
 def _unsupported(what):
     raise NotImplementedError(
-        f"neucam_b200 fused step: {what} is not built yet (SURVEY.md section 8f 'next' rows); the fused path "
-        "covers the static multi-focus / multi-exposure pipeline: atlas_b + blur + focal + exp + tm")
+        f"neucam_b200 fused step: {what} is outside FusedTrainStep, which covers the static multi-focus / "
+        "multi-exposure pipeline (atlas_b + blur + focal + exp + tm); the uv-mapping / two-layer configs run "
+        "through neucam_b200.layered.LayeredTrainStep (neucam_b200.training.train picks it automatically)")
+
+
+def flat_adam(P, lr, lr_groups=None):
+    """One Adam update of the flat buffers `P` (FlatParameters).  lr_groups: optional {slot: lr or None}; None
+    freezes the slot (the post-freeze optimizer of training.py:300-313 drops tm / exp / focal and gives the blur
+    net its own rate).  Default: one launch over the whole buffer (all groups identical, training.py:51)."""
+    ops.adam_tick(P.adam_state)
+    if lr_groups is None:
+        ops.adam_step(P.flat, P.grad, P.exp_avg, P.exp_avg_sq, P.adam_state, lr)
+        return
+    for slot, (lo, hi) in P.slot_ranges.items():
+        g_lr = lr_groups.get(slot, lr)
+        if g_lr is None or hi == lo:
+            continue
+        ops.adam_step(P.flat[lo:hi], P.grad[lo:hi], P.exp_avg[lo:hi], P.exp_avg_sq[lo:hi], P.adam_state, g_lr)
 
 
 class FusedTrainStep:
@@ -302,18 +332,9 @@ class FusedTrainStep:
         lr_groups: optional {slot: lr or None}; None freezes the slot (the post-freeze optimizer of
         training.py:300-313 drops tm / exp / focal and gives the blur net its own rate).  Default: one launch
         over the whole flat buffer at `lr` (all groups identical, training.py:51)."""
-        P = self.params
         if reduce:
             self.reduce_gradients()
-        ops.adam_tick(P.adam_state)
-        if lr_groups is None:
-            ops.adam_step(P.flat, P.grad, P.exp_avg, P.exp_avg_sq, P.adam_state, self.opt.lr if lr is None else lr)
-        else:
-            for slot, (lo, hi) in P.slot_ranges.items():
-                g_lr = lr_groups.get(slot, self.opt.lr)
-                if g_lr is None or hi == lo:
-                    continue
-                ops.adam_step(P.flat[lo:hi], P.grad[lo:hi], P.exp_avg[lo:hi], P.exp_avg_sq[lo:hi], P.adam_state, g_lr)
+        flat_adam(self.params, self.opt.lr if lr is None else lr, lr_groups)
         self.repack()
 
     def grad_loss(self, rand_radiance=None, rand_exposure=None):

@@ -1,6 +1,7 @@
 """`train()` with the reference's signature (training.py:18) driving the fused CUDA step.
 
-Mirrors the cadence of the reference loop: per-step pipeline (training.py:95-271) = FusedTrainStep; the freeze
+Mirrors the cadence of the reference loop: per-step pipeline (training.py:95-271) = FusedTrainStep for the static
+multi-focus / multi-exposure model set, LayeredTrainStep for the uv-mapping / two-layer ones; the freeze
 schedule at `opt.start_freeze_tm` (training.py:300-314: a FRESH Adam with lr 1e-5, blur lr 1e-6, tm / exp /
 focal no longer updated, mask weights switched on); checkpoints under the reference's keys every
 `epochs_til_ckpt` epochs and at the end (training.py:86-87, 317).  What it does not reproduce: TensorBoard
@@ -13,6 +14,7 @@ import os
 import torch
 
 from . import utils as nutils
+from .layered import LayeredTrainStep, needs_layered_step
 from .step import FusedTrainStep, StepOptions
 
 
@@ -35,7 +37,11 @@ def train(models, train_dataloader, model_dir, loss_fn=None, summary_fn=None, va
     os.makedirs(os.path.join(model_dir, "checkpoints"), exist_ok=True)
     first_in, _ = next(iter(train_dataloader))
     B = first_in["coords"].reshape(-1, 3).shape[0]
-    step = FusedTrainStep(models, video_shape, StepOptions.from_opt(opt), B, process_group=process_group)
+    layered = needs_layered_step(models)   # uv-mapping / two-layer configs (me_dynamic, video_deblur, video_hdr)
+    if layered:
+        step = LayeredTrainStep(models, video_shape, StepOptions.from_opt(opt), process_group=process_group)
+    else:
+        step = FusedTrainStep(models, video_shape, StepOptions.from_opt(opt), B, process_group=process_group)
 
     use_mask = False
     lr_groups = None
@@ -46,9 +52,12 @@ def train(models, train_dataloader, model_dir, loss_fn=None, summary_fn=None, va
             nutils.save_model(models, os.path.join(model_dir, "checkpoints", "model_epoch_%04d.pth" % epoch))
         for model_input, gt in train_dataloader:
             gamma = (torch.rand(1) * 100 + 1.0) if step.opt.use_random_gamma else None     # training.py:181
-            step.load_batch(model_input, gt, gamma)
-            step.forward_backward(use_mask=use_mask)
-            step.optimizer_step(lr_groups=lr_groups)
+            if layered:
+                step.step(model_input, gt, gamma, use_mask=use_mask, lr_groups=lr_groups)
+            else:
+                step.load_batch(model_input, gt, gamma)
+                step.forward_backward(use_mask=use_mask)
+                step.optimizer_step(lr_groups=lr_groups)
             if not total_steps % log_every:
                 losses = {k: float(v) for k, v in step.losses().items()}
                 history.append((total_steps, losses))

@@ -1,0 +1,158 @@
+"""GPU parity of the uv-mapping / two-layer step (neucam_b200.layered.LayeredTrainStep: fused tcgen05 scene
+networks + autograd glue + fused flat Adam) against the oracle on the same state and batch, at the shipped
+network widths (atlases 512, uv / alpha MLPs 256).  The oracle itself is pinned to the unmodified reference for
+these three configurations by tests/test_oracle_vs_golden.py; the glue is pinned to the reference directly by
+tests/test_layered_cpu.py.  Tolerances: losses 1e-3, gradients 1e-2 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from oracle_replay import orc, rel
+
+from neucam_b200 import harness
+from neucam_b200.layered import LayeredTrainStep
+from neucam_b200.step import FusedTrainStep, StepOptions
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {"me_dynamic": (3, 40, 60), "video_deblur": (6, 36, 64), "video_hdr": (6, 36, 64)}
+
+
+def _setup(kind, B, seed=0):
+    spec = harness.LAYERED_CONFIGS[kind]
+    shape = SHAPES[kind]
+    models = harness.build_layered_models(kind, shape, seed=seed)
+    with torch.no_grad():   # non-trivial exposure / focus / CRF state so every gradient path is exercised
+        models["exp"].exps.copy_(torch.linspace(-0.4, 0.5, shape[0]))
+        if models["focal"] is not None:
+            models["focal"].focus.copy_(torch.linspace(-0.6, 0.7, shape[0]).view_as(models["focal"].focus))
+    state = {s: {k: v.detach().clone() for k, v in m.state_dict().items()} for s, m in models.items() if m is not None}
+    opts = StepOptions(patch_size=9, offset_size=5, use_random_gamma=spec["use_random_gamma"], lr=1e-4,
+                       **spec["options"])
+    g = torch.Generator().manual_seed(seed + 7)
+    n, h, w = shape
+    grid = harness.mgrid(shape)
+    idx = torch.randint(0, n * h * w, (B,), generator=g)
+    batch = {"coords": grid[idx][None], "coord_idx": idx[None], "img": torch.rand(1, B, 3, generator=g) * 2 - 1,
+             "gamma_weights": torch.rand(1, B, 1, generator=g)}
+    nets = {s: dict(last=spec[s][3], skip=(4,), num_frequencies=spec[s][2] if spec[s][1] else None)
+            for s in ("uv_b", "uv_f", "alpha") if s in spec}
+    o = spec["options"]
+    cfg = orc.StepConfig(shape, use_random_gamma=spec["use_random_gamma"], with_grad_loss=False,
+                         uv_mapping_scale=o["uv_mapping_scale"], rigidity_loss_w=o.get("rigidity_loss_w"),
+                         sparsity_loss_w=o.get("sparsity_loss_w"), alpha_loss_w=o.get("alpha_loss_w"), nets=nets)
+    return models, state, opts, batch, cfg
+
+
+@pytest.mark.parametrize("kind", ["me_dynamic", "video_deblur", "video_hdr"])
+def test_losses_and_gradients_match_oracle(kind):
+    B = 700   # ragged against the 128-row tiles of the chain, also after the x9 taps
+    models, state, opts, batch, cfg = _setup(kind, B)
+    step = LayeredTrainStep(models, SHAPES[kind], opts, device="cuda")
+    gamma = torch.tensor([37.0]) if opts.use_random_gamma else None
+    losses = step.forward_backward(batch, {"img": batch["img"]}, gamma)
+    torch.cuda.synchronize()
+    dev_state = {s: {k: v.cuda() for k, v in d.items()} for s, d in state.items()}
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    ref_l, ref_g = orc.step_grads(dev_state, dev_batch, cfg, gamma.cuda() if gamma is not None else None)
+    for k, v in losses.items():
+        assert v.item() == pytest.approx(ref_l[k].item(), rel=1e-3, abs=1e-7), k
+    assert set(losses) == set(ref_l)
+    worst = ("", 0.0)
+    for slot, d in ref_g.items():
+        for k, g_ref in d.items():
+            g = dict(models[slot].named_parameters())[k].grad
+            if g_ref.abs().max() == 0:
+                assert g.abs().max() == 0, (slot, k)
+                continue
+            e = rel(g, g_ref)
+            worst = max(worst, (f"{slot}.{k}", e), key=lambda t: t[1])
+            assert e < 1e-2, (slot, k, e)
+    print(kind, "worst gradient error", worst)
+
+
+def test_adam_steps_follow_oracle():
+    """Three consecutive steps: parameters after each fused Adam update against the oracle's Adam on ITS OWN
+    gradients (free-running, so differences compound: 2.5e-5 absolute = a quarter of one lr-sized update)."""
+    kind, B = "video_hdr", 512
+    models, state, opts, batch, cfg = _setup(kind, B, seed=3)
+    step = LayeredTrainStep(models, SHAPES[kind], opts, device="cuda")
+    dev_state = {s: {k: v.cuda() for k, v in d.items()} for s, d in state.items()}
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    m1 = {s: {k: torch.zeros_like(v) for k, v in d.items()} for s, d in dev_state.items()}
+    m2 = {s: {k: torch.zeros_like(v) for k, v in d.items()} for s, d in dev_state.items()}
+    for it in range(3):
+        step.step(batch, {"img": batch["img"]})
+        _, g = orc.step_grads(dev_state, dev_batch, cfg)
+        for s, d in dev_state.items():
+            for k in d:
+                d[k], m1[s][k], m2[s][k] = orc.adam_update(d[k], g[s][k], m1[s][k], m2[s][k], it + 1, 1e-4)
+        moved = 0.0
+        for s, d in dev_state.items():
+            mine = dict(models[s].named_parameters())
+            for k, p_ref in d.items():
+                assert (mine[k].detach() - p_ref).abs().max().item() < 2.5e-5 * (it + 1), (it, s, k)
+                moved = max(moved, (p_ref - state[s][k].cuda()).abs().max().item())
+        assert moved > 5e-5
+
+
+def test_layered_step_reproduces_fused_step_on_static_models():
+    """The layered step is the general pipeline: on the static multi-focus model set it must give the gradients
+    of FusedTrainStep (two independent implementations of training.py:95-271 above the same scene kernels)."""
+    shape, B = (2, 30, 45), 600
+    g = torch.Generator().manual_seed(5)
+    grid = harness.mgrid(shape)
+    idx = torch.randint(0, grid.shape[0], (B,), generator=g)
+    inp = {"coords": grid[idx][None], "coord_idx": idx[None]}
+    gt = {"img": torch.rand(1, B, 3, generator=g) * 2 - 1}
+    opts = StepOptions(lr=1e-4)
+    grads = []
+    for cls in (FusedTrainStep, LayeredTrainStep):
+        models = harness.build_static_models(shape, [-1.0, 1.0], seed=11)
+        if cls is FusedTrainStep:
+            st = cls(models, shape, opts, B, device="cuda")
+            st.load_batch(inp, gt)
+            st.forward_backward()
+        else:
+            st = cls(models, shape, opts, device="cuda")
+            st.forward_backward(inp, gt)
+        torch.cuda.synchronize()
+        grads.append({(s, k): p.grad.clone() for s, m in models.items() if m is not None
+                      for k, p in m.named_parameters()})
+    for key, g0 in grads[0].items():
+        if g0.abs().max() == 0:
+            assert grads[1][key].abs().max() == 0, key
+        else:
+            assert rel(grads[1][key], g0) < 1e-2, (key, rel(grads[1][key], g0))
+
+
+def test_train_loop_dispatches_layered_step(tmp_path):
+    import argparse
+    from neucam_b200 import training, utils as nutils
+    kind = "video_deblur"
+    shape = SHAPES[kind]
+    models = harness.build_layered_models(kind, shape, seed=2)
+    spec = harness.LAYERED_CONFIGS[kind]
+    o = spec["options"]
+    opt = argparse.Namespace(num_epochs=1, lr=1e-4, steps_til_summary=100, epochs_til_ckpt=100, patch_size=9,
+                             offset_size=5, use_random_gamma=False, fixed_value=0.0, start_freeze_tm=2,
+                             uv_mapping_scale=o["uv_mapping_scale"], rigidity_loss=True,
+                             rigidity_loss_w=o["rigidity_loss_w"], rigidity_loss_steps=3, sparsity_loss=True,
+                             sparsity_loss_w=o["sparsity_loss_w"], alpha_loss=True, alpha_loss_w=o["alpha_loss_w"])
+    g = torch.Generator().manual_seed(1)
+    grid = harness.mgrid(shape)
+    target = torch.rand(grid.shape[0], 3, generator=g) * 2 - 1
+    batches = []
+    for _ in range(5):
+        idx = torch.randint(0, grid.shape[0], (384,), generator=g)
+        batches.append(({"coords": grid[idx][None], "coord_idx": idx[None], "weights": torch.ones(1, 384, 1)},
+                        {"img": target[idx][None]}))
+    before = models["tm"].layers_r[0].weight.detach().clone()
+    hist = training.train(models, batches, str(tmp_path), video_shape=shape, opt=opt, log_every=1)
+    assert len(hist) == 5
+    assert "rigidity_loss" in hist[0][1] and "rigidity_loss" in hist[2][1] and "rigidity_loss" not in hist[3][1]
+    assert all(torch.isfinite(torch.tensor(list(h[1].values()))).all() for h in hist)
+    ck = torch.load(tmp_path / "checkpoints" / "model_final.pth", weights_only=False)
+    for slot in ("atlas_b", "atlas_f", "uv_b", "uv_f", "alpha", "blur", "exp", "focal", "tm"):
+        assert nutils.CHECKPOINT_KEYS[slot] in ck, slot
+    # tm moved during the first three steps and is frozen afterwards (training.py:300-313)
+    assert not torch.equal(models["tm"].layers_r[0].weight.detach().cpu(), before.cpu())
