@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NEUCAM_ABI_VERSION 4
+#define NEUCAM_ABI_VERSION 5
 
 #define NEUCAM_ERR_BAD_ARG (-1)
 #define NEUCAM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point unavailable */
@@ -89,6 +89,39 @@ int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const 
 
 /* neucam_sine_mlp_head_wgrad: ACCUMULATES dW4 [out_dim,512] += dy^T a4 (a4 = act16 slot 3). */
 int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q, float* dw4,
+                               void* stream);
+
+/* ---- 256-wide ReLU MLPs: the uv-mapping and alpha networks of the layered configs --------------------------
+ * Replaces SimpleMLP.forward (modules.py:282-306) as called at training.py:131-137 (uv_b / uv_f), 148-150
+ * (alpha) and utils.py:418-419 (rigidity loss), and the autograd backward of those calls (training.py:270).
+ *
+ * The network input is handed over ENCODED: feat16 [Q,64] fp16 = raw coordinates + NeRF positional encoding
+ * (modules.py:567-580) in any column order the caller likes, zero padded to 64; weights that multiply the
+ * encoded input are given in the same column order.  A network with H+1 Linear layers is H tensor-core GEMMs
+ * (first layer, hidden layers, with the reference's skip connection modules.py:299-300 as an extra K-block on
+ * the encoded input) followed by the out_dim <= 4 output layer and its nonlinearity on CUDA cores.
+ *
+ * neucam_relu_mlp_fwd: w_stages [S*256,64] fp16 = for every GEMM in order its 256(out) x 64(in) K-blocks;
+ *   stage_begin[n_gemm+1] delimits them; a_src[S] says what each K-block multiplies (0..3 = that 64-column block
+ *   of the previous activation, 4 = the encoded input).  bias [n_gemm,256]; w_last [out_dim,256], b_last fp32;
+ *   out_kind 0 none / 1 tanh / 2 sigmoid.  Writes y [Q,out_dim] fp32 and, when act16 != NULL, the activations
+ *   h_0..h_{H-1} as [H,Q,256] fp16.
+ * neucam_relu_mlp_bwd: dpre [Q,out_dim] fp32 = dL/d(output-layer pre-activation); wT_stages = for layer H-1
+ *   down to 1 (then layer 0 if dfeat != NULL) the four 256(in, zero padded) x 64(out) K-blocks of the TRANSPOSED
+ *   weight (skip columns excluded: the reference detaches the skip input, modules.py:287).  Writes dz16 [H,Q,256]
+ *   fp16 (times *scale_dev, a power of two) and dfeat [Q,64] fp32 (unscaled) when asked.
+ * neucam_relu_mlp_wgrad / _head_wgrad: ACCUMULATE the weight and bias gradients (divided by *scale_dev) from
+ *   dz16 / act16 / feat16: dw_first [256,64] and dw_skip[l] [256,64] in encoded-input column order, dw[l] with row
+ *   pitch ldw[l] for l >= 1 (its first 256 columns), db[l] [256]; dw_last [out_dim,256] += dpre^T h_{H-1}. */
+int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_stages, int n_gemm, const int* stage_begin,
+                        const uint8_t* a_src, const float* bias, const float* w_last, const float* b_last,
+                        int out_dim, int out_kind, float* y, void* act16, void* stream);
+int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_stages, int H, const float* w_last, int out_dim,
+                        const void* act16, const float* scale_dev, void* dz16, float* dfeat, void* stream);
+int neucam_relu_mlp_wgrad(const void* dz16, const void* act16, const void* feat16, int64_t Q, int H,
+                          const float* scale_dev, float* dw_first, float* const* dw, const int* ldw,
+                          float* const* db, float* const* dw_skip, void* stream);
+int neucam_relu_mlp_head_wgrad(const void* h16, const float* dpre, int out_dim, int64_t Q, float* dw_last,
                                void* stream);
 
 /* ---- per-pixel stages around the scene MLP ------------------------------------------------------------

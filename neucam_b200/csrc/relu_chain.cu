@@ -1,0 +1,445 @@
+// relu_chain.cu -- the 256-wide ReLU MLPs of the layered configs (uv-mapping and alpha networks:
+// reference modules.py:255-306 `SimpleMLP`, called at training.py:131-137,148-150 and utils.py:418-419),
+// forward and input/activation gradient, as ONE persistent tcgen05 kernel per direction.
+//
+//   forward   feat[Q,64] --W0--> relu --W1--> relu ... --W_{H-1}--> relu --w_last (SIMT)--> tanh|sigmoid
+//   backward  dpre[Q,out] --w_last (SIMT)--> mask --W_{H-1}^T--> mask ... --W_1^T--> mask [--W_0^T--> dfeat]
+//
+// A CTA owns a 128-sample tile for the whole chain: the activation tile lives in shared memory as the K-major
+// SWIZZLE_128B A operand (4 k-blocks of 128 x 64 fp16), every layer is 4 (+1 for a skip connection) weight
+// "stages" of 256 x 64 fp16 streamed through a 4-deep TMA ring, accumulated by M128 x N256 x K16 MMAs into 256
+// TMEM columns, drained by 4 epilogue warps (thread = sample row) that apply bias + ReLU (forward) or the ReLU
+// mask of the saved activation (backward), write the next operand tile in place and TMA-store it to HBM for
+// the weight-gradient GEMMs.  The encoded input (raw coordinates + NeRF positional encoding, zero-padded to 64
+// features) is its own 16 KB operand tile, so the first layer and the skip connection are tensor-core GEMMs too.
+//
+// Warp roles: 0..3 epilogue, 4 TMA producer, 5 MMA issuer + TMEM owner (control warps have the highest ids).
+#include "host_util.h"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+namespace {
+
+constexpr int WID = 256;
+constexpr int TILE_M = 128;
+constexpr int NSTAGE = 4;
+constexpr int MAX_GEMM = 8;
+constexpr int MAX_STAGES = 40;
+constexpr int FEAT = 64;
+constexpr uint32_t KB_BYTES = TILE_M * 128;      // one k-block of the operand tile: 128 rows x 64 fp16
+constexpr uint32_t STAGE_BYTES = WID * 128;      // one weight stage: 256 rows x 64 fp16
+constexpr uint32_t OFF_A = 0;
+constexpr uint32_t OFF_F = OFF_A + 4 * KB_BYTES;
+constexpr uint32_t OFF_W = OFF_F + KB_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_W + NSTAGE * STAGE_BYTES;      // float [MAX_GEMM][256] (forward)
+constexpr uint32_t OFF_HEAD = OFF_BIAS + MAX_GEMM * WID * 4;     // float [4][256] last-layer weights
+constexpr uint32_t OFF_BAR = OFF_HEAD + 4 * WID * 4;
+constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
+constexpr int NTHREADS = 192;
+constexpr int WARP_PRODUCER = 4, WARP_MMA = 5;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_AREADY = 9, BAR_FFULL = 10, BAR_FEMPTY = 11 };
+
+struct ReluMaps {
+  CUtensorMap feat;            // [Q,64] fp16, box 64 x 128 (forward)
+  CUtensorMap w;               // weight stages [S*256, 64] fp16, box 64 x 256
+  CUtensorMap act[MAX_GEMM];   // forward: h_l ; backward: dz_l   ([Q,256] fp16, box 64 x 128)
+};
+
+struct ReluParams {
+  int Q, ntiles, n_gemm, H;            // H = number of saved activation layers (= forward GEMMs)
+  int stage_begin[MAX_GEMM + 1];
+  uint8_t a_src[MAX_STAGES];           // per stage: 0..3 = k-block of the operand tile, 4 = encoded-input tile
+  int feat_last_gemm;                  // forward: last GEMM of a tile that reads the encoded-input tile
+  const float* bias;                   // forward: [n_gemm][256]
+  const float* w_last;                 // [out_dim][256] fp32
+  const float* b_last;                 // [out_dim]
+  int out_dim, out_kind;               // 0 none, 1 tanh, 2 sigmoid
+  int store;                           // TMA-store the operand tiles (activations / dz) to HBM
+  float* y;                            // forward [Q,out_dim]
+  const float* dpre;                   // backward [Q,out_dim]: dL/d(pre-activation of the last layer)
+  const __half* act16;                 // backward [H][Q,256]: saved activations (ReLU masks)
+  const float* scale;                  // backward: device scalar loss scale
+  float* dfeat;                        // backward [Q,64] fp32 or null (the last GEMM then computes it)
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 32 consecutive columns (chunk c of 8) of one row of the operand tile: 16 packed words
+__device__ __forceinline__ void write_chunk(uint32_t a_base, uint32_t c, uint32_t row, const uint32_t (&w)[16]) {
+  const uint32_t blk = a_base + (c >> 1) * KB_BYTES;
+  const uint32_t qb = (c & 1u) * 4u;
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q)
+    st_shared_v4(blk + sw128_offset(row, qb + q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(NTHREADS, 1)
+relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__ ReluParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+  float* s_bias = reinterpret_cast<float*>(sm + OFF_BIAS);
+  float* s_head = reinterpret_cast<float*>(sm + OFF_HEAD);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + OFF_TMEM);
+  const uint32_t bar0 = base + OFF_BAR;
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (!BWD)
+    for (int i = tid; i < p.n_gemm * WID; i += NTHREADS) s_bias[i] = p.bias[i];
+  for (int i = tid; i < 4 * WID; i += NTHREADS) s_head[i] = (i < p.out_dim * WID) ? p.w_last[i] : 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar(BAR_WFULL + s), 1);
+      mbar_init(bar(BAR_WEMPTY + s), 1);
+    }
+    mbar_init(bar(BAR_ACC), 1);
+    mbar_init(bar(BAR_AREADY), 128);
+    mbar_init(bar(BAR_FFULL), 1);
+    mbar_init(bar(BAR_FEMPTY), 1);
+    mbar_fence_init();
+  }
+  if (warp == WARP_MMA) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int S = p.stage_begin[p.n_gemm];
+
+  if (warp == WARP_PRODUCER) {
+    // ---------------- TMA producer: encoded-input tile (forward) + the weight stages of every GEMM ----------------
+    uint32_t slot = 0, ph = 0, fph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      if (!BWD) {
+        mbar_wait(bar(BAR_FEMPTY), fph ^ 1);
+        fph ^= 1;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar(BAR_FFULL), KB_BYTES);
+          tma_load_2d(base + OFF_F, &maps.feat, bar(BAR_FFULL), 0, tile * TILE_M);
+        }
+        __syncwarp();
+      }
+      for (int s = 0; s < S; ++s) {
+        mbar_wait(bar(BAR_WEMPTY + slot), ph ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar(BAR_WFULL + slot), STAGE_BYTES);
+          tma_load_2d(base + OFF_W + slot * STAGE_BYTES, &maps.w, bar(BAR_WFULL + slot), 0, s * WID);
+        }
+        __syncwarp();
+        if (++slot == NSTAGE) { slot = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = make_idesc_f16(TILE_M, WID, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
+    uint32_t slot = 0, ph = 0, aph = 0, fph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int g = 0; g < p.n_gemm; ++g) {
+        mbar_wait(bar(BAR_AREADY), aph);   // operand tile written (and the accumulator drained)
+        aph ^= 1;
+        if (!BWD && g == 0) {
+          mbar_wait(bar(BAR_FFULL), fph);
+          fph ^= 1;
+        }
+        tc_fence_after_sync();
+        for (int s = p.stage_begin[g]; s < p.stage_begin[g + 1]; ++s) {
+          mbar_wait(bar(BAR_WFULL + slot), ph);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t src = p.a_src[s];
+            const uint32_t a_addr = base + (src == 4 ? OFF_F : OFF_A + src * KB_BYTES);
+            const uint32_t b_addr = base + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_f16_ss(tmem_base, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
+                          make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc,
+                          (s > p.stage_begin[g] || k16 > 0) ? 1u : 0u);
+            umma_commit(bar(BAR_WEMPTY + slot));
+          }
+          __syncwarp();
+          if (++slot == NSTAGE) { slot = 0; ph ^= 1; }
+        }
+        if (lane == 0) {
+          if (!BWD && g == p.feat_last_gemm) umma_commit(bar(BAR_FEMPTY));
+          umma_commit(bar(BAR_ACC));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 0..3: thread = sample row = TMEM lane ----------------
+    const uint32_t row = tid;
+    const uint32_t t_row = tmem_base + ((warp * 32u) << 16);
+    const uint32_t a_base = base + OFF_A;
+    uint32_t acc_ph = 0;
+    if (!BWD) mbar_arrive(bar(BAR_AREADY));   // the first GEMM of the first tile has nothing to wait for
+    float scale = 1.f, inv_scale = 1.f;
+    if (BWD) {
+      scale = *p.scale;
+      inv_scale = 1.f / scale;
+    }
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const long long grow = (long long)tile * TILE_M + row;
+      const bool valid = grow < p.Q;
+      if (BWD) {
+        // prologue: dz_{H-1} = mask(h_{H-1}) * (dpre . w_last), scaled, as the first operand tile
+        float dp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid)
+          for (int o = 0; o < p.out_dim; ++o) dp[o] = p.dpre[grow * p.out_dim + o] * scale;
+        const __half* mrow = p.act16 + ((size_t)(p.H - 1) * p.Q + (valid ? grow : 0)) * WID;
+        if (tid == 0) tma_store_wait_read0();
+        epi_bar_sync();
+        for (uint32_t c = 0; c < 8; ++c) {
+          uint4 m[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[q] = valid ? *reinterpret_cast<const uint4*>(mrow + c * 32 + q * 8) : make_uint4(0, 0, 0, 0);
+          const uint32_t* mw = reinterpret_cast<const uint32_t*>(m);
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c * 32 + 2 * j;
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              d0 = fmaf(dp[o], s_head[o * WID + col], d0);
+              d1 = fmaf(dp[o], s_head[o * WID + col + 1], d1);
+            }
+            if ((mw[j] & 0x7FFFu) == 0u) d0 = 0.f;            // h == 0  <=>  ReLU closed (h is never negative)
+            if ((mw[j] & 0x7FFF0000u) == 0u) d1 = 0.f;
+            w[j] = pack_h2_sat(d0, d1);
+          }
+          write_chunk(a_base, c, row, w);
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (tid == 0 && p.store) {
+          for (int kb = 0; kb < 4; ++kb) tma_store_2d(&maps.act[p.H - 1], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
+          tma_store_commit();
+        }
+        mbar_arrive(bar(BAR_AREADY));
+      }
+      for (int g = 0; g < p.n_gemm; ++g) {
+        const bool last = (g == p.n_gemm - 1);
+        const bool dfeat_gemm = BWD && last && p.dfeat != nullptr;
+        const int layer = BWD ? (p.H - 2 - g) : g;        // layer whose operand tile this epilogue produces
+        const __half* mrow = nullptr;
+        if (BWD && !dfeat_gemm) mrow = p.act16 + ((size_t)layer * p.Q + (valid ? grow : 0)) * WID;
+        mbar_wait(bar(BAR_ACC), acc_ph);
+        acc_ph ^= 1;
+        tc_fence_after_sync();
+        if (dfeat_gemm) {
+          // input gradient: first 64 accumulator columns, unscaled, fp32
+          for (uint32_t c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c * 32, r);
+            tmem_ld_wait();
+            if (valid) {
+              float4* dst = reinterpret_cast<float4*>(p.dfeat + grow * FEAT + c * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                dst[q] = make_float4(__uint_as_float(r[4 * q]) * inv_scale, __uint_as_float(r[4 * q + 1]) * inv_scale,
+                                     __uint_as_float(r[4 * q + 2]) * inv_scale, __uint_as_float(r[4 * q + 3]) * inv_scale);
+            }
+          }
+          tc_fence_before_sync();
+          continue;   // last GEMM of the tile: the next tile's prologue re-arms BAR_AREADY
+        }
+        if (tid == 0) tma_store_wait_read0();   // the previous TMA store has finished reading the tile
+        epi_bar_sync();
+        float yacc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (uint32_t c = 0; c < 8; ++c) {
+          uint4 m[4];
+          if (BWD) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = valid ? *reinterpret_cast<const uint4*>(mrow + c * 32 + q * 8) : make_uint4(0, 0, 0, 0);
+          }
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          uint32_t w[16];
+          if (!BWD) {
+            const float* bz = s_bias + g * WID + c * 32;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float h0 = fmaxf(__uint_as_float(r[2 * j]) + bz[2 * j], 0.f);
+              const float h1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bz[2 * j + 1], 0.f);
+              if (last) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  yacc[o] = fmaf(h0, s_head[o * WID + c * 32 + 2 * j], yacc[o]);
+                  yacc[o] = fmaf(h1, s_head[o * WID + c * 32 + 2 * j + 1], yacc[o]);
+                }
+              }
+              w[j] = pack_h2(h0, h1);
+            }
+          } else {
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(m);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float d0 = __uint_as_float(r[2 * j]), d1 = __uint_as_float(r[2 * j + 1]);
+              if ((mw[j] & 0x7FFFu) == 0u) d0 = 0.f;
+              if ((mw[j] & 0x7FFF0000u) == 0u) d1 = 0.f;
+              w[j] = pack_h2_sat(d0, d1);
+            }
+          }
+          write_chunk(a_base, c, row, w);
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (tid == 0 && p.store) {
+          for (int kb = 0; kb < 4; ++kb) tma_store_2d(&maps.act[layer], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
+          tma_store_commit();
+        }
+        if (!BWD || !last) mbar_arrive(bar(BAR_AREADY));
+        if (!BWD && last && valid) {
+          for (int o = 0; o < p.out_dim; ++o) {
+            float v = yacc[o] + p.b_last[o];
+            if (p.out_kind == 1) v = tanhf(v);
+            else if (p.out_kind == 2) v = 1.f / (1.f + expf(-v));
+            p.y[grow * p.out_dim + o] = v;
+          }
+        }
+      }
+    }
+    if (tid == 0) tma_store_wait0();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, 256);
+}
+
+int check_stage_plan(int n_gemm, const int* stage_begin) {
+  if (n_gemm < 1 || n_gemm > MAX_GEMM) return 1;
+  if (stage_begin[0] != 0) return 1;
+  for (int g = 0; g < n_gemm; ++g)
+    if (stage_begin[g + 1] <= stage_begin[g]) return 1;
+  return stage_begin[n_gemm] > MAX_STAGES;
+}
+
+}  // namespace
+
+// forward of one ReLU MLP.  feat16 [Q,64] fp16 (encoded input, zero padded); w_stages [S*256,64] fp16 (per GEMM:
+// its 256 x 64 K-blocks in order); stage_begin[n_gemm+1]; a_src[S] (0..3 operand k-block, 4 encoded input);
+// bias [n_gemm,256]; w_last [out_dim,256], b_last [out_dim] fp32; out_kind 0 none / 1 tanh / 2 sigmoid;
+// y [Q,out_dim] fp32; act16 [n_gemm,Q,256] fp16 or NULL (saved activations for the backward pass).
+extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_stages, int n_gemm,
+                                   const int* stage_begin, const uint8_t* a_src, const float* bias,
+                                   const float* w_last, const float* b_last, int out_dim, int out_kind, float* y,
+                                   void* act16, void* stream) {
+  NC_CHECK_ARG(feat16 && w_stages && stage_begin && a_src && bias && w_last && b_last && y);
+  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && out_kind >= 0 && out_kind <= 2);
+  NC_CHECK_ARG(check_stage_plan(n_gemm, stage_begin) == 0);
+  ReluMaps maps;
+  ReluParams p{};
+  const int S = stage_begin[n_gemm];
+  int rc = nchost::make_tmap_16b(&maps.feat, feat16, (uint64_t)Q, FEAT, FEAT, TILE_M, 64);
+  if (rc) return rc;
+  rc = nchost::make_tmap_16b(&maps.w, w_stages, (uint64_t)S * WID, 64, 64, WID, 64);
+  if (rc) return rc;
+  p.feat_last_gemm = 0;
+  for (int g = 0; g < n_gemm; ++g) {
+    const __half* a = act16 ? (const __half*)act16 + (size_t)g * Q * WID : (const __half*)feat16;
+    rc = nchost::make_tmap_16b(&maps.act[g], a, (uint64_t)Q, act16 ? WID : FEAT, act16 ? WID : FEAT, TILE_M, 64);
+    if (rc) return rc;
+    p.stage_begin[g] = stage_begin[g];
+    for (int s = stage_begin[g]; s < stage_begin[g + 1]; ++s) {
+      NC_CHECK_ARG(a_src[s] <= 4);
+      NC_CHECK_ARG(g > 0 || a_src[s] == 4);     // the first GEMM reads the encoded input only
+      p.a_src[s] = a_src[s];
+      if (a_src[s] == 4) p.feat_last_gemm = g;
+    }
+  }
+  p.stage_begin[n_gemm] = S;
+  p.Q = (int)Q;
+  p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
+  p.n_gemm = n_gemm;
+  p.H = n_gemm;
+  p.bias = bias;
+  p.w_last = w_last;
+  p.b_last = b_last;
+  p.out_dim = out_dim;
+  p.out_kind = out_kind;
+  p.store = act16 != nullptr;
+  p.y = y;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NC_CHECK_CUDA(cudaFuncSetAttribute(relu_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  const int sms = nchost::sm_count();
+  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  relu_chain_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// backward of one ReLU MLP w.r.t. its activations (and, when dfeat is given, its encoded input).
+// dpre [Q,out_dim] fp32 = dL/d(last layer's pre-activation); act16 [H,Q,256] saved by the forward;
+// wT_stages: per backward GEMM (layer H-1 down to 1, then layer 0 when dfeat != NULL) the 256 x 64 K-blocks of the
+// TRANSPOSED weight (rows = input feature, zero padded to 256); scale_dev: power-of-two loss scale applied to dz;
+// dz16 [H,Q,256] fp16 out (scaled); dfeat [Q,64] fp32 out or NULL.
+extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_stages, int H, const float* w_last,
+                                   int out_dim, const void* act16, const float* scale_dev, void* dz16,
+                                   float* dfeat, void* stream) {
+  NC_CHECK_ARG(dpre && wT_stages && w_last && act16 && scale_dev && dz16);
+  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && H >= 1 && H <= MAX_GEMM);
+  const int n_gemm = (H - 1) + (dfeat ? 1 : 0);
+  ReluMaps maps;
+  ReluParams p{};
+  int rc = nchost::make_tmap_16b(&maps.feat, dz16, (uint64_t)Q, WID, WID, TILE_M, 64);   // unused in this direction
+  if (rc) return rc;
+  rc = nchost::make_tmap_16b(&maps.w, wT_stages, (uint64_t)(n_gemm > 0 ? n_gemm : 1) * 4 * WID, 64, 64, WID, 64);
+  if (rc) return rc;
+  for (int l = 0; l < H; ++l) {
+    rc = nchost::make_tmap_16b(&maps.act[l], (const __half*)dz16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, TILE_M, 64);
+    if (rc) return rc;
+  }
+  for (int g = 0; g <= n_gemm; ++g) p.stage_begin[g] = 4 * g;
+  for (int s = 0; s < 4 * n_gemm; ++s) p.a_src[s] = (uint8_t)(s & 3);
+  p.Q = (int)Q;
+  p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
+  p.n_gemm = n_gemm;
+  p.H = H;
+  p.w_last = w_last;
+  p.out_dim = out_dim;
+  p.store = 1;
+  p.dpre = dpre;
+  p.act16 = (const __half*)act16;
+  p.scale = scale_dev;
+  p.dfeat = dfeat;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NC_CHECK_CUDA(cudaFuncSetAttribute(relu_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  const int sms = nchost::sm_count();
+  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  relu_chain_kernel<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -29,17 +29,25 @@ constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
 constexpr int NTHREADS = 192;
 constexpr uint16_t PAIR_MASK = 0x3;
 
-struct WgradMaps {
-  CUtensorMap dz[3];    // dz_1..dz_3   [Q,512] fp16, box 64 x 64
-  CUtensorMap act[3];   // a_1..a_3
+// One 256 x 256 output tile of one weight gradient: dw[m0 + i, n0 + j] += sum_r dz[r, m0 + i] * act[r, n0 + j].
+// Columns of `act` beyond its extent are zero-filled by TMA, so narrow right-hand sides (the 64-feature encoded
+// input of the ReLU MLPs) use the same tile shape and write back only `n_valid` columns.
+struct WgradJob {
+  CUtensorMap dz;       // [Q, *] fp16 row-major, box 64 x 64
+  CUtensorMap act;      // [Q, *] fp16 row-major, box 64 x 64
+  float* dw;            // fp32, row pitch ldw (accumulated into)
+  float* db;            // fp32 [*] or null: db[m0 + i] += sum_r dz[r, m0 + i]
+  int m0, n0, ldw, n_valid;
+};
+constexpr int MAX_JOBS = 12;
+struct WgradJobs {
+  WgradJob job[MAX_JOBS];
 };
 
 struct WgradParams {
   int Q;
   int nkb;              // ceil(Q / 64)
   int kb_per_split;
-  float* dw[3];         // fp32 [512,512] each (accumulated into)
-  float* db[3];         // fp32 [512]
   const float* scale;   // device scalar: loss scale carried by dz
 };
 
@@ -47,7 +55,7 @@ struct WgradParams {
 // axis: each CTA stages its 128 dz-columns (A, M side) and its 128 activation-columns (B, N side) per 64-row
 // k-block; the leader issues M256 x N256 x K16 MMAs; each CTA's TMEM holds its own 128 output rows.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
+hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -59,15 +67,14 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
   const int split = blockIdx.x >> 1;
-  const int mt = blockIdx.y >> 1, nt = blockIdx.y & 1;   // 256-wide tile coordinates
-  const int layer = blockIdx.z;
+  const WgradJob& job = jobs.job[blockIdx.y];
   const int kb0 = split * p.kb_per_split;
   int kb1 = kb0 + p.kb_per_split;
   if (kb1 > p.nkb) kb1 = p.nkb;
   const int nk = kb1 - kb0;   // may be <= 0 for trailing splits (identical in both CTAs of a pair)
-  const bool with_bias = (nt == 0);
-  const int m0 = mt * 256 + (int)crank * 128;   // this CTA's dz columns  = dW rows
-  const int n0 = nt * 256 + (int)crank * 128;   // this CTA's act columns = dW columns it STAGES (not the ones it owns)
+  const bool with_bias = job.db != nullptr;
+  const int m0 = job.m0 + (int)crank * 128;   // this CTA's dz columns  = dW rows
+  const int n0 = job.n0 + (int)crank * 128;   // this CTA's act columns = dW columns it STAGES (not the ones it owns)
 
   // all-ones tile for the bias-gradient MMA
   for (uint32_t i = tid; i < ATOM_BYTES / 4; i += NTHREADS)
@@ -94,8 +101,8 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
   if (nk > 0) {
     if (warp == 4) {
       // whole warp runs the loop / waits; lane 0 issues (no permanently diverged control warp)
-      const CUtensorMap* ta = &maps.dz[layer];
-      const CUtensorMap* tb = &maps.act[layer];
+      const CUtensorMap* ta = &job.dz;
+      const CUtensorMap* tb = &job.act;
       uint32_t s = 0, ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -143,9 +150,10 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
       const float inv = 1.f / *p.scale;
       mbar_wait(bar_acc, 0);
       tc_fence_after_sync();
-      float* out = p.dw[layer] + (size_t)(m0 + row) * HID + nt * 256;
+      float* out = job.dw + (size_t)(m0 + row) * job.ldw + job.n0;
       const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
-      for (int i = 0; i < 8; ++i) {
+      const int nchunk = job.n_valid >> 5;
+      for (int i = 0; i < nchunk; ++i) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + i * 32, r);
         tmem_ld_wait();
@@ -156,7 +164,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_row + 256, r);
         tmem_ld_wait();
-        atomicAdd(p.db[layer] + m0 + row, __uint_as_float(r[0]) * inv);
+        atomicAdd(job.db + m0 + row, __uint_as_float(r[0]) * inv);
       }
     }
   }
@@ -169,26 +177,30 @@ hidden_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p)
 
 // out[c][k] += sum_r s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
 // 512 threads = 8 row lanes x 64 column groups of 8 (one 16-byte load each), 4 rows in flight per thread.
+template <int WIDTH>
 __global__ void __launch_bounds__(512)
 skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int nc, int Q,
                     int rows_per_block, float* __restrict__ out) {
-  extern __shared__ float s_acc_raw[];   // [8][4][512] floats = 64 KB (dynamic: above the 48 KB static limit)
+  constexpr int HID = WIDTH;                 // row length of x
+  constexpr int CG = WIDTH / 8;              // column groups of 8 (one 16-byte load each)
+  constexpr int RL = 512 / CG;               // row lanes
+  extern __shared__ float s_acc_raw[];   // [RL][4][WIDTH] floats = 64 KB (dynamic: above the 48 KB static limit)
   float (*s_acc)[4][HID] = reinterpret_cast<float (*)[4][HID]>(s_acc_raw);
   const int r0 = blockIdx.x * rows_per_block;
   int r1 = r0 + rows_per_block;
   if (r1 > Q) r1 = Q;
-  const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
   float acc[4][8];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
-  for (int rb = r0 + rl; rb < r1; rb += 32) {
+  for (int rb = r0 + rl; rb < r1; rb += 4 * RL) {
     uint4 v[4];
     float sv[4][4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int r = rb + 8 * u;
+      const int r = rb + RL * u;
       if (r < r1) {
         v[u] = *reinterpret_cast<const uint4*>(x + (size_t)r * HID + cg * 8);
 #pragma unroll
@@ -222,38 +234,22 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
     const int c = e / HID, k = e % HID;
     float t = 0.f;
 #pragma unroll
-    for (int l = 0; l < 8; ++l) t += s_acc[l][c][k];
+    for (int l = 0; l < RL; ++l) t += s_acc[l][c][k];
     atomicAdd(out + c * HID + k, t);
   }
 }
 
 }  // namespace
 
-extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const float* scale_dev,
-                                     float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
-                                     void* stream) {
-  NC_CHECK_ARG(dz16 && act16 && scale_dev && dw1 && db1 && dw2 && db2 && dw3 && db3);
-  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128);
-  WgradMaps maps;
-  for (int l = 0; l < 3; ++l) {
-    // dz16 = [3,Q,512] holding dz_1..dz_3 ; act16 = [4,Q,512] holding a_1..a_4
-    const __half* dz = (const __half*)dz16 + (size_t)l * Q * HID;
-    const __half* a = (const __half*)act16 + (size_t)l * Q * HID;
-    int rc = nchost::make_tmap_16b(&maps.dz[l], dz, (uint64_t)Q, HID, HID, 64, 64);
-    if (rc) return rc;
-    rc = nchost::make_tmap_16b(&maps.act[l], a, (uint64_t)Q, HID, HID, 64, 64);
-    if (rc) return rc;
-  }
+// shared launch: n_jobs pair tiles x Q-slices filling the machine's CTA pairs
+static int launch_wgrad_jobs(WgradJobs& jobs, int n_jobs, int64_t Q, const float* scale_dev, void* stream) {
   WgradParams p{};
   p.Q = (int)Q;
   p.nkb = (int)((Q + 63) / 64);
-  // 12 pair-tiles of 256 x 256; fill the machine's 74 CTA pairs with ~6 Q-slices per tile
-  int splits = (nchost::sm_count() / 2) / 12;
+  int splits = (nchost::sm_count() / 2) / n_jobs;
   if (splits < 1) splits = 1;
   if (splits > p.nkb) splits = p.nkb;
   p.kb_per_split = (p.nkb + splits - 1) / splits;
-  p.dw[0] = dw1; p.dw[1] = dw2; p.dw[2] = dw3;
-  p.db[0] = db1; p.db[1] = db2; p.db[2] = db3;
   p.scale = scale_dev;
   static bool attr_set = false;
   if (!attr_set) {
@@ -261,8 +257,89 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
                                        (int)SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(2 * splits, 4, 3);
-  hidden_wgrad_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
+  dim3 grid(2 * splits, n_jobs, 1);
+  hidden_wgrad_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(jobs, p);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int fill_job(WgradJob& j, const void* dz, int dz_cols, const void* act, int act_cols, int64_t Q, float* dw,
+                    float* db, int m0, int n0, int ldw, int n_valid) {
+  int rc = nchost::make_tmap_16b(&j.dz, dz, (uint64_t)Q, dz_cols, dz_cols, 64, 64);
+  if (rc) return rc;
+  rc = nchost::make_tmap_16b(&j.act, act, (uint64_t)Q, act_cols, act_cols, 64, 64);
+  if (rc) return rc;
+  j.dw = dw; j.db = db; j.m0 = m0; j.n0 = n0; j.ldw = ldw; j.n_valid = n_valid;
+  return 0;
+}
+
+extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const float* scale_dev,
+                                     float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
+                                     void* stream) {
+  NC_CHECK_ARG(dz16 && act16 && scale_dev && dw1 && db1 && dw2 && db2 && dw3 && db3);
+  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128);
+  float* dw[3] = {dw1, dw2, dw3};
+  float* db[3] = {db1, db2, db3};
+  WgradJobs jobs;
+  int n = 0;
+  for (int l = 0; l < 3; ++l) {
+    // dz16 = [3,Q,512] holding dz_1..dz_3 ; act16 = [4,Q,512] holding a_1..a_4
+    const __half* dz = (const __half*)dz16 + (size_t)l * Q * HID;
+    const __half* a = (const __half*)act16 + (size_t)l * Q * HID;
+    for (int mt = 0; mt < 2; ++mt)
+      for (int nt = 0; nt < 2; ++nt) {
+        int rc = fill_job(jobs.job[n++], dz, HID, a, HID, Q, dw[l], nt == 0 ? db[l] : nullptr, mt * 256, nt * 256,
+                          HID, 256);
+        if (rc) return rc;
+      }
+  }
+  return launch_wgrad_jobs(jobs, n, Q, scale_dev, stream);
+}
+
+// Weight gradients of one 256-wide ReLU MLP (reference modules.py:255-306) from the buffers the chain kernels stored.
+//   dz16 [H,Q,256], act16 [H,Q,256], feat16 [Q,64] fp16.  Layer 0: dw_first [256,64] (encoded-input layout) and
+//   db[0]; layers l = 1..H-1: dw[l] with row pitch ldw[l] (its first 256 columns are written) and db[l]; a layer
+//   with skip[l] != 0 also gets dw_skip[l] [256,64] = dz_l^T feat.  All accumulated into (caller zeroes).
+extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* act16, const void* feat16, int64_t Q, int H,
+                                     const float* scale_dev, float* dw_first, float* const* dw, const int* ldw,
+                                     float* const* db, float* const* dw_skip, void* stream) {
+  NC_CHECK_ARG(dz16 && act16 && feat16 && scale_dev && dw_first && dw && ldw && db && dw_skip);
+  NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && H >= 1 && H <= 8);
+  constexpr int W = 256;
+  WgradJobs jobs;
+  int n = 0;
+  for (int l = 0; l < H; ++l) {
+    const __half* dz = (const __half*)dz16 + (size_t)l * Q * W;
+    int rc;
+    if (l == 0) {
+      rc = fill_job(jobs.job[n++], dz, W, feat16, 64, Q, dw_first, db[0], 0, 0, 64, 64);
+    } else {
+      NC_CHECK_ARG(dw[l] && db[l] && ldw[l] >= W);
+      rc = fill_job(jobs.job[n++], dz, W, (const __half*)act16 + (size_t)(l - 1) * Q * W, W, Q, dw[l], db[l], 0, 0,
+                    ldw[l], 256);
+      if (rc == 0 && dw_skip[l]) {
+        NC_CHECK_ARG(n < MAX_JOBS);
+        rc = fill_job(jobs.job[n++], dz, W, feat16, 64, Q, dw_skip[l], nullptr, 0, 0, 64, 64);
+      }
+    }
+    if (rc) return rc;
+    NC_CHECK_ARG(n <= MAX_JOBS);
+  }
+  return launch_wgrad_jobs(jobs, n, Q, scale_dev, stream);
+}
+
+template <int WIDTH>
+static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, float* out, void* stream) {
+  const int blocks = nchost::sm_count() * 2;
+  int rows = (int)((Q + blocks - 1) / blocks);
+  if (rows < 32) rows = 32;
+  const int grid = (int)((Q + rows - 1) / rows);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NC_CHECK_CUDA(cudaFuncSetAttribute(skinny_wgrad_kernel<WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr_set = true;
+  }
+  skinny_wgrad_kernel<WIDTH><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows, out);
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -271,16 +348,13 @@ extern "C" int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, in
                                           float* dw4, void* stream) {
   NC_CHECK_ARG(a4_16 && dy && dw4);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  const int blocks = nchost::sm_count() * 2;
-  int rows = (int)((Q + blocks - 1) / blocks);
-  if (rows < 32) rows = 32;
-  const int grid = (int)((Q + rows - 1) / rows);
-  static bool attr_set2 = false;
-  if (!attr_set2) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(skinny_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    attr_set2 = true;
-  }
-  skinny_wgrad_kernel<<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)a4_16, dy, out_dim, (int)Q, rows, dw4);
-  NC_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_skinny<512>(a4_16, dy, out_dim, Q, dw4, stream);
+}
+
+// dw_last[c,k] += sum_r dpre[r,c] * h[r,k] for the last layer of a 256-wide ReLU MLP (h fp16 [Q,256], c < 4).
+extern "C" int neucam_relu_mlp_head_wgrad(const void* h16, const float* dpre, int out_dim, int64_t Q,
+                                          float* dw_last, void* stream) {
+  NC_CHECK_ARG(h16 && dpre && dw_last);
+  NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
+  return launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, stream);
 }

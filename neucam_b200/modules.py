@@ -305,6 +305,11 @@ class SimpleMLP(nn.Module):
             input_ch = output_ch
 
     def forward(self, x):
+        if x.is_cuda and self.layers[0].out_features == 256:
+            # the uv-mapping / alpha networks: tcgen05 chain kernels (forward, input gradient, weight gradients)
+            from . import relu_mlp
+            if relu_mlp.eligible(self):
+                return relu_mlp.fused_forward(self, x)
         if self.use_encoding:
             x = self.positional_encoding(x).view(-1, self.positional_encoding.out_dim)
         else:
