@@ -101,9 +101,14 @@ int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, 
  * (first layer, hidden layers, with the reference's skip connection modules.py:299-300 as an extra K-block on
  * the encoded input) followed by the out_dim <= 4 output layer and its nonlinearity on CUDA cores.
  *
- * neucam_relu_mlp_fwd: w_stages [S*256,64] fp16 = for every GEMM in order its 256(out) x 64(in) K-blocks;
- *   stage_begin[n_gemm+1] delimits them; a_src[S] says what each K-block multiplies (0..3 = that 64-column block
- *   of the previous activation, 4 = the encoded input).  bias [n_gemm,256]; w_last [out_dim,256], b_last fp32;
+ * The forward runs SPLIT-fp16 (hi + lo pairs for activations and weights, three MMAs per product) because a ReLU
+ * network's gradient is discontinuous in its pre-activations; see csrc/relu_chain.cu.
+ *
+ * neucam_relu_mlp_fwd: w_stages [S*256,64] fp16 = for every GEMM in order its 256(out) x 64(in) K-blocks (hi
+ *   and lo parts of the weights as separate stages); stage_begin[n_gemm+1] delimits them; a_src[S] says what each
+ *   K-block multiplies (0..3 = that 64-column block of the previous activation's hi part, 4 = the encoded input)
+ *   and a_src2[S] whether it also multiplies the lo part of a block (5..8, else 255).  The activation of the
+ *   kernel's operand tile is hi = fp16(h), lo = fp16(h - hi).  bias [n_gemm,256]; w_last [out_dim,256], b_last fp32;
  *   out_kind 0 none / 1 tanh / 2 sigmoid.  Writes y [Q,out_dim] fp32 and, when act16 != NULL, the activations
  *   h_0..h_{H-1} as [H,Q,256] fp16.
  * neucam_relu_mlp_bwd: dpre [Q,out_dim] fp32 = dL/d(output-layer pre-activation); wT_stages = for layer H-1
@@ -114,8 +119,8 @@ int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, 
  *   dz16 / act16 / feat16: dw_first [256,64] and dw_skip[l] [256,64] in encoded-input column order, dw[l] with row
  *   pitch ldw[l] for l >= 1 (its first 256 columns), db[l] [256]; dw_last [out_dim,256] += dpre^T h_{H-1}. */
 int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_stages, int n_gemm, const int* stage_begin,
-                        const uint8_t* a_src, const float* bias, const float* w_last, const float* b_last,
-                        int out_dim, int out_kind, float* y, void* act16, void* stream);
+                        const uint8_t* a_src, const uint8_t* a_src2, const float* bias, const float* w_last,
+                        const float* b_last, int out_dim, int out_kind, float* y, void* act16, void* stream);
 int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_stages, int H, const float* w_last, int out_dim,
                         const void* act16, const float* scale_dev, void* dz16, float* dfeat, void* stream);
 int neucam_relu_mlp_wgrad(const void* dz16, const void* act16, const void* feat16, int64_t Q, int H,

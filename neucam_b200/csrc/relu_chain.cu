@@ -13,6 +13,12 @@
 // the weight-gradient GEMMs.  The encoded input (raw coordinates + NeRF positional encoding, zero-padded to 64
 // features) is its own 16 KB operand tile, so the first layer and the skip connection are tensor-core GEMMs too.
 //
+// Precision.  A ReLU network's gradient is discontinuous in its pre-activations: with plain fp16 operands the
+// forward's ~4e-4 relative error in z flips ~3e-4 of the ReLU gates against the fp32 reference, which alone puts
+// ~2 % error on every gradient (measured).  The FORWARD therefore runs split-fp16: activations and weights are
+// carried as hi + lo fp16 pairs and each product is three MMAs (hi*hi + lo*hi + hi*lo, fp32 accumulation), i.e.
+// ~2^-21 relative; the backward (smooth in its operands) stays single fp16 with a power-of-two loss scale.
+//
 // Warp roles: 0..3 epilogue, 4 TMA producer, 5 MMA issuer + TMEM owner (control warps have the highest ids).
 #include "host_util.h"
 #include "tc05.cuh"
@@ -23,16 +29,18 @@ namespace {
 
 constexpr int WID = 256;
 constexpr int TILE_M = 128;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE_BWD = 4;                    // backward: 4 weight stages in the 128 KB ring region
+constexpr int NSTAGE_FWD = 2;                    // forward: 2 stages; the other 64 KB hold the lo operand tile
 constexpr int MAX_GEMM = 8;
-constexpr int MAX_STAGES = 40;
+constexpr int MAX_STAGES = 64;
 constexpr int FEAT = 64;
 constexpr uint32_t KB_BYTES = TILE_M * 128;      // one k-block of the operand tile: 128 rows x 64 fp16
 constexpr uint32_t STAGE_BYTES = WID * 128;      // one weight stage: 256 rows x 64 fp16
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_F = OFF_A + 4 * KB_BYTES;
 constexpr uint32_t OFF_W = OFF_F + KB_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_W + NSTAGE * STAGE_BYTES;      // float [MAX_GEMM][256] (forward)
+constexpr uint32_t OFF_ALO = OFF_W + NSTAGE_FWD * STAGE_BYTES;   // forward: lo halves of the operand tile
+constexpr uint32_t OFF_BIAS = OFF_W + NSTAGE_BWD * STAGE_BYTES;  // float [MAX_GEMM][256] (forward)
 constexpr uint32_t OFF_HEAD = OFF_BIAS + MAX_GEMM * WID * 4;     // float [4][256] last-layer weights
 constexpr uint32_t OFF_BAR = OFF_HEAD + 4 * WID * 4;
 constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
@@ -52,7 +60,8 @@ struct ReluMaps {
 struct ReluParams {
   int Q, ntiles, n_gemm, H;            // H = number of saved activation layers (= forward GEMMs)
   int stage_begin[MAX_GEMM + 1];
-  uint8_t a_src[MAX_STAGES];           // per stage: 0..3 = k-block of the operand tile, 4 = encoded-input tile
+  uint8_t a_src[MAX_STAGES];           // per stage: 0..3 = k-block of the operand tile, 4 = encoded-input tile,
+  uint8_t a_src2[MAX_STAGES];          //   5..8 = k-block of the lo operand tile; a_src2 = 255: single product
   int feat_last_gemm;                  // forward: last GEMM of a tile that reads the encoded-input tile
   const float* bias;                   // forward: [n_gemm][256]
   const float* w_last;                 // [out_dim][256] fp32
@@ -102,12 +111,13 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t NSTAGE = BWD ? NSTAGE_BWD : NSTAGE_FWD;
 
   if (!BWD)
     for (int i = tid; i < p.n_gemm * WID; i += NTHREADS) s_bias[i] = p.bias[i];
   for (int i = tid; i < 4 * WID; i += NTHREADS) s_head[i] = (i < p.out_dim * WID) ? p.w_last[i] : 0.f;
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (uint32_t s = 0; s < NSTAGE; ++s) {
       mbar_init(bar(BAR_WFULL + s), 1);
       mbar_init(bar(BAR_WEMPTY + s), 1);
     }
@@ -167,14 +177,20 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           mbar_wait(bar(BAR_WFULL + slot), ph);
           tc_fence_after_sync();
           if (lane == 0) {
-            const uint32_t src = p.a_src[s];
-            const uint32_t a_addr = base + (src == 4 ? OFF_F : OFF_A + src * KB_BYTES);
             const uint32_t b_addr = base + OFF_W + slot * STAGE_BYTES;
+            const uint32_t srcs[2] = {p.a_src[s], p.a_src2[s]};
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16)
-              umma_f16_ss(tmem_base, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
-                          make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc,
-                          (s > p.stage_begin[g] || k16 > 0) ? 1u : 0u);
+            for (int t = 0; t < 2; ++t) {
+              const uint32_t src = srcs[t];
+              if (src == 255u) continue;
+              const uint32_t a_addr = base + (src == 4 ? OFF_F : src < 4 ? OFF_A + src * KB_BYTES
+                                                                         : OFF_ALO + (src - 5) * KB_BYTES);
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16)
+                umma_f16_ss(tmem_base, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
+                            make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc,
+                            (s > p.stage_begin[g] || t > 0 || k16 > 0) ? 1u : 0u);
+            }
             umma_commit(bar(BAR_WEMPTY + slot));
           }
           __syncwarp();
@@ -280,6 +296,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           uint32_t w[16];
           if (!BWD) {
             const float* bz = s_bias + g * WID + c * 32;
+            uint32_t wl[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float h0 = fmaxf(__uint_as_float(r[2 * j]) + bz[2 * j], 0.f);
@@ -292,7 +309,10 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
                 }
               }
               w[j] = pack_h2(h0, h1);
+              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              wl[j] = pack_h2(h0 - hi.x, h1 - hi.y);
             }
+            if (!last) write_chunk(base + OFF_ALO, c, row, wl);
           } else {
             const uint32_t* mw = reinterpret_cast<const uint32_t*>(m);
 #pragma unroll
@@ -342,14 +362,16 @@ int check_stage_plan(int n_gemm, const int* stage_begin) {
 }  // namespace
 
 // forward of one ReLU MLP.  feat16 [Q,64] fp16 (encoded input, zero padded); w_stages [S*256,64] fp16 (per GEMM:
-// its 256 x 64 K-blocks in order); stage_begin[n_gemm+1]; a_src[S] (0..3 operand k-block, 4 encoded input);
+// its 256 x 64 K-blocks in order); stage_begin[n_gemm+1]; a_src[S] (0..3 operand k-block, 4 encoded input) and
+// a_src2[S] (5..8: the stage ALSO multiplies that k-block of the lo operand tile; 255: it does not);
 // bias [n_gemm,256]; w_last [out_dim,256], b_last [out_dim] fp32; out_kind 0 none / 1 tanh / 2 sigmoid;
 // y [Q,out_dim] fp32; act16 [n_gemm,Q,256] fp16 or NULL (saved activations for the backward pass).
 extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_stages, int n_gemm,
-                                   const int* stage_begin, const uint8_t* a_src, const float* bias,
+                                   const int* stage_begin, const uint8_t* a_src, const uint8_t* a_src2,
+                                   const float* bias,
                                    const float* w_last, const float* b_last, int out_dim, int out_kind, float* y,
                                    void* act16, void* stream) {
-  NC_CHECK_ARG(feat16 && w_stages && stage_begin && a_src && bias && w_last && b_last && y);
+  NC_CHECK_ARG(feat16 && w_stages && stage_begin && a_src && a_src2 && bias && w_last && b_last && y);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && out_kind >= 0 && out_kind <= 2);
   NC_CHECK_ARG(check_stage_plan(n_gemm, stage_begin) == 0);
   ReluMaps maps;
@@ -366,9 +388,10 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
     if (rc) return rc;
     p.stage_begin[g] = stage_begin[g];
     for (int s = stage_begin[g]; s < stage_begin[g + 1]; ++s) {
-      NC_CHECK_ARG(a_src[s] <= 4);
-      NC_CHECK_ARG(g > 0 || a_src[s] == 4);     // the first GEMM reads the encoded input only
+      NC_CHECK_ARG(a_src[s] <= 4 && (a_src2[s] == 255 || (a_src2[s] >= 5 && a_src2[s] <= 8)));
+      NC_CHECK_ARG(g > 0 || (a_src[s] == 4 && a_src2[s] == 255));   // the first GEMM reads the encoded input only
       p.a_src[s] = a_src[s];
+      p.a_src2[s] = a_src2[s];
       if (a_src[s] == 4) p.feat_last_gemm = g;
     }
   }
@@ -419,7 +442,10 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
     if (rc) return rc;
   }
   for (int g = 0; g <= n_gemm; ++g) p.stage_begin[g] = 4 * g;
-  for (int s = 0; s < 4 * n_gemm; ++s) p.a_src[s] = (uint8_t)(s & 3);
+  for (int s = 0; s < 4 * n_gemm; ++s) {
+    p.a_src[s] = (uint8_t)(s & 3);
+    p.a_src2[s] = 255;
+  }
   p.Q = (int)Q;
   p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
   p.n_gemm = n_gemm;

@@ -7,11 +7,12 @@ and every weight / bias gradient come from `csrc/relu_chain.cu` + `csrc/wgrad.cu
 
 Encoded-input tile (`feat`, [Q,64], built here with torch elementwise ops so that autograd carries the gradient
 back through the positional encoding to the coordinates):
-    columns [0,E)    the reference's network input: raw (t,y,x), then the NeRF encoding (modules.py:567-580);
-                     the raw coordinates are rounded to fp16 ("hi" part) ...
-    columns [E,E+3)  ... and their fp16 rounding residual ("lo" part) rides along as three more features that
-                     multiply the same weight columns, so the first layer sees the coordinates to ~2^-22
-    columns [E+3,64) zero
+    columns [0,E)    the reference's network input: raw (t,y,x), then the NeRF encoding (modules.py:567-580),
+                     rounded to fp16 ("hi" part) ...
+    columns [E,2E)   ... and the fp16 rounding residual ("lo" part) of every feature, as E more features that
+                     multiply the same weight columns, so the first layer sees its input to ~2^-22
+    columns [2E,64)  zero
+The forward is split-fp16 throughout (see csrc/relu_chain.cu): weights go in as hi and lo stages too.
 """
 import ctypes
 
@@ -30,7 +31,7 @@ def eligible(module):
     if module.in_dim != 3 or L < 3 or L > 9 or module.last_nonlinear not in OUT_KINDS:
         return False
     E = module.positional_encoding.out_dim if module.use_encoding else module.in_dim
-    if E + 3 > FEAT:
+    if 2 * E > FEAT:
         return False
     skips = [i for i in module.skip_layer if i < L]
     if any(i < 1 or i > L - 2 for i in skips):
@@ -44,12 +45,20 @@ def eligible(module):
     return True
 
 
-def _encoded_block(w, E):
-    """[256,E] weight columns that multiply the encoded input -> [256,64] in the feat column layout."""
+def _encoded_block(w, E, with_lo=True):
+    """[256,E] weight columns that multiply the encoded input -> [256,64] in the feat column layout (the same
+    weights multiply the hi and, when with_lo, the lo half of the features)."""
     out = w.new_zeros((w.shape[0], FEAT))
     out[:, :E] = w
-    out[:, E:E + 3] = w[:, 0:3]
+    if with_lo:
+        out[:, E:2 * E] = w
     return out
+
+
+def _split(w):
+    """fp32 -> (hi, lo) with hi = fp16(w), lo = fp16(w - hi), both returned as fp32 tensors holding fp16 values."""
+    hi = w.to(torch.float16).float()
+    return hi, (w - hi).to(torch.float16).float()
 
 
 def _k_blocks(w):
@@ -67,13 +76,21 @@ class _ReluMLPFunction(torch.autograd.Function):
         Q = feat.shape[0]
         dev = feat.device
         feat16 = feat.to(torch.float16).contiguous()
-        blocks, stage_begin, a_src = [_encoded_block(ws[0], E)], [0, 1], [4]
+        # stage plan: every weight block as a hi stage (x hi and lo activations) and a lo stage (x hi activations)
+        w0_hi, w0_lo = _split(ws[0])
+        blocks = [_encoded_block(w0_hi, E), _encoded_block(w0_lo, E, with_lo=False)]
+        stage_begin, a_src, a_src2 = [0, 2], [4, 4], [255, 255]
         for l in range(1, H):
-            blocks.append(_k_blocks(ws[l][:, :WID]))
-            a_src += [0, 1, 2, 3]
+            w_hi, w_lo = _split(ws[l])
+            kb_hi, kb_lo = _k_blocks(w_hi[:, :WID]).view(4, WID, 64), _k_blocks(w_lo[:, :WID]).view(4, WID, 64)
+            for kb in range(4):
+                blocks += [kb_hi[kb], kb_lo[kb]]
+                a_src += [kb, kb]
+                a_src2 += [5 + kb, 255]
             if l in skips:
-                blocks.append(_encoded_block(ws[l][:, WID:], E))
-                a_src.append(4)
+                blocks += [_encoded_block(w_hi[:, WID:], E), _encoded_block(w_lo[:, WID:], E, with_lo=False)]
+                a_src += [4, 4]
+                a_src2 += [255, 255]
             stage_begin.append(len(a_src))
         w_stages = torch.cat(blocks, 0).to(torch.float16).contiguous()
         bias = torch.stack(bs[:H]).contiguous()
@@ -84,7 +101,8 @@ class _ReluMLPFunction(torch.autograd.Function):
         y = torch.empty((Q, out_dim), dtype=torch.float32, device=dev)
         sb = (ctypes.c_int * len(stage_begin))(*stage_begin)
         src = (ctypes.c_uint8 * len(a_src))(*a_src)
-        rc = _lib.lib().neucam_relu_mlp_fwd(_lib.ptr(feat16), ctypes.c_int64(Q), _lib.ptr(w_stages), H, sb, src,
+        src2 = (ctypes.c_uint8 * len(a_src2))(*a_src2)
+        rc = _lib.lib().neucam_relu_mlp_fwd(_lib.ptr(feat16), ctypes.c_int64(Q), _lib.ptr(w_stages), H, sb, src, src2,
                                             _lib.ptr(bias), _lib.ptr(w_last), _lib.ptr(b_last), out_dim, out_kind,
                                             _lib.ptr(y), _lib.ptr(act16), _lib.cur_stream())
         _lib.check(rc, "neucam_relu_mlp_fwd")
@@ -113,8 +131,7 @@ class _ReluMLPFunction(torch.autograd.Function):
         blocks = [_k_blocks(ws[l][:, :WID].t()) for l in range(H - 1, 0, -1)]
         if want_dfeat:
             w0t = ws[0].new_zeros((WID, WID))
-            w0t[:FEAT] = _encoded_block(ws[0], E).t()
-            w0t[E:E + 3] = 0.0      # the residual features are constants: no gradient through them
+            w0t[:E] = ws[0].t()     # rows E..2E (the residual features) stay zero: they are constants
             blocks.append(_k_blocks(w0t))
         wT_stages = (torch.cat(blocks, 0) if blocks else ws[0].new_zeros((4 * WID, 64))).to(torch.float16).contiguous()
         w_last = ws[H].contiguous()
@@ -144,7 +161,7 @@ class _ReluMLPFunction(torch.autograd.Function):
                                            _lib.ptr(dw[H]), _lib.cur_stream())
         _lib.check(rc, "neucam_relu_mlp_head_wgrad")
         db[H] = dpre.sum(0)
-        fold = lambda e: torch.cat((e[:, :3] + e[:, E:E + 3], e[:, 3:E]), 1)      # hi + lo columns of the coordinates
+        fold = lambda e: e[:, :E] + e[:, E:2 * E]      # hi + lo halves of the features
         dw[0] = fold(enc[0])
         for l, slot in skip_slot.items():
             dw[l][:, WID:] = fold(enc[slot])
@@ -163,11 +180,10 @@ def fused_forward(module, x):
         E = module.in_dim
         enc = x.reshape(-1, E)
     enc = enc.float()
-    raw = enc[:, :3]
-    hi = raw.to(torch.float16).float()
-    lo = (raw - hi).detach()
-    raw_hi = raw + (hi - raw).detach()          # value = the fp16-representable part, gradient = identity
-    feat = torch.cat((raw_hi, enc[:, 3:], lo, enc.new_zeros((enc.shape[0], FEAT - E - 3))), 1)
+    hi = enc.detach().to(torch.float16).float()
+    lo = enc.detach() - hi
+    enc_hi = enc + (hi - enc.detach())          # value = the fp16-representable part, gradient = identity
+    feat = torch.cat((enc_hi, lo, enc.new_zeros((enc.shape[0], FEAT - 2 * E))), 1)
     L = module.num_layer
     skips = tuple(i for i in module.skip_layer if i < L)
     params = []
