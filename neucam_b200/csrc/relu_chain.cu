@@ -7,7 +7,7 @@
 //
 // A CTA owns a 128-sample tile for the whole chain: the activation tile lives in shared memory as the K-major
 // SWIZZLE_128B A operand (4 k-blocks of 128 x 64 fp16), every layer is 4 (+1 for a skip connection) weight
-// "stages" of 256 x 64 fp16 streamed through a 4-deep TMA ring, accumulated by M128 x N256 x K16 MMAs into 256
+// "stages" of 256 x 64 fp16 streamed through a 2-deep TMA ring, accumulated by M128 x N256 x K16 MMAs into 256
 // TMEM columns, drained by 4 epilogue warps (thread = sample row) that apply bias + ReLU (forward) or the ReLU
 // mask of the saved activation (backward), write the next operand tile in place and TMA-store it to HBM for
 // the weight-gradient GEMMs.  The encoded input (raw coordinates + NeRF positional encoding, zero-padded to 64
@@ -17,7 +17,11 @@
 // forward's ~4e-4 relative error in z flips ~3e-4 of the ReLU gates against the fp32 reference, which alone puts
 // ~2 % error on every gradient (measured).  The FORWARD therefore runs split-fp16: activations and weights are
 // carried as hi + lo fp16 pairs and each product is three MMAs (hi*hi + lo*hi + hi*lo, fp32 accumulation), i.e.
-// ~2^-21 relative; the backward (smooth in its operands) stays single fp16 with a power-of-two loss scale.
+// ~2^-21 relative.  The backward is smooth in its operands, but the rigidity loss (utils.py:402-454) differences
+// the network at neighbouring pixels, so per-sample rounding of dz / h (random, ~3e-4) is amplified ~30x in the
+// summed weight gradients (measured 1.7e-2 on a first-layer bias, 77x amplification): dz, the transposed weights
+// and the saved activations are carried as hi + lo pairs as well (three MMAs per product), with a power-of-two
+// loss scale on dz.
 //
 // Warp roles: 0..3 epilogue, 4 TMA producer, 5 MMA issuer + TMEM owner (control warps have the highest ids).
 #include "host_util.h"
@@ -29,8 +33,7 @@ namespace {
 
 constexpr int WID = 256;
 constexpr int TILE_M = 128;
-constexpr int NSTAGE_BWD = 4;                    // backward: 4 weight stages in the 128 KB ring region
-constexpr int NSTAGE_FWD = 2;                    // forward: 2 stages; the other 64 KB hold the lo operand tile
+constexpr int NSTAGE = 2;                        // weight stages in flight (64 KB); the lo operand tile takes 64 KB
 constexpr int MAX_GEMM = 8;
 constexpr int MAX_STAGES = 64;
 constexpr int FEAT = 64;
@@ -39,8 +42,8 @@ constexpr uint32_t STAGE_BYTES = WID * 128;      // one weight stage: 256 rows x
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_F = OFF_A + 4 * KB_BYTES;
 constexpr uint32_t OFF_W = OFF_F + KB_BYTES;
-constexpr uint32_t OFF_ALO = OFF_W + NSTAGE_FWD * STAGE_BYTES;   // forward: lo halves of the operand tile
-constexpr uint32_t OFF_BIAS = OFF_W + NSTAGE_BWD * STAGE_BYTES;  // float [MAX_GEMM][256] (forward)
+constexpr uint32_t OFF_ALO = OFF_W + NSTAGE * STAGE_BYTES;       // lo halves of the operand tile
+constexpr uint32_t OFF_BIAS = OFF_ALO + 4 * KB_BYTES;            // float [MAX_GEMM][256] (forward)
 constexpr uint32_t OFF_HEAD = OFF_BIAS + MAX_GEMM * WID * 4;     // float [4][256] last-layer weights
 constexpr uint32_t OFF_BAR = OFF_HEAD + 4 * WID * 4;
 constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
@@ -54,7 +57,8 @@ enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_AREADY = 9, BAR_FFULL = 1
 struct ReluMaps {
   CUtensorMap feat;            // [Q,64] fp16, box 64 x 128 (forward)
   CUtensorMap w;               // weight stages [S*256, 64] fp16, box 64 x 256
-  CUtensorMap act[MAX_GEMM];   // forward: h_l ; backward: dz_l   ([Q,256] fp16, box 64 x 128)
+  CUtensorMap act[MAX_GEMM];   // forward: h_l ; backward: dz_l   ([Q,256] fp16, box 64 x 128): hi parts
+  CUtensorMap act_lo[MAX_GEMM];  // the same tensors' lo parts (fp16 rounding residuals)
 };
 
 struct ReluParams {
@@ -111,13 +115,12 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t NSTAGE = BWD ? NSTAGE_BWD : NSTAGE_FWD;
 
   if (!BWD)
     for (int i = tid; i < p.n_gemm * WID; i += NTHREADS) s_bias[i] = p.bias[i];
   for (int i = tid; i < 4 * WID; i += NTHREADS) s_head[i] = (i < p.out_dim * WID) ? p.w_last[i] : 0.f;
   if (tid == 0) {
-    for (uint32_t s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(bar(BAR_WFULL + s), 1);
       mbar_init(bar(BAR_WEMPTY + s), 1);
     }
@@ -231,7 +234,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 4; ++q) m[q] = valid ? *reinterpret_cast<const uint4*>(mrow + c * 32 + q * 8) : make_uint4(0, 0, 0, 0);
           const uint32_t* mw = reinterpret_cast<const uint32_t*>(m);
-          uint32_t w[16];
+          uint32_t w[16], wl[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = c * 32 + 2 * j;
@@ -244,13 +247,19 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             if ((mw[j] & 0x7FFFu) == 0u) d0 = 0.f;            // h == 0  <=>  ReLU closed (h is never negative)
             if ((mw[j] & 0x7FFF0000u) == 0u) d1 = 0.f;
             w[j] = pack_h2_sat(d0, d1);
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
           }
           write_chunk(a_base, c, row, w);
+          write_chunk(base + OFF_ALO, c, row, wl);
         }
         fence_proxy_async_smem();
         epi_bar_sync();
         if (tid == 0 && p.store) {
-          for (int kb = 0; kb < 4; ++kb) tma_store_2d(&maps.act[p.H - 1], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
+          for (int kb = 0; kb < 4; ++kb) {
+            tma_store_2d(&maps.act[p.H - 1], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
+            tma_store_2d(&maps.act_lo[p.H - 1], base + OFF_ALO + kb * KB_BYTES, kb * 64, tile * TILE_M);
+          }
           tma_store_commit();
         }
         mbar_arrive(bar(BAR_AREADY));
@@ -293,10 +302,9 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_row + c * 32, r);
           tmem_ld_wait();
-          uint32_t w[16];
+          uint32_t w[16], wl[16];
           if (!BWD) {
             const float* bz = s_bias + g * WID + c * 32;
-            uint32_t wl[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float h0 = fmaxf(__uint_as_float(r[2 * j]) + bz[2 * j], 0.f);
@@ -312,7 +320,6 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
               const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
               wl[j] = pack_h2(h0 - hi.x, h1 - hi.y);
             }
-            if (!last) write_chunk(base + OFF_ALO, c, row, wl);
           } else {
             const uint32_t* mw = reinterpret_cast<const uint32_t*>(m);
 #pragma unroll
@@ -321,15 +328,21 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
               if ((mw[j] & 0x7FFFu) == 0u) d0 = 0.f;
               if ((mw[j] & 0x7FFF0000u) == 0u) d1 = 0.f;
               w[j] = pack_h2_sat(d0, d1);
+              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
             }
           }
           write_chunk(a_base, c, row, w);
+          write_chunk(base + OFF_ALO, c, row, wl);
         }
         tc_fence_before_sync();
         fence_proxy_async_smem();
         epi_bar_sync();
         if (tid == 0 && p.store) {
-          for (int kb = 0; kb < 4; ++kb) tma_store_2d(&maps.act[layer], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
+          for (int kb = 0; kb < 4; ++kb) {
+            tma_store_2d(&maps.act[layer], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
+            tma_store_2d(&maps.act_lo[layer], base + OFF_ALO + kb * KB_BYTES, kb * 64, tile * TILE_M);
+          }
           tma_store_commit();
         }
         if (!BWD || !last) mbar_arrive(bar(BAR_AREADY));
@@ -365,15 +378,16 @@ int check_stage_plan(int n_gemm, const int* stage_begin) {
 // its 256 x 64 K-blocks in order); stage_begin[n_gemm+1]; a_src[S] (0..3 operand k-block, 4 encoded input) and
 // a_src2[S] (5..8: the stage ALSO multiplies that k-block of the lo operand tile; 255: it does not);
 // bias [n_gemm,256]; w_last [out_dim,256], b_last [out_dim] fp32; out_kind 0 none / 1 tanh / 2 sigmoid;
-// y [Q,out_dim] fp32; act16 [n_gemm,Q,256] fp16 or NULL (saved activations for the backward pass).
+// y [Q,out_dim] fp32; act16 / act_lo16 [n_gemm,Q,256] fp16 or both NULL (saved activations, hi and lo parts).
 extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_stages, int n_gemm,
                                    const int* stage_begin, const uint8_t* a_src, const uint8_t* a_src2,
                                    const float* bias,
                                    const float* w_last, const float* b_last, int out_dim, int out_kind, float* y,
-                                   void* act16, void* stream) {
+                                   void* act16, void* act_lo16, void* stream) {
   NC_CHECK_ARG(feat16 && w_stages && stage_begin && a_src && a_src2 && bias && w_last && b_last && y);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && out_kind >= 0 && out_kind <= 2);
   NC_CHECK_ARG(check_stage_plan(n_gemm, stage_begin) == 0);
+  NC_CHECK_ARG((act16 == nullptr) == (act_lo16 == nullptr));
   ReluMaps maps;
   ReluParams p{};
   const int S = stage_begin[n_gemm];
@@ -385,6 +399,9 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   for (int g = 0; g < n_gemm; ++g) {
     const __half* a = act16 ? (const __half*)act16 + (size_t)g * Q * WID : (const __half*)feat16;
     rc = nchost::make_tmap_16b(&maps.act[g], a, (uint64_t)Q, act16 ? WID : FEAT, act16 ? WID : FEAT, TILE_M, 64);
+    if (rc) return rc;
+    const __half* al = act_lo16 ? (const __half*)act_lo16 + (size_t)g * Q * WID : (const __half*)feat16;
+    rc = nchost::make_tmap_16b(&maps.act_lo[g], al, (uint64_t)Q, act16 ? WID : FEAT, act16 ? WID : FEAT, TILE_M, 64);
     if (rc) return rc;
     p.stage_begin[g] = stage_begin[g];
     for (int s = stage_begin[g]; s < stage_begin[g + 1]; ++s) {
@@ -422,29 +439,34 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
 
 // backward of one ReLU MLP w.r.t. its activations (and, when dfeat is given, its encoded input).
 // dpre [Q,out_dim] fp32 = dL/d(last layer's pre-activation); act16 [H,Q,256] saved by the forward;
-// wT_stages: per backward GEMM (layer H-1 down to 1, then layer 0 when dfeat != NULL) the 256 x 64 K-blocks of the
-// TRANSPOSED weight (rows = input feature, zero padded to 256); scale_dev: power-of-two loss scale applied to dz;
-// dz16 [H,Q,256] fp16 out (scaled); dfeat [Q,64] fp32 out or NULL.
+// wT_stages: per backward GEMM (layer H-1 down to 1, then layer 0 when dfeat != NULL) the four 256 x 64 K-blocks of
+// the TRANSPOSED weight (rows = input feature, zero padded to 256), each as a hi stage followed by a lo stage;
+// scale_dev: power-of-two loss scale applied to dz;
+// dz16 / dz_lo16 [H,Q,256] fp16 out (scaled; hi and lo parts); dfeat [Q,64] fp32 out or NULL.
 extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_stages, int H, const float* w_last,
                                    int out_dim, const void* act16, const float* scale_dev, void* dz16,
-                                   float* dfeat, void* stream) {
-  NC_CHECK_ARG(dpre && wT_stages && w_last && act16 && scale_dev && dz16);
+                                   void* dz_lo16, float* dfeat, void* stream) {
+  NC_CHECK_ARG(dpre && wT_stages && w_last && act16 && scale_dev && dz16 && dz_lo16);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && H >= 1 && H <= MAX_GEMM);
   const int n_gemm = (H - 1) + (dfeat ? 1 : 0);
   ReluMaps maps;
   ReluParams p{};
   int rc = nchost::make_tmap_16b(&maps.feat, dz16, (uint64_t)Q, WID, WID, TILE_M, 64);   // unused in this direction
   if (rc) return rc;
-  rc = nchost::make_tmap_16b(&maps.w, wT_stages, (uint64_t)(n_gemm > 0 ? n_gemm : 1) * 4 * WID, 64, 64, WID, 64);
+  rc = nchost::make_tmap_16b(&maps.w, wT_stages, (uint64_t)(n_gemm > 0 ? n_gemm : 1) * 8 * WID, 64, 64, WID, 64);
   if (rc) return rc;
   for (int l = 0; l < H; ++l) {
     rc = nchost::make_tmap_16b(&maps.act[l], (const __half*)dz16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, TILE_M, 64);
     if (rc) return rc;
+    rc = nchost::make_tmap_16b(&maps.act_lo[l], (const __half*)dz_lo16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, TILE_M, 64);
+    if (rc) return rc;
   }
-  for (int g = 0; g <= n_gemm; ++g) p.stage_begin[g] = 4 * g;
-  for (int s = 0; s < 4 * n_gemm; ++s) {
-    p.a_src[s] = (uint8_t)(s & 3);
-    p.a_src2[s] = 255;
+  // per K-block: a hi stage (x dz_hi and dz_lo) and a lo stage (x dz_hi)
+  for (int g = 0; g <= n_gemm; ++g) p.stage_begin[g] = 8 * g;
+  for (int s = 0; s < 8 * n_gemm; ++s) {
+    const int kb = (s >> 1) & 3;
+    p.a_src[s] = (uint8_t)kb;
+    p.a_src2[s] = (s & 1) ? (uint8_t)255 : (uint8_t)(5 + kb);
   }
   p.Q = (int)Q;
   p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);

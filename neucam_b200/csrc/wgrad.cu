@@ -39,7 +39,7 @@ struct WgradJob {
   float* db;            // fp32 [*] or null: db[m0 + i] += sum_r dz[r, m0 + i]
   int m0, n0, ldw, n_valid;
 };
-constexpr int MAX_JOBS = 12;
+constexpr int MAX_JOBS = 24;
 struct WgradJobs {
   WgradJob job[MAX_JOBS];
 };
@@ -297,33 +297,44 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
 }
 
 // Weight gradients of one 256-wide ReLU MLP (reference modules.py:255-306) from the buffers the chain kernels stored.
-//   dz16 [H,Q,256], act16 [H,Q,256], feat16 [Q,64] fp16.  Layer 0: dw_first [256,64] (encoded-input layout) and
-//   db[0]; layers l = 1..H-1: dw[l] with row pitch ldw[l] (its first 256 columns are written) and db[l]; a layer
-//   with skip[l] != 0 also gets dw_skip[l] [256,64] = dz_l^T feat.  All accumulated into (caller zeroes).
-extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* act16, const void* feat16, int64_t Q, int H,
-                                     const float* scale_dev, float* dw_first, float* const* dw, const int* ldw,
-                                     float* const* db, float* const* dw_skip, void* stream) {
-  NC_CHECK_ARG(dz16 && act16 && feat16 && scale_dev && dw_first && dw && ldw && db && dw_skip);
+//   dz16 / dz_lo16 [H,Q,256], act16 / act_lo16 [H,Q,256] (hi and lo fp16 parts), feat16 [Q,64] fp16.
+//   Layer 0: dw_first [256,64] (encoded-input layout) and db[0]; layers l = 1..H-1: dw[l] with row pitch ldw[l]
+//   (its first 256 columns are written) and db[l]; a layer with dw_skip[l] != NULL also gets that [256,64] =
+//   dz_l^T feat.  Every product is split: (dz_hi + dz_lo)^T h_hi + dz_hi^T h_lo.  All accumulated into (caller zeroes).
+extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, const void* act16, const void* act_lo16,
+                                     const void* feat16, int64_t Q, int H, const float* scale_dev, float* dw_first,
+                                     float* const* dw, const int* ldw, float* const* db, float* const* dw_skip,
+                                     void* stream) {
+  NC_CHECK_ARG(dz16 && dz_lo16 && act16 && act_lo16 && feat16 && scale_dev && dw_first && dw && ldw && db && dw_skip);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && H >= 1 && H <= 8);
   constexpr int W = 256;
   WgradJobs jobs;
   int n = 0;
+  auto add = [&](const void* dz, const void* act, int act_cols, float* w, float* b, int pitch, int n_valid) -> int {
+    if (n >= MAX_JOBS) return NEUCAM_ERR_BAD_ARG;
+    return fill_job(jobs.job[n++], dz, W, act, act_cols, Q, w, b, 0, 0, pitch, n_valid);
+  };
   for (int l = 0; l < H; ++l) {
-    const __half* dz = (const __half*)dz16 + (size_t)l * Q * W;
-    int rc;
+    const __half* dzh = (const __half*)dz16 + (size_t)l * Q * W;
+    const __half* dzl = (const __half*)dz_lo16 + (size_t)l * Q * W;
+    int rc = 0;
     if (l == 0) {
-      rc = fill_job(jobs.job[n++], dz, W, feat16, 64, Q, dw_first, db[0], 0, 0, 64, 64);
+      NC_CHECK_ARG(db[0]);
+      rc = add(dzh, feat16, 64, dw_first, db[0], 64, 64);
+      if (!rc) rc = add(dzl, feat16, 64, dw_first, db[0], 64, 64);
     } else {
       NC_CHECK_ARG(dw[l] && db[l] && ldw[l] >= W);
-      rc = fill_job(jobs.job[n++], dz, W, (const __half*)act16 + (size_t)(l - 1) * Q * W, W, Q, dw[l], db[l], 0, 0,
-                    ldw[l], 256);
-      if (rc == 0 && dw_skip[l]) {
-        NC_CHECK_ARG(n < MAX_JOBS);
-        rc = fill_job(jobs.job[n++], dz, W, feat16, 64, Q, dw_skip[l], nullptr, 0, 0, 64, 64);
+      const __half* ah = (const __half*)act16 + (size_t)(l - 1) * Q * W;
+      const __half* al = (const __half*)act_lo16 + (size_t)(l - 1) * Q * W;
+      rc = add(dzh, ah, W, dw[l], db[l], ldw[l], 256);
+      if (!rc) rc = add(dzl, ah, W, dw[l], db[l], ldw[l], 256);
+      if (!rc) rc = add(dzh, al, W, dw[l], nullptr, ldw[l], 256);
+      if (!rc && dw_skip[l]) {
+        rc = add(dzh, feat16, 64, dw_skip[l], nullptr, 64, 64);
+        if (!rc) rc = add(dzl, feat16, 64, dw_skip[l], nullptr, 64, 64);
       }
     }
     if (rc) return rc;
-    NC_CHECK_ARG(n <= MAX_JOBS);
   }
   return launch_wgrad_jobs(jobs, n, Q, scale_dev, stream);
 }
@@ -351,10 +362,13 @@ extern "C" int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, in
   return launch_skinny<512>(a4_16, dy, out_dim, Q, dw4, stream);
 }
 
-// dw_last[c,k] += sum_r dpre[r,c] * h[r,k] for the last layer of a 256-wide ReLU MLP (h fp16 [Q,256], c < 4).
-extern "C" int neucam_relu_mlp_head_wgrad(const void* h16, const float* dpre, int out_dim, int64_t Q,
-                                          float* dw_last, void* stream) {
-  NC_CHECK_ARG(h16 && dpre && dw_last);
+// dw_last[c,k] += sum_r dpre[r,c] * (h[r,k] + h_lo[r,k]) for the last layer of a 256-wide ReLU MLP
+// (h, h_lo fp16 [Q,256]; c < 4).
+extern "C" int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, const float* dpre, int out_dim,
+                                          int64_t Q, float* dw_last, void* stream) {
+  NC_CHECK_ARG(h16 && h_lo16 && dpre && dw_last);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  return launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, stream);
+  int rc = launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, stream);
+  if (rc) return rc;
+  return launch_skinny<256>(h_lo16, dpre, out_dim, Q, dw_last, stream);
 }

@@ -23,6 +23,8 @@ from . import _lib, ops
 WID = 256
 FEAT = 64
 OUT_KINDS = {"none": 0, "tanh": 1, "sigmoid": 2}
+_KEEP_LAST_ACTIVATIONS = False      # diagnostics (tools/relu_diag.py): keep the saved activations of each call
+_last_activations = []
 
 
 def eligible(module):
@@ -97,18 +99,21 @@ class _ReluMLPFunction(torch.autograd.Function):
         w_last, b_last = ws[H].contiguous(), bs[H].contiguous()
         out_dim = w_last.shape[0]
         need_grad = any(ctx.needs_input_grad)
-        act16 = torch.empty((H, Q, WID), dtype=torch.float16, device=dev) if need_grad else None
+        act16 = torch.empty((2, H, Q, WID), dtype=torch.float16, device=dev) if need_grad else None   # hi, lo
         y = torch.empty((Q, out_dim), dtype=torch.float32, device=dev)
         sb = (ctypes.c_int * len(stage_begin))(*stage_begin)
         src = (ctypes.c_uint8 * len(a_src))(*a_src)
         src2 = (ctypes.c_uint8 * len(a_src2))(*a_src2)
         rc = _lib.lib().neucam_relu_mlp_fwd(_lib.ptr(feat16), ctypes.c_int64(Q), _lib.ptr(w_stages), H, sb, src, src2,
                                             _lib.ptr(bias), _lib.ptr(w_last), _lib.ptr(b_last), out_dim, out_kind,
-                                            _lib.ptr(y), _lib.ptr(act16), _lib.cur_stream())
+                                            _lib.ptr(y), _lib.ptr(act16[0] if need_grad else None),
+                                            _lib.ptr(act16[1] if need_grad else None), _lib.cur_stream())
         _lib.check(rc, "neucam_relu_mlp_fwd")
         if need_grad:
             ctx.save_for_backward(feat16, act16, y, *ws)
             ctx.meta = meta
+            if _KEEP_LAST_ACTIVATIONS:
+                _last_activations.append(act16)
         return y
 
     @staticmethod
@@ -128,20 +133,24 @@ class _ReluMLPFunction(torch.autograd.Function):
         dpre = dpre.contiguous()
         scale = ops.loss_scale_from(dpre)
         want_dfeat = ctx.needs_input_grad[0]
-        blocks = [_k_blocks(ws[l][:, :WID].t()) for l in range(H - 1, 0, -1)]
+        def hi_lo_stages(wt):       # [256,256] transposed weight -> its K-blocks as (hi, lo) stage pairs
+            hi, lo = _split(wt)
+            return torch.stack((_k_blocks(hi).view(4, WID, 64), _k_blocks(lo).view(4, WID, 64)), 1).reshape(8 * WID, 64)
+
+        blocks = [hi_lo_stages(ws[l][:, :WID].t()) for l in range(H - 1, 0, -1)]
         if want_dfeat:
             w0t = ws[0].new_zeros((WID, WID))
             w0t[:E] = ws[0].t()     # rows E..2E (the residual features) stay zero: they are constants
-            blocks.append(_k_blocks(w0t))
-        wT_stages = (torch.cat(blocks, 0) if blocks else ws[0].new_zeros((4 * WID, 64))).to(torch.float16).contiguous()
+            blocks.append(hi_lo_stages(w0t))
+        wT_stages = (torch.cat(blocks, 0) if blocks else ws[0].new_zeros((8 * WID, 64))).to(torch.float16).contiguous()
         w_last = ws[H].contiguous()
         out_dim = w_last.shape[0]
-        dz16 = torch.empty((H, Q, WID), dtype=torch.float16, device=dev)
+        dz16 = torch.empty((2, H, Q, WID), dtype=torch.float16, device=dev)   # hi, lo
         dfeat = torch.empty((Q, FEAT), dtype=torch.float32, device=dev) if want_dfeat else None
         L_ = _lib.lib()
         rc = L_.neucam_relu_mlp_bwd(_lib.ptr(dpre), ctypes.c_int64(Q), _lib.ptr(wT_stages), H, _lib.ptr(w_last),
-                                    out_dim, _lib.ptr(act16), _lib.ptr(scale), _lib.ptr(dz16), _lib.ptr(dfeat),
-                                    _lib.cur_stream())
+                                    out_dim, _lib.ptr(act16[0]), _lib.ptr(scale), _lib.ptr(dz16[0]), _lib.ptr(dz16[1]),
+                                    _lib.ptr(dfeat), _lib.cur_stream())
         _lib.check(rc, "neucam_relu_mlp_bwd")
         # weight gradients
         dw = [torch.zeros_like(w) for w in ws]
@@ -153,12 +162,13 @@ class _ReluMLPFunction(torch.autograd.Function):
         db_arr = arr(db[:H])
         skip_arr = arr([enc[skip_slot[l]] if l in skip_slot else None for l in range(H)])
         ldw = (ctypes.c_int * H)(*[int(w.shape[1]) for w in ws[:H]])
-        rc = L_.neucam_relu_mlp_wgrad(_lib.ptr(dz16), _lib.ptr(act16), _lib.ptr(feat16), ctypes.c_int64(Q), H,
+        rc = L_.neucam_relu_mlp_wgrad(_lib.ptr(dz16[0]), _lib.ptr(dz16[1]), _lib.ptr(act16[0]), _lib.ptr(act16[1]),
+                                      _lib.ptr(feat16), ctypes.c_int64(Q), H,
                                       _lib.ptr(scale), _lib.ptr(enc[0]), dw_arr, ldw, db_arr, skip_arr,
                                       _lib.cur_stream())
         _lib.check(rc, "neucam_relu_mlp_wgrad")
-        rc = L_.neucam_relu_mlp_head_wgrad(_lib.ptr(act16[H - 1]), _lib.ptr(dpre), out_dim, ctypes.c_int64(Q),
-                                           _lib.ptr(dw[H]), _lib.cur_stream())
+        rc = L_.neucam_relu_mlp_head_wgrad(_lib.ptr(act16[0, H - 1]), _lib.ptr(act16[1, H - 1]), _lib.ptr(dpre), out_dim,
+                                           ctypes.c_int64(Q), _lib.ptr(dw[H]), _lib.cur_stream())
         _lib.check(rc, "neucam_relu_mlp_head_wgrad")
         db[H] = dpre.sum(0)
         fold = lambda e: e[:, :E] + e[:, E:2 * E]      # hi + lo halves of the features
