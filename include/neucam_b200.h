@@ -131,6 +131,19 @@ int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, const void* act
 int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, const float* dpre, int out_dim, int64_t Q,
                                float* dw_last, void* stream);
 
+/* Helpers around the chain (csrc/relu_aux.cu).
+ * neucam_relu_mlp_encode: x [Q,3] fp32 -> feat16 [Q,64] fp16 = [ hi(E) | lo(E) | 0 ], E = 3 + 6*num_freq, the
+ *   features in PosEncodingNeRF's order (modules.py:567-580; num_freq = 0: use_encoding=False).
+ * neucam_relu_mlp_encode_bwd: dfeat [Q,64] fp32 (from neucam_relu_mlp_bwd) -> dx [Q,3] through the encoding.
+ * neucam_relu_mlp_pack: fp32 Linear weights w[l] ([out,in_l], row pitch ld[l]) -> w_stages for the forward plan
+ *   (per stage: st_layer, st_kb 0..3 | 4 = encoded-input block, st_lo 0 hi / 1 lo) and wT_stages in
+ *   neucam_relu_mlp_bwd's fixed order (NULL to skip). */
+int neucam_relu_mlp_encode(const float* x, int64_t Q, int num_freq, void* feat16, void* stream);
+int neucam_relu_mlp_encode_bwd(const float* x, const float* dfeat, int64_t Q, int num_freq, float* dx, void* stream);
+int neucam_relu_mlp_pack(const float* const* w, const int* ld, int L, int E, int S, const uint8_t* st_layer,
+                         const uint8_t* st_kb, const uint8_t* st_lo, int with_input_grad, void* w_stages,
+                         void* wT_stages, void* stream);
+
 /* ---- per-pixel stages around the scene MLP ------------------------------------------------------------
  * Layout conventions: a step samples B pixels; every pixel has K taps (K = patch_size = 9 with the blur
  * model, 1 without); per-tap tensors are tap-major [K,B,...] exactly like the reference's coords patch
