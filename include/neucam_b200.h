@@ -110,7 +110,8 @@ int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, 
  *   and a_src2[S] whether it also multiplies the lo part of a block (5..8, else 255).  The activation of the
  *   kernel's operand tile is hi = fp16(h), lo = fp16(h - hi).  bias [n_gemm,256]; w_last [out_dim,256], b_last fp32;
  *   out_kind 0 none / 1 tanh / 2 sigmoid.  Writes y [Q,out_dim] fp32 and, when act16 != NULL, the activations
- *   h_0..h_{H-1} as [H,Q,256] fp16 hi (act16) and lo (act_lo16) parts.
+ *   h_0..h_{H-1} as [H,Q,256] fp16 hi (act16) and lo (act_lo16) parts plus gates [H,Q,8] uint32 (bit u of a row:
+ *   hidden unit u is open), which is all the backward chain reads of the forward.
  * neucam_relu_mlp_bwd: dpre [Q,out_dim] fp32 = dL/d(output-layer pre-activation); wT_stages = for layer H-1
  *   down to 1 (then layer 0 if dfeat != NULL) the four 256(in, zero padded) x 64(out) K-blocks of the TRANSPOSED
  *   weight, each as a hi stage then a lo stage (skip columns excluded: the reference detaches the skip input, modules.py:287).  Writes dz16 / dz_lo16
@@ -121,9 +122,9 @@ int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, 
 int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_stages, int n_gemm, const int* stage_begin,
                         const uint8_t* a_src, const uint8_t* a_src2, const float* bias, const float* w_last,
                         const float* b_last, int out_dim, int out_kind, float* y, void* act16, void* act_lo16,
-                        void* stream);
+                        void* gates, void* stream);
 int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_stages, int H, const float* w_last, int out_dim,
-                        const void* act16, const float* scale_dev, void* dz16, void* dz_lo16, float* dfeat,
+                        const void* gates, const float* scale_dev, void* dz16, void* dz_lo16, float* dfeat,
                         void* stream);
 int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, const void* act16, const void* act_lo16,
                           const void* feat16, int64_t Q, int H, const float* scale_dev, float* dw_first,

@@ -101,15 +101,16 @@ class _ReluMLPFunction(torch.autograd.Function):
         w_last, b_last = ws[H].contiguous(), bs[H].contiguous()
         out_dim = w_last.shape[0]
         act16 = torch.empty((2, H, Q, WID), dtype=torch.float16, device=dev) if need_grad else None   # hi, lo
+        gates = torch.empty((H, Q, 8), dtype=torch.int32, device=dev) if need_grad else None
         y = torch.empty((Q, out_dim), dtype=torch.float32, device=dev)
         rc = lib.neucam_relu_mlp_fwd(_lib.ptr(feat16), ctypes.c_int64(Q), _lib.ptr(w_stages), H,
                                      (ctypes.c_int * len(begin))(*begin), _u8(a_src), _u8(a_src2), _lib.ptr(bias),
                                      _lib.ptr(w_last), _lib.ptr(b_last), out_dim, out_kind, _lib.ptr(y),
                                      _lib.ptr(act16[0] if need_grad else None),
-                                     _lib.ptr(act16[1] if need_grad else None), stream)
+                                     _lib.ptr(act16[1] if need_grad else None), _lib.ptr(gates), stream)
         _lib.check(rc, "neucam_relu_mlp_fwd")
         if need_grad:
-            ctx.save_for_backward(x, feat16, act16, y, wT_stages, *ws)
+            ctx.save_for_backward(x, feat16, act16, y, wT_stages, gates, *ws)
             ctx.meta = meta
             if _KEEP_LAST_ACTIVATIONS:
                 _last_activations.append(act16)
@@ -117,7 +118,7 @@ class _ReluMLPFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, feat16, act16, y, wT_stages, *ws = ctx.saved_tensors
+        x, feat16, act16, y, wT_stages, gates, *ws = ctx.saved_tensors
         skips, out_kind, nf, E = ctx.meta
         H = len(ws) - 1
         Q = feat16.shape[0]
@@ -139,7 +140,7 @@ class _ReluMLPFunction(torch.autograd.Function):
         dz16 = torch.empty((2, H, Q, WID), dtype=torch.float16, device=dev)   # hi, lo
         dfeat = torch.empty((Q, FEAT), dtype=torch.float32, device=dev) if want_dx else None
         rc = lib.neucam_relu_mlp_bwd(_lib.ptr(dpre), ctypes.c_int64(Q), _lib.ptr(wT_stages), H, _lib.ptr(w_last),
-                                     out_dim, _lib.ptr(act16[0]), _lib.ptr(scale), _lib.ptr(dz16[0]),
+                                     out_dim, _lib.ptr(gates), _lib.ptr(scale), _lib.ptr(dz16[0]),
                                      _lib.ptr(dz16[1]), _lib.ptr(dfeat), stream)
         _lib.check(rc, "neucam_relu_mlp_bwd")
         dx = None

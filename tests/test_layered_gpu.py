@@ -55,7 +55,7 @@ def _record_call_scales(monkeypatch, models):
 
     def recording_backward(ctx, dy):
         out = orig(ctx, dy)
-        slot = first_weight[ctx.saved_tensors[5].data_ptr()]
+        slot = first_weight[ctx.saved_tensors[6].data_ptr()]
         for i, g in enumerate(out[2:]):
             name = f"layers.{i // 2}.{'weight' if i % 2 == 0 else 'bias'}"
             scales[(slot, name)] = scales.get((slot, name), 0.0) + g.double().norm().item()
