@@ -6,10 +6,14 @@ What runs where:
   * both scene networks (atlas_b, atlas_f)     fused tcgen05 chains + split-K wgrad kernels, through
                                                modules.SingleBVPNet -> _SineMLPFunction (forward, dgrad incl.
                                                d/d(u,v), weight gradients)
+  * uv-mapping / alpha networks                tcgen05 ReLU chains (relu_mlp.py: encoding, forward, input gradient,
+                                               weight gradients)
+  * blur taps; PSF sum + exposure + CRF +      the per-pixel kernels of the static step (pixel_ops.py: blur_taps,
+    image_mse (+gamma, mask) + ue_loss         psf_crf_loss -- forward and gradients in one pass)
   * Adam over every model                      ONE fused launch over the flat parameter buffer (adam.cu)
   * value-only grad_loss                       neucam_tm_min_slope
-  * uv / alpha / blur ReLU MLPs, layer blend,  torch ops on the device, differentiated by autograd (cuBLAS GEMMs:
-    PSF sum, CRF, the losses                   library code, the part of this path still to be hand-written)
+  * warp = (mlp + position) / 2, layer blend,  torch elementwise ops on the device under autograd
+    rigidity / sparsity / alpha losses
 
 Nothing here has a CPU path: the scene networks raise on CPU tensors and the optimizer is the CUDA kernel.
 
@@ -21,7 +25,7 @@ from collections import OrderedDict
 
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, pixel_ops
 from .step import FlatParameters, StepOptions, flat_adam  # noqa: F401  (StepOptions re-exported)
 
 _LAYER_SLOTS = ("uv_b", "uv_f", "atlas_f", "alpha")
@@ -68,6 +72,13 @@ class LayeredTrainStep:
         self.K = int(options.patch_size) if models.get("blur") is not None else 1
         if self.K not in (1, 9, 25):
             raise ValueError("patch_size must be 9 or 25 (utils.get_input_patch)")
+        if not _host_logic_only and self.K > 1:
+            blur = models["blur"]
+            if not (self.K == 9 and len(blur.layers) == 4 and not blur.use_encoding and blur.layers[0].in_features == 3
+                    and blur.layers[0].out_features == 64 and blur.layers[3].out_features == 27
+                    and blur.last_nonlinear == "both"):
+                raise NotImplementedError("the blur kernels execute SimpleMLP(64, 4 layers, 3 -> 27, 'both') with "
+                                          "patch_size 9 (every shipped config with `deblur`)")
         side = {1: (0,), 9: (-1, 0, 1), 25: (-2, -1, 0, 1, 2)}[self.K]
         # tap k = (row dy, column dx) of the neighbourhood, dy outer (utils.py:587-612)
         self.tap_shift = torch.tensor([[0.0, dy * 2 / (h - 1), dx * 2 / (w - 1)] for dy in side for dx in side],
@@ -140,7 +151,13 @@ class LayeredTrainStep:
         global_pixels = self.global_pixels if self.global_pixels is not None else B * self.world
         share = B / float(global_pixels)
 
-        taps, psf = self._taps(coords, coord_idx)
+        kernels = self.params is not None      # product path; False only for the CPU host-logic tests
+        if kernels and K > 1:
+            uv_taps, psf = pixel_ops.blur_taps(coords[0].contiguous(), coord_idx, m["focal"].focus, m["blur"],
+                                               self.shape, K, opt.offset_size)
+            taps = torch.cat((coords[..., :1].expand(K, -1, -1), uv_taps), -1)
+        else:
+            taps, psf = self._taps(coords, coord_idx)
         uv_b = self._warp("uv_b", taps) if m.get("uv_b") is not None else taps[..., 1:]
         radiance = m["atlas_b"]({"coords": uv_b})["model_out"]                             # [K,B,3] log radiance
         alpha = front = uv_f = None
@@ -153,25 +170,35 @@ class LayeredTrainStep:
             alpha = m["alpha"](taps).view(K, -1, 1) if m.get("alpha") is not None else torch.sigmoid(front[..., -1:])
             radiance = torch.lerp(radiance, front[..., 0:3], alpha)                        # training.py:152
             alpha = alpha[K // 2].unsqueeze(0)
-        if psf is not None:
-            radiance = (psf * radiance).sum(0, keepdim=True)                               # training.py:157
-        if m.get("exp") is not None:
-            exposure = self._frame_value(m["exp"](), coord_idx)
-        else:
-            exposure = model_input["exps"].to(dev, torch.float32).view(-1, 1)
-        ldr = m["tm"](radiance.view(-1, 3), exposure, None)
-
-        fake, real = ldr, target
-        if opt.use_random_gamma:                                                           # training.py:180-183
-            g = torch.as_tensor(gamma, dtype=torch.float32).to(dev).view(1)
-            gw = model_input["gamma_weights"].to(dev, torch.float32).view(-1, 1)
-            log1pg = torch.log(g + 1.0)
-            curve = lambda x: torch.log((x * 0.5 + 0.5) * g + 1.0) / log1pg * 2.0 - 1.0    # utils.gamma_map
-            fake, real = fake + curve(ldr) * gw, real + curve(target) * gw
         mask = model_input["weights"].to(dev, torch.float32).view(-1, 1) if use_mask else None
-        sq = (fake - real) ** 2
         losses = OrderedDict()
-        losses["img_loss"] = (sq * mask if mask is not None else sq).mean() * share        # loss_functions.py:8-12
+        if kernels:
+            # PSF sum, exposure, CRF, image_mse (+ gamma, mask), ue_loss and all their gradients: one kernel
+            given_exp = None if m.get("exp") is not None else model_input["exps"].to(dev, torch.float32).view(-1).contiguous()
+            gw = model_input["gamma_weights"].to(dev, torch.float32).view(-1).contiguous() if opt.use_random_gamma else None
+            g_dev = torch.as_tensor(gamma, dtype=torch.float32).to(dev).view(1) if opt.use_random_gamma else None
+            pixel_total, img_value, ue_value = pixel_ops.psf_crf_loss(
+                radiance.contiguous(), psf, m["exp"].exps if m.get("exp") is not None else None, given_exp, m["tm"],
+                self.shape, K, opt.fixed_value, 1.0 / self.world, global_pixels, coord_idx, target.contiguous(), gw,
+                mask.view(-1).contiguous() if mask is not None else None, g_dev)
+            losses["img_loss"] = img_value
+        else:
+            if psf is not None:
+                radiance = (psf * radiance).sum(0, keepdim=True)                           # training.py:157
+            if m.get("exp") is not None:
+                exposure = self._frame_value(m["exp"](), coord_idx)
+            else:
+                exposure = model_input["exps"].to(dev, torch.float32).view(-1, 1)
+            ldr = m["tm"](radiance.view(-1, 3), exposure, None)
+            fake, real = ldr, target
+            if opt.use_random_gamma:                                                       # training.py:180-183
+                g = torch.as_tensor(gamma, dtype=torch.float32).to(dev).view(1)
+                gw = model_input["gamma_weights"].to(dev, torch.float32).view(-1, 1)
+                log1pg = torch.log(g + 1.0)
+                curve = lambda x: torch.log((x * 0.5 + 0.5) * g + 1.0) / log1pg * 2.0 - 1.0    # utils.gamma_map
+                fake, real = fake + curve(ldr) * gw, real + curve(target) * gw
+            sq = (fake - real) ** 2
+            losses["img_loss"] = (sq * mask if mask is not None else sq).mean() * share    # loss_functions.py:8-12
 
         if opt.rigidity_loss_w is not None and self.step_index < opt.rigidity_loss_steps:  # training.py:203-217
             rig = self._rigidity("uv_b", coords, uv_b[K // 2], mask)
@@ -186,9 +213,13 @@ class LayeredTrainStep:
                 losses["sparsity_loss2"] = (-1 / entropy).mean() * share
             if opt.alpha_loss_w is not None:
                 losses["alpha_loss"] = alpha.mean() * (opt.alpha_loss_w * share)
-        black = m["tm"](*self._black)                                                      # training.py:244-245
-        losses["ue_loss"] = (black - opt.fixed_value).abs().mean() / self.world
-        losses["total"] = sum(losses.values())
+        if kernels:
+            losses["ue_loss"] = ue_value
+            losses["total"] = pixel_total + sum(v for k, v in losses.items() if k not in ("img_loss", "ue_loss"))
+        else:
+            black = m["tm"](*self._black)                                                  # training.py:244-245
+            losses["ue_loss"] = (black - opt.fixed_value).abs().mean() / self.world
+            losses["total"] = sum(losses.values())
         return losses
 
     # -- backward / optimizer ---------------------------------------------------------------------------------

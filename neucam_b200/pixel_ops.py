@@ -1,0 +1,94 @@
+"""autograd bindings of the per-pixel kernels (csrc/pixel.cu) for steps that are assembled with autograd
+(neucam_b200.layered.LayeredTrainStep).  FusedTrainStep calls the same kernels directly on its static buffers.
+
+  blur_taps        utils.get_input_patch + focus gather + blur-kernel SimpleMLP + defocus offsets + centre-tap reset
+                   (training.py:99-121)  ->  tap positions [K,B,2] and PSF weights [K,B]
+  psf_crf_loss     PSF sum, exposure, TonemapNet, image_mse (+ random gamma, mask), ue_loss (training.py:157-188,
+                   244-245): the kernel computes the loss AND every gradient in one pass; backward hands them out
+"""
+import torch
+
+from . import ops
+
+
+class _BlurTaps(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, coord_idx, focus, cfg, *blur_params):
+        shape, K, offset_size = cfg
+        B = coords.shape[0]
+        dev = coords.device
+        uv = torch.empty((K, B, 2), device=dev)
+        kout = torch.empty((3 * K, B), device=dev)
+        hid = torch.empty((192, B), device=dev)
+        params = [p.contiguous() for p in blur_params]
+        focus_flat = focus.reshape(-1).contiguous()
+        ops.blur_fwd(coords, coord_idx, focus_flat, params, shape, K, float(offset_size), uv, kout, hid)
+        ctx.save_for_backward(coords, coord_idx, focus_flat, kout, hid, *params)
+        ctx.cfg = cfg
+        ctx.focus_shape = focus.shape
+        kw = kout[:K].clone()
+        return uv, kw
+
+    @staticmethod
+    def backward(ctx, duv, dkw):
+        coords, coord_idx, focus_flat, kout, hid, *params = ctx.saved_tensors
+        shape, K, offset_size = ctx.cfg
+        sizes = [p.numel() for p in params] + [focus_flat.numel()]
+        buf = torch.zeros(sum(sizes), device=coords.device)
+        parts = torch.split(buf, sizes)
+        grads = [g.view_as(p) for g, p in zip(parts[:-1], params)]
+        ops.blur_bwd(coords, coord_idx, focus_flat, params, grads, parts[-1], shape, K, float(offset_size), kout, hid,
+                     dkw.contiguous(), duv.contiguous())
+        return (None, None, parts[-1].view(ctx.focus_shape), None, *grads)
+
+
+def blur_taps(coords, coord_idx, focus, blur_module, shape, K, offset_size):
+    """coords [B,3] fp32, coord_idx [B] int64 -> (tap (y,x) positions [K,B,2], PSF weights [K,B])."""
+    params = []
+    for layer in blur_module.layers:
+        params += [layer.weight, layer.bias]
+    return _BlurTaps.apply(coords, coord_idx, focus, (tuple(shape), int(K), float(offset_size)), *params)
+
+
+class _PsfCrfLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, kw, exps, fixed_exps, cfg, coord_idx, gt, gamma_w, mask_w, gamma_dev, *tm_params):
+        shape, K, fixed_value, ue_weight, global_pixels = cfg
+        dev = y.device
+        has_blur = kw is not None
+        tm = [p.contiguous() for p in tm_params]
+        n_exp = exps.numel() if exps is not None else 0
+        sizes = [p.numel() for p in tm] + [max(n_exp, 1), 4, 4, 1]     # tm grads | dexps | db4 | sums | absmax bits
+        buf = torch.zeros(sum(sizes), device=dev)
+        parts = torch.split(buf, sizes)
+        tm_g = [g.view_as(p) for g, p in zip(parts[:len(tm)], tm)]
+        dexps, db4, sums, absmax = parts[len(tm):]
+        dy = torch.empty_like(y)
+        dkw = torch.empty_like(kw) if has_blur else None
+        scale = torch.empty(1, device=dev)
+        ops.psf_crf_loss(y, kw, coord_idx, exps.reshape(-1) if exps is not None else None, fixed_exps, gt, gamma_w,
+                         mask_w, tm, tm_g, shape, K, has_blur, gamma_dev, float(fixed_value), float(ue_weight),
+                         3 * int(global_pixels), dy, dkw, dexps if exps is not None else None, db4, sums,
+                         absmax.view(torch.int32), scale)
+        img = sums[0] / float(3 * int(global_pixels))
+        ue = sums[1] * float(ue_weight)
+        ctx.save_for_backward(dy, dkw, dexps, *tm_g)
+        ctx.exps_shape = exps.shape if exps is not None else None
+        ctx.mark_non_differentiable(img, ue)
+        return img + ue, img, ue
+
+    @staticmethod
+    def backward(ctx, g_total, _g_img, _g_ue):
+        dy, dkw, dexps, *tm_g = ctx.saved_tensors
+        d_exps = (dexps[:ctx.exps_shape.numel()].view(ctx.exps_shape) * g_total) if ctx.exps_shape is not None else None
+        return (dy * g_total, dkw * g_total if dkw is not None else None, d_exps, None, None, None, None, None, None,
+                None, *[g * g_total for g in tm_g])
+
+
+def psf_crf_loss(y, kw, exps, fixed_exps, tm_module, shape, K, fixed_value, ue_weight, global_pixels, coord_idx, gt,
+                 gamma_w=None, mask_w=None, gamma_dev=None):
+    """y [K,B,3] (log radiance per tap), kw [K,B] PSF weights or None (K = 1).  Returns (img_loss + ue_loss with
+    gradient, img_loss value, ue_loss value); img_loss is this rank's share of the global mean, ue_loss is weighted
+    by ue_weight (1 / world size)."""
+    return _PsfCrfLoss.apply(y, kw, exps, fixed_exps, (tuple(shape), int(K), fixed_value, ue_weight, global_pixels),
+                             coord_idx, gt, gamma_w, mask_w, gamma_dev, *tm_module.parameters())
