@@ -96,3 +96,35 @@ def test_host_logic_instance_cannot_train(cpu_scene_networks):
     b = batch_of(fx, 0)
     with pytest.raises(Exception):
         step.forward_backward(b, {"img": b["img"]}, 2.0)
+
+
+@pytest.mark.parametrize("name", ["video_deblur_small", "me_dynamic_small"])
+def test_pixel_shards_sum_to_the_full_batch(name, cpu_scene_networks):
+    """Data parallel contract: two ranks with a (ragged) half of the pixels each, losses
+    weighted by B_local / B_global and ue_loss by 1 / world, SUM of the gradients == one rank with all pixels."""
+    fx = load_fixture(name)
+    b = batch_of(fx, 0)
+    gamma, _ = replay_rng(fx, 0)
+    B = fx["B"]
+    cut = B // 2 - 3
+
+    def grads_of(world, lo, hi):
+        models = _models_for(fx)
+        harness.load_state(models, fx["init_state"])
+        step = LayeredTrainStep(models, fx["shape"], _options(fx), global_pixels=B, _host_logic_only=True)
+        step.world = world
+        part = {k: (v[:, lo:hi] if torch.is_tensor(v) and v.dim() >= 2 and v.shape[1] == B else v) for k, v in b.items()}
+        losses = step.forward(part, {"img": part["img"]}, gamma)
+        losses["total"].backward()
+        return ({k: v.item() for k, v in losses.items()},
+                {(s, k): (p.grad.clone() if p.grad is not None else torch.zeros_like(p))
+                 for s, m in models.items() if m is not None for k, p in m.named_parameters()})
+
+    l_full, g_full = grads_of(1, 0, B)
+    l0, g0 = grads_of(2, 0, cut)
+    l1, g1 = grads_of(2, cut, B)
+    for k in l_full:
+        assert l0[k] + l1[k] == pytest.approx(l_full[k], rel=2e-5), k
+    for key, g in g_full.items():
+        if g.abs().max() > 0:
+            assert rel(g0[key] + g1[key], g) < 2e-4, key
