@@ -255,7 +255,7 @@ class LayeredTrainStep:
         return self._losses
 
     # -- CUDA graph ---------------------------------------------------------------------------------------------
-    def capture(self, model_input, gt, gamma=None, use_mask=False):
+    def capture(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None):
         """Captures forward + autograd backward + Adam over STATIC device copies of one batch into a CUDA graph
         (two graphs around the eager gradient all-reduce when distributed); `run_resident()` replays it after
         `load_resident()` refreshed the static buffers.  The rigidity window is decided at capture time."""
@@ -270,7 +270,7 @@ class LayeredTrainStep:
         with torch.cuda.stream(side):          # warm-up off the capture stream (kernel attributes, cuBLAS handles)
             for _ in range(2):
                 self.forward_backward(self._static_in, self._static_gt, self._static_gamma, use_mask)
-                self.optimizer_step()
+                self.optimizer_step(lr_groups=lr_groups)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         for dst, src in zip((P.flat, P.exp_avg, P.exp_avg_sq, P.adam_state), saved):
@@ -279,14 +279,27 @@ class LayeredTrainStep:
         with torch.cuda.graph(g1):
             self.forward_backward(self._static_in, self._static_gt, self._static_gamma, use_mask)
             if self.world == 1:
-                self.optimizer_step(reduce=False)
+                self.optimizer_step(reduce=False, lr_groups=lr_groups)
         g2 = None
         if self.world > 1:
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
-                self.optimizer_step(reduce=False)
+                self.optimizer_step(reduce=False, lr_groups=lr_groups)
         self._graph = (g1, g2)
         return self._graph
+
+    def graph_step(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None):
+        """`step()` through a CUDA graph: (re)captures whenever something baked into the graph changes -- the mask
+        switch, the rigidity window (training.py:203), the optimizer groups (training.py:300-313) or the batch
+        size -- then copies the batch into the static buffers and replays."""
+        rigid = self.opt.rigidity_loss_w is not None and self.step_index < self.opt.rigidity_loss_steps
+        groups = None if lr_groups is None else tuple(sorted((k, v) for k, v in lr_groups.items()))
+        key = (bool(use_mask), rigid, groups, int(model_input["coords"].numel()))
+        if getattr(self, "_graph_key", None) != key:
+            self.capture(model_input, gt, gamma, use_mask, lr_groups)
+            self._graph_key = key
+        self.load_resident(model_input, gt, gamma)
+        return self.run_resident()
 
     def load_resident(self, model_input, gt, gamma=None, non_blocking=True):
         for k, dst in self._static_in.items():

@@ -53,7 +53,7 @@ def train(models, train_dataloader, model_dir, loss_fn=None, summary_fn=None, va
         for model_input, gt in train_dataloader:
             gamma = (torch.rand(1) * 100 + 1.0) if step.opt.use_random_gamma else None     # training.py:181
             if layered:
-                step.step(model_input, gt, gamma, use_mask=use_mask, lr_groups=lr_groups)
+                step.graph_step(model_input, gt, gamma, use_mask=use_mask, lr_groups=lr_groups)
             else:
                 step.load_batch(model_input, gt, gamma)
                 step.forward_backward(use_mask=use_mask)

@@ -192,3 +192,28 @@ def test_train_loop_dispatches_layered_step(tmp_path):
         assert nutils.CHECKPOINT_KEYS[slot] in ck, slot
     # tm moved during the first three steps and is frozen afterwards (training.py:300-313)
     assert not torch.equal(models["tm"].layers_r[0].weight.detach().cpu(), before.cpu())
+
+
+def test_graph_step_equals_eager_step():
+    """CUDA-graph replay (what train() runs) against eager stepping on the same batches, including a batch change
+    between replays: parameters agree to float-atomics noise."""
+    kind = "video_deblur"
+    results = []
+    for use_graph in (False, True):
+        models, state, opts, batch, cfg = _setup(kind, 256, seed=5)
+        step = LayeredTrainStep(models, SHAPES[kind], opts, device="cuda")
+        g = torch.Generator().manual_seed(11)
+        grid = harness.mgrid(SHAPES[kind])
+        for it in range(4):
+            idx = torch.randint(0, grid.shape[0], (256,), generator=g)
+            b = {"coords": grid[idx][None], "coord_idx": idx[None], "img": torch.rand(1, 256, 3, generator=g) * 2 - 1}
+            (step.graph_step if use_graph else step.step)(b, {"img": b["img"]})
+        torch.cuda.synchronize()
+        results.append({(s, k): p.detach().clone() for s, m in models.items() if m is not None
+                        for k, p in m.named_parameters()})
+        assert step.step_index == 4
+    for key, p in results[0].items():
+        # 4 Adam steps of lr 1e-4 move a weight by up to 4e-4; entries whose gradient is ~eps can take a different
+        # sign-step under a different atomics order, hence the 1e-4 bound on single entries and 2e-6 on the mean
+        d = (results[1][key] - p).abs()
+        assert d.max().item() < 1.5e-4 and d.mean().item() < 2e-6, (key, d.max().item(), d.mean().item())
