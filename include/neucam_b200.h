@@ -67,6 +67,8 @@ int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float
 int neucam_debug_set_chain_trace(long long* trace_dev);
 /* Debug experiments (outputs become garbage): bit0 = chain kernels issue no MMAs, bit1 = no weight TMA loads. */
 int neucam_debug_set_chain_flags(int flags);
+int neucam_debug_set_relu_trace(void* trace);  /* CTA 0 event/clock trace of the next ReLU-chain forward launches */
+int neucam_debug_set_relu_flags(int flags);   /* timing experiments on the ReLU chain (forward); results invalid */
 
 /* neucam_sine_mlp_bwd:  given dy[Q,out_dim] computes duv[Q,2], ACCUMULATES the first layer's
  *   gradients into dw0 [512,2] / db0 [512] and writes dz16 = fp16 [3,Q,512] holding

@@ -5,13 +5,17 @@
 //   forward   feat[Q,64] --W0--> relu --W1--> relu ... --W_{H-1}--> relu --w_last (SIMT)--> tanh|sigmoid
 //   backward  dpre[Q,out] --w_last (SIMT)--> mask --W_{H-1}^T--> mask ... --W_1^T--> mask [--W_0^T--> dfeat]
 //
-// A CTA owns a 128-sample tile for the whole chain: the activation tile lives in shared memory as the K-major
-// SWIZZLE_128B A operand (4 k-blocks of 128 x 64 fp16), every layer is 4 (+1 for a skip connection) weight
-// "stages" of 256 x 64 fp16 streamed through a 2-deep TMA ring, accumulated by M128 x N256 x K16 MMAs into 256
-// TMEM columns, drained by 4 epilogue warps (thread = sample row) that apply bias + ReLU (forward) or the ReLU
-// mask of the saved activation (backward), write the next operand tile in place and TMA-store it to HBM for
-// the weight-gradient GEMMs.  The encoded input (raw coordinates + NeRF positional encoding, zero-padded to 64
-// features) is its own 16 KB operand tile, so the first layer and the skip connection are tensor-core GEMMs too.
+// A CTA owns a 128-sample tile for the whole chain.  The activation tile never touches shared memory: it lives in
+// TENSOR MEMORY as the A operand of tcgen05.mma (lane = sample row, two fp16 per 32-bit column: 128 columns for the
+// hi parts, 128 for the lo parts, next to the 256 accumulator columns = all 512 columns of the SM).  Every layer is
+// a sequence of weight "stages" of 256 x 64 fp16 streamed through a 4-deep TMA ring (128 KB of shared memory),
+// accumulated by M128 x N256 x K16 MMAs, drained by 4 epilogue warps (thread = sample row) that apply bias + ReLU
+// (forward) or the forward's gate bits (backward), write the next operand tile back into tensor memory with
+// tcgen05.st and TMA-store it to HBM for the weight-gradient GEMMs through a 4 KB staging tile per warp (32 rows x
+// 32 columns, hi and lo; direct st.global from the row-per-thread layout cost 32 L1 tag requests per instruction and
+// 8 k cycles per GEMM).  The encoded input (raw coordinates + NeRF positional
+// encoding, zero-padded to 64 features) is a 16 KB shared-memory operand tile loaded by TMA, so the first layer and
+// the skip connection are tensor-core GEMMs too.
 //
 // Precision.  A ReLU network's gradient is discontinuous in its pre-activations: with plain fp16 operands the
 // forward's ~4e-4 relative error in z flips ~3e-4 of the ReLU gates against the fp32 reference, which alone puts
@@ -23,7 +27,10 @@
 // and the saved activations are carried as hi + lo pairs as well (three MMAs per product), with a power-of-two
 // loss scale on dz.
 //
-// Warp roles: 0..3 epilogue, 4 TMA producer, 5 MMA issuer + TMEM owner (control warps have the highest ids).
+// Warp roles: 0..15 epilogue (warp e: TMEM lane quadrant e & 3 = 32 sample rows, column quarter e >> 2 = 64 of the
+// 256 hidden units), 16 TMA producer, 17 MMA issuer + TMEM owner (control warps have the highest ids).  With only 4
+// epilogue warps (one per scheduler) the per-element work ran at IPC ~0.3 and was 75 % of the kernel (measured with
+// the dbg flags: 218 of 293 us with no MMA, no loads, no TMEM traffic at all).
 #include "host_util.h"
 #include "tc05.cuh"
 
@@ -33,23 +40,26 @@ namespace {
 
 constexpr int WID = 256;
 constexpr int TILE_M = 128;
-constexpr int NSTAGE = 2;                        // weight stages in flight (64 KB); the lo operand tile takes 64 KB
-constexpr int MAX_GEMM = 8;
+constexpr int NSTAGE = 4;                        // weight stages in flight (128 KB)
+constexpr int MAX_GEMM = 7;
 constexpr int MAX_STAGES = 64;
 constexpr int FEAT = 64;
 constexpr uint32_t KB_BYTES = TILE_M * 128;      // one k-block of the operand tile: 128 rows x 64 fp16
 constexpr uint32_t STAGE_BYTES = WID * 128;      // one weight stage: 256 rows x 64 fp16
-constexpr uint32_t OFF_A = 0;
-constexpr uint32_t OFF_F = OFF_A + 4 * KB_BYTES;
+constexpr uint32_t OFF_F = 0;                                    // encoded-input operand tile (forward)
 constexpr uint32_t OFF_W = OFF_F + KB_BYTES;
-constexpr uint32_t OFF_ALO = OFF_W + NSTAGE * STAGE_BYTES;       // lo halves of the operand tile
-constexpr uint32_t OFF_BIAS = OFF_ALO + 4 * KB_BYTES;            // float [MAX_GEMM][256] (forward)
+constexpr uint32_t OFF_STAGE = OFF_W + NSTAGE * STAGE_BYTES;     // per epilogue warp: 32 rows x 64 B hi | lo
+constexpr uint32_t OFF_BIAS = OFF_STAGE + 16 * 4096;             // float [MAX_GEMM][256] (forward)
+// tensor-memory columns: accumulator | hi operand tile | lo operand tile
+constexpr uint32_t TM_ACC = 0, TM_AHI = 256, TM_ALO = 384;
 constexpr uint32_t OFF_HEAD = OFF_BIAS + MAX_GEMM * WID * 4;     // float [4][256] last-layer weights
-constexpr uint32_t OFF_BAR = OFF_HEAD + 4 * WID * 4;
+constexpr uint32_t OFF_XCH = OFF_HEAD + 4 * WID * 4;              // float4 [3][128]: output-layer partial sums
+constexpr uint32_t OFF_BAR = OFF_XCH + 3 * TILE_M * 16;
 constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
-constexpr int NTHREADS = 192;
-constexpr int WARP_PRODUCER = 4, WARP_MMA = 5;
+constexpr int NEPI_WARPS = 16;                    // 4 per scheduler: the epilogue is SIMT-latency bound with fewer
+constexpr int NTHREADS = (NEPI_WARPS + 2) * 32;
+constexpr int WARP_PRODUCER = NEPI_WARPS, WARP_MMA = NEPI_WARPS + 1;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_AREADY = 9, BAR_FFULL = 10, BAR_FEMPTY = 11 };
@@ -57,8 +67,8 @@ enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_AREADY = 9, BAR_FFULL = 1
 struct ReluMaps {
   CUtensorMap feat;            // [Q,64] fp16, box 64 x 128 (forward)
   CUtensorMap w;               // weight stages [S*256, 64] fp16, box 64 x 256
-  CUtensorMap act[MAX_GEMM];   // forward: h_l ; backward: dz_l   ([Q,256] fp16, box 64 x 128): hi parts
-  CUtensorMap act_lo[MAX_GEMM];  // the same tensors' lo parts (fp16 rounding residuals)
+  CUtensorMap out_hi[MAX_GEMM];  // forward h_l / backward dz_l: [Q,256] fp16, SWIZZLE_64B box 32 x 32 (hi parts)
+  CUtensorMap out_lo[MAX_GEMM];  // the same tensors' lo parts (fp16 rounding residuals)
 };
 
 struct ReluParams {
@@ -78,6 +88,9 @@ struct ReluParams {
   const uint32_t* gates;               // backward: the same bits (ReLU masks)
   const float* scale;                  // backward: device scalar loss scale
   float* dfeat;                        // backward [Q,64] fp32 or null (the last GEMM then computes it)
+  long long* trace;                    // diagnostics: CTA 0 writes (event id, clock64) pairs per role, or null
+  int dbg;                             // timing experiments (results are garbage): 1 no operand write-back,
+                                       // 2 no MMA issue, 4 no weight loads, 8 no accumulator drain
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -89,17 +102,44 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// 32 consecutive columns (chunk c of 8) of one row of the operand tile: 16 packed words
-__device__ __forceinline__ void write_chunk(uint32_t a_base, uint32_t c, uint32_t row, const uint32_t (&w)[16]) {
-  const uint32_t blk = a_base + (c >> 1) * KB_BYTES;
-  const uint32_t qb = (c & 1u) * 4u;
+// One warp's 32 rows x 32 columns (hi and lo) -> its staging tile -> two TMA stores.  The previous pair of stores
+// must have finished READING the tile before it is rewritten.
+__device__ __forceinline__ void store_chunk_tma(const CUtensorMap* m_hi, const CUtensorMap* m_lo, uint32_t stage,
+                                                uint32_t lane, int col0, int row0, const uint32_t (&w)[16],
+                                                const uint32_t (&wl)[16]) {
+  if (lane == 0) tma_store_wait_read0();
+  __syncwarp();
+  const uint32_t hi = stage + lane * 64u, lo = hi + 2048u;
+  const uint32_t sw = (lane >> 1) & 3u;   // SWIZZLE_64B: piece index ^ ((row >> 1) & 3): bank-conflict free
 #pragma unroll
-  for (uint32_t q = 0; q < 4; ++q)
-    st_shared_v4(blk + sw128_offset(row, qb + q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  for (uint32_t q = 0; q < 4; ++q) {
+    st_shared_v4(hi + ((q ^ sw) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    st_shared_v4(lo + ((q ^ sw) << 4), wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(m_hi, stage, col0, row0);
+    tma_store_2d(m_lo, stage + 2048u, col0, row0);
+    tma_store_commit();
+  }
+}
+
+// trace[role][0] = number of events; events at trace[role][1 + 2 i] = id, [2 + 2 i] = clock64.  256 events per role.
+__device__ __forceinline__ void stamp(long long* trace, int role, int id) {
+  if (trace == nullptr || blockIdx.x != 0 || (threadIdx.x & 31) != 0) return;
+  long long* t = trace + role * 520;
+  const long long n = t[0];
+  if (n < 256) {
+    t[1 + 2 * n] = id;
+    t[2 + 2 * n] = clock64();
+    t[0] = n + 1;
+  }
 }
 
 template <bool BWD>
@@ -126,13 +166,13 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
       mbar_init(bar(BAR_WEMPTY + s), 1);
     }
     mbar_init(bar(BAR_ACC), 1);
-    mbar_init(bar(BAR_AREADY), 128);
+    mbar_init(bar(BAR_AREADY), NEPI_WARPS * 32);
     mbar_init(bar(BAR_FFULL), 1);
     mbar_init(bar(BAR_FEMPTY), 1);
     mbar_fence_init();
   }
   if (warp == WARP_MMA) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 256);
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -155,10 +195,15 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         __syncwarp();
       }
       for (int s = 0; s < S; ++s) {
-        mbar_wait(bar(BAR_WEMPTY + slot), ph ^ 1);
+        mbar_wait_backoff(bar(BAR_WEMPTY + slot), ph ^ 1, 32);
+        stamp(p.trace, 0, 100 + s);
         if (lane == 0) {
-          mbar_arrive_expect_tx(bar(BAR_WFULL + slot), STAGE_BYTES);
-          tma_load_2d(base + OFF_W + slot * STAGE_BYTES, &maps.w, bar(BAR_WFULL + slot), 0, s * WID);
+          if (p.dbg & 4) {
+            mbar_arrive(bar(BAR_WFULL + slot));
+          } else {
+            mbar_arrive_expect_tx(bar(BAR_WFULL + slot), STAGE_BYTES);
+            tma_load_2d(base + OFF_W + slot * STAGE_BYTES, &maps.w, bar(BAR_WFULL + slot), 0, s * WID);
+          }
         }
         __syncwarp();
         if (++slot == NSTAGE) { slot = 0; ph ^= 1; }
@@ -170,8 +215,10 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
     uint32_t slot = 0, ph = 0, aph = 0, fph = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int g = 0; g < p.n_gemm; ++g) {
-        mbar_wait(bar(BAR_AREADY), aph);   // operand tile written (and the accumulator drained)
+        stamp(p.trace, 1, 10 * g + 0);
+        mbar_wait_backoff(bar(BAR_AREADY), aph, 32);   // operand tile written (and the accumulator drained)
         aph ^= 1;
+        stamp(p.trace, 1, 10 * g + 1);
         if (!BWD && g == 0) {
           mbar_wait(bar(BAR_FFULL), fph);
           fph ^= 1;
@@ -187,13 +234,16 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             for (int t = 0; t < 2; ++t) {
               const uint32_t src = srcs[t];
               if (src == 255u) continue;
-              const uint32_t a_addr = base + (src == 4 ? OFF_F : src < 4 ? OFF_A + src * KB_BYTES
-                                                                         : OFF_ALO + (src - 5) * KB_BYTES);
+              // operand k-block: 64 K-elements = 32 tensor-memory columns; one K16 step = 8 columns
+              const uint32_t a_tm = tmem_base + (src < 4 ? TM_AHI + src * 32 : TM_ALO + (src - 5) * 32);
 #pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16)
-                umma_f16_ss(tmem_base, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
-                            make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc,
-                            (s > p.stage_begin[g] || t > 0 || k16 > 0) ? 1u : 0u);
+              for (int k16 = 0; k16 < 4; ++k16) {
+                if (p.dbg & 2) continue;
+                const uint32_t acc = (s > p.stage_begin[g] || t > 0 || k16 > 0) ? 1u : 0u;
+                const uint64_t bd = make_sdesc_sw128(b_addr + k16 * 32, 0, 1024);
+                if (src == 4) umma_f16_ss(tmem_base + TM_ACC, make_sdesc_sw128(base + OFF_F + k16 * 32, 0, 1024), bd, idesc, acc);
+                else          umma_f16_ts(tmem_base + TM_ACC, a_tm + k16 * 8, bd, idesc, acc);
+              }
             }
             umma_commit(bar(BAR_WEMPTY + slot));
           }
@@ -205,13 +255,17 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           umma_commit(bar(BAR_ACC));
         }
         __syncwarp();
+        stamp(p.trace, 1, 10 * g + 2);
       }
     }
   } else {
-    // ---------------- epilogue warps 0..3: thread = sample row = TMEM lane ----------------
-    const uint32_t row = tid;
-    const uint32_t t_row = tmem_base + ((warp * 32u) << 16);
-    const uint32_t a_base = base + OFF_A;
+    // ---------------- epilogue warps: thread = (sample row = TMEM lane, column quarter) ----------------
+    const uint32_t quad = warp & 3u, sub = warp >> 2;
+    const uint32_t row = quad * 32u + lane;
+    const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
+    const uint32_t c_lo = 2u * sub, c_hi = 2u * sub + 2u;   // this thread's two 32-column chunks
+    float4* s_xch = reinterpret_cast<float4*>(sm + OFF_XCH);
+    const uint32_t stage = base + OFF_STAGE + warp * 4096u;
     uint32_t acc_ph = 0;
     if (!BWD) mbar_arrive(bar(BAR_AREADY));   // the first GEMM of the first tile has nothing to wait for
     float scale = 1.f, inv_scale = 1.f;
@@ -227,18 +281,11 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         float dp[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid)
           for (int o = 0; o < p.out_dim; ++o) dp[o] = p.dpre[grow * p.out_dim + o] * scale;
-        uint32_t gate[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (valid) {
-          const uint4* gp = reinterpret_cast<const uint4*>(p.gates + ((size_t)(p.H - 1) * p.Q + grow) * 8);
-          const uint4 g0 = gp[0], g1 = gp[1];
-          gate[0] = g0.x; gate[1] = g0.y; gate[2] = g0.z; gate[3] = g0.w;
-          gate[4] = g1.x; gate[5] = g1.y; gate[6] = g1.z; gate[7] = g1.w;
-        }
-        if (tid == 0) tma_store_wait_read0();
-        epi_bar_sync();
-#pragma unroll
-        for (uint32_t c = 0; c < 8; ++c) {
-          const uint32_t gw = gate[c];
+        uint2 gq = make_uint2(0, 0);
+        if (valid) gq = *reinterpret_cast<const uint2*>(p.gates + ((size_t)(p.H - 1) * p.Q + grow) * 8 + c_lo);
+#pragma unroll 1
+        for (uint32_t c = c_lo; c < c_hi; ++c) {
+          const uint32_t gw = (c & 1u) ? gq.y : gq.x;
           uint32_t w[16], wl[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -255,39 +302,33 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
             wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
           }
-          write_chunk(a_base, c, row, w);
-          write_chunk(base + OFF_ALO, c, row, wl);
+          tmem_st_32x32b_x16(t_row + TM_AHI + c * 16, w);
+          tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
+          if (p.store)
+            store_chunk_tma(&maps.out_hi[p.H - 1], &maps.out_lo[p.H - 1], stage, lane, (int)c * 32,
+                            tile * TILE_M + (int)quad * 32, w, wl);
         }
-        fence_proxy_async_smem();
-        epi_bar_sync();
-        if (tid == 0 && p.store) {
-          for (int kb = 0; kb < 4; ++kb) {
-            tma_store_2d(&maps.act[p.H - 1], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
-            tma_store_2d(&maps.act_lo[p.H - 1], base + OFF_ALO + kb * KB_BYTES, kb * 64, tile * TILE_M);
-          }
-          tma_store_commit();
-        }
+        tmem_st_wait();
+        tc_fence_before_sync();
         mbar_arrive(bar(BAR_AREADY));
       }
       for (int g = 0; g < p.n_gemm; ++g) {
         const bool last = (g == p.n_gemm - 1);
         const bool dfeat_gemm = BWD && last && p.dfeat != nullptr;
         const int layer = BWD ? (p.H - 2 - g) : g;        // layer whose operand tile this epilogue produces
-        uint32_t gate[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (BWD && !dfeat_gemm && valid) {   // fetched before the accumulator wait: the latency hides under the MMAs
-          const uint4* gp = reinterpret_cast<const uint4*>(p.gates + ((size_t)layer * p.Q + grow) * 8);
-          const uint4 g0 = gp[0], g1 = gp[1];
-          gate[0] = g0.x; gate[1] = g0.y; gate[2] = g0.z; gate[3] = g0.w;
-          gate[4] = g1.x; gate[5] = g1.y; gate[6] = g1.z; gate[7] = g1.w;
-        }
-        mbar_wait(bar(BAR_ACC), acc_ph);
+        uint2 gq = make_uint2(0, 0);
+        if (BWD && !dfeat_gemm && valid)   // fetched before the accumulator wait: the latency hides under the MMAs
+          gq = *reinterpret_cast<const uint2*>(p.gates + ((size_t)layer * p.Q + grow) * 8 + c_lo);
+        if (warp == 0) stamp(p.trace, 2, 10 * g + 0);
+        mbar_wait_backoff(bar(BAR_ACC), acc_ph, 64);
         acc_ph ^= 1;
+        if (warp == 0) stamp(p.trace, 2, 10 * g + 1);
         tc_fence_after_sync();
         if (dfeat_gemm) {
-          // input gradient: first 64 accumulator columns, unscaled, fp32
-          for (uint32_t c = 0; c < 2; ++c) {
+          // input gradient: first 64 accumulator columns (the sub == 0 warps), unscaled, fp32
+          for (uint32_t c = 0; c < 2 && sub == 0; ++c) {
             uint32_t r[32];
-            tmem_ld_32x32b_x32(t_row + c * 32, r);
+            tmem_ld_32x32b_x32(t_row + TM_ACC + c * 32, r);
             tmem_ld_wait();
             if (valid) {
               float4* dst = reinterpret_cast<float4*>(p.dfeat + grow * FEAT + c * 32);
@@ -300,17 +341,19 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           tc_fence_before_sync();
           continue;   // last GEMM of the tile: the next tile's prologue re-arms BAR_AREADY
         }
-        if (tid == 0) tma_store_wait_read0();   // the previous TMA store has finished reading the tile
-        epi_bar_sync();
         float yacc[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t* gate_dst = (!BWD && p.gates_out != nullptr && valid) ? p.gates_out + ((size_t)g * p.Q + grow) * 8 : nullptr;
-        // backward: unrolled so that gate[c] stays in registers; forward: rolled (the unrolled body thrashes the
-        // instruction cache: measured 225 -> 291 us)
-#pragma unroll(BWD ? 8 : 1)
-        for (uint32_t c = 0; c < 8; ++c) {
+        // rolled: the unrolled body thrashes the instruction cache (forward measured 225 -> 291 us)
+#pragma unroll 1
+        for (uint32_t c = c_lo; c < c_hi; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + c * 32, r);
-          tmem_ld_wait();
+          if (!(p.dbg & 8)) {
+            tmem_ld_32x32b_x32(t_row + TM_ACC + c * 32, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0x3f000000u + c + j;
+          }
           uint32_t w[16], wl[16];
           if (!BWD) {
             const float* bz = s_bias + g * WID + c * 32;
@@ -335,7 +378,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             }
             if (gate_dst != nullptr) gate_dst[c] = gbits;
           } else {
-            const uint32_t gw = gate[c];
+            const uint32_t gw = (c & 1u) ? gq.y : gq.x;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float d0 = __uint_as_float(r[2 * j]), d1 = __uint_as_float(r[2 * j + 1]);
@@ -346,38 +389,57 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
               wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
             }
           }
-          write_chunk(a_base, c, row, w);
-          write_chunk(base + OFF_ALO, c, row, wl);
-        }
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        epi_bar_sync();
-        if (tid == 0 && p.store) {
-          for (int kb = 0; kb < 4; ++kb) {
-            tma_store_2d(&maps.act[layer], a_base + kb * KB_BYTES, kb * 64, tile * TILE_M);
-            tma_store_2d(&maps.act_lo[layer], base + OFF_ALO + kb * KB_BYTES, kb * 64, tile * TILE_M);
+          if (!(p.dbg & 1)) {
+            tmem_st_32x32b_x16(t_row + TM_AHI + c * 16, w);
+            tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
+          } else if (w[3] == 0x12345678u && wl[5] == 0x9abcdef0u) {
+            p.y[0] = 1.f;   // keeps the math alive
           }
-          tma_store_commit();
+          if (p.store)
+            store_chunk_tma(&maps.out_hi[layer], &maps.out_lo[layer], stage, lane, (int)c * 32,
+                            tile * TILE_M + (int)quad * 32, w, wl);
         }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        if (warp == 0) stamp(p.trace, 2, 10 * g + 2);
         if (!BWD || !last) mbar_arrive(bar(BAR_AREADY));
 
-        if (!BWD && last && valid) {
-          for (int o = 0; o < p.out_dim; ++o) {
-            float v = yacc[o] + p.b_last[o];
-            if (p.out_kind == 1) v = tanhf(v);
-            else if (p.out_kind == 2) v = 1.f / (1.f + expf(-v));
-            p.y[grow * p.out_dim + o] = v;
+        if (!BWD && last) {
+          // output layer: combine the four column quarters of every row in a fixed order (bit-reproducible)
+          if (sub > 0) s_xch[(sub - 1) * TILE_M + row] = make_float4(yacc[0], yacc[1], yacc[2], yacc[3]);
+          epi_bar_sync();
+          if (sub == 0 && valid) {
+            float4 o4 = make_float4(yacc[0], yacc[1], yacc[2], yacc[3]);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const float4 t = s_xch[q * TILE_M + row];
+              o4.x += t.x; o4.y += t.y; o4.z += t.z; o4.w += t.w;
+            }
+            const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o < p.out_dim) {
+                float v = ov[o] + p.b_last[o];
+                if (p.out_kind == 1) v = tanhf(v);
+                else if (p.out_kind == 2) v = 1.f / (1.f + expf(-v));
+                p.y[grow * p.out_dim + o] = v;
+              }
+            }
           }
+          epi_bar_sync();   // s_xch is free again before the next tile's last GEMM
         }
       }
     }
-    if (tid == 0) tma_store_wait0();
+    if (lane == 0) tma_store_wait0();
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == WARP_MMA) tmem_dealloc(tmem_base, 256);
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
+
+int g_relu_dbg = 0;
+long long* g_relu_trace = nullptr;
 
 int check_stage_plan(int n_gemm, const int* stage_begin) {
   if (n_gemm < 1 || n_gemm > MAX_GEMM) return 1;
@@ -388,6 +450,19 @@ int check_stage_plan(int n_gemm, const int* stage_begin) {
 }
 
 }  // namespace
+
+// Timing experiments on the ReLU chain (results are garbage): see ReluParams::dbg.
+extern "C" int neucam_debug_set_relu_flags(int flags) {
+  g_relu_dbg = flags;
+  return 0;
+}
+// Diagnostics: CTA 0 of the next forward launches records (event, clock64) pairs into trace [3][520] int64 (zeroed by
+// the caller): role 0 producer (100 + stage), 1 MMA warp (10 g + {0 wait operand, 1 start, 2 committed}), 2 epilogue
+// warp 0 (10 g + {0 wait accumulator, 1 start, 2 done}).  NULL switches it off.
+extern "C" int neucam_debug_set_relu_trace(void* trace) {
+  g_relu_trace = (long long*)trace;
+  return 0;
+}
 
 // forward of one ReLU MLP.  feat16 [Q,64] fp16 (encoded input, zero padded); w_stages [S*256,64] fp16 (per GEMM:
 // its 256 x 64 K-blocks in order); stage_begin[n_gemm+1]; a_src[S] (0..3 operand k-block, 4 encoded input) and
@@ -413,12 +488,15 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   if (rc) return rc;
   p.feat_last_gemm = 0;
   for (int g = 0; g < n_gemm; ++g) {
-    const __half* a = act16 ? (const __half*)act16 + (size_t)g * Q * WID : (const __half*)feat16;
-    rc = nchost::make_tmap_16b(&maps.act[g], a, (uint64_t)Q, act16 ? WID : FEAT, act16 ? WID : FEAT, TILE_M, 64);
-    if (rc) return rc;
-    const __half* al = act_lo16 ? (const __half*)act_lo16 + (size_t)g * Q * WID : (const __half*)feat16;
-    rc = nchost::make_tmap_16b(&maps.act_lo[g], al, (uint64_t)Q, act16 ? WID : FEAT, act16 ? WID : FEAT, TILE_M, 64);
-    if (rc) return rc;
+    if (act16) {
+      rc = nchost::make_tmap_16b_sw64(&maps.out_hi[g], (const __half*)act16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+      if (rc) return rc;
+      rc = nchost::make_tmap_16b_sw64(&maps.out_lo[g], (const __half*)act_lo16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+      if (rc) return rc;
+    } else {
+      maps.out_hi[g] = maps.feat;
+      maps.out_lo[g] = maps.feat;
+    }
     p.stage_begin[g] = stage_begin[g];
     for (int s = stage_begin[g]; s < stage_begin[g + 1]; ++s) {
       NC_CHECK_ARG(a_src[s] <= 4 && (a_src2[s] == 255 || (a_src2[s] >= 5 && a_src2[s] <= 8)));
@@ -441,6 +519,8 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   p.store = act16 != nullptr;
   p.gates_out = (uint32_t*)gates;
   p.y = y;
+  p.dbg = g_relu_dbg;
+  p.trace = g_relu_trace;
   static bool attr_set = false;
   if (!attr_set) {
     NC_CHECK_CUDA(cudaFuncSetAttribute(relu_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -465,19 +545,14 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
                                    void* dz_lo16, float* dfeat, void* stream) {
   NC_CHECK_ARG(dpre && wT_stages && w_last && gates && scale_dev && dz16 && dz_lo16);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && H >= 1 && H <= MAX_GEMM);
+  NC_CHECK_ARG(H - 1 + (dfeat ? 1 : 0) <= MAX_GEMM);
   const int n_gemm = (H - 1) + (dfeat ? 1 : 0);
   ReluMaps maps;
   ReluParams p{};
-  int rc = nchost::make_tmap_16b(&maps.feat, dz16, (uint64_t)Q, WID, WID, TILE_M, 64);   // unused in this direction
+  int rc = nchost::make_tmap_16b(&maps.feat, wT_stages, 8 * WID, 64, 64, TILE_M, 64);   // unused in this direction
   if (rc) return rc;
   rc = nchost::make_tmap_16b(&maps.w, wT_stages, (uint64_t)(n_gemm > 0 ? n_gemm : 1) * 8 * WID, 64, 64, WID, 64);
   if (rc) return rc;
-  for (int l = 0; l < H; ++l) {
-    rc = nchost::make_tmap_16b(&maps.act[l], (const __half*)dz16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, TILE_M, 64);
-    if (rc) return rc;
-    rc = nchost::make_tmap_16b(&maps.act_lo[l], (const __half*)dz_lo16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, TILE_M, 64);
-    if (rc) return rc;
-  }
   // per K-block: a hi stage (x dz_hi and dz_lo) and a lo stage (x dz_hi)
   for (int g = 0; g <= n_gemm; ++g) p.stage_begin[g] = 8 * g;
   for (int s = 0; s < 8 * n_gemm; ++s) {
@@ -491,6 +566,17 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
   p.H = H;
   p.w_last = w_last;
   p.out_dim = out_dim;
+  for (int l = 0; l < MAX_GEMM; ++l) {
+    if (l < H) {
+      rc = nchost::make_tmap_16b_sw64(&maps.out_hi[l], (const __half*)dz16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+      if (rc) return rc;
+      rc = nchost::make_tmap_16b_sw64(&maps.out_lo[l], (const __half*)dz_lo16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+      if (rc) return rc;
+    } else {
+      maps.out_hi[l] = maps.w;
+      maps.out_lo[l] = maps.w;
+    }
+  }
   p.store = 1;
   p.dpre = dpre;
   p.gates = (const uint32_t*)gates;

@@ -83,6 +83,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// The same wait for phases that are known to be LONG (an epilogue waiting for a whole GEMM, the MMA warp waiting
+// for an epilogue): sleeps between polls so that the spinning warps do not take issue slots from the warps that
+// are working (measured in relu_chain_kernel: 55 % of all executed instructions were try_wait / clock / branch).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t sleep_ns = 64) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t polls = 0;
+  while (true) {
+    __nanosleep(sleep_ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((++polls & 1023u) == 0 && clock64() - t0 > TC05_WAIT_TIMEOUT_CYCLES) {
+      printf("tc05: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
@@ -246,6 +264,21 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (lane = row, 32-bit columns hold two
+// consecutive K elements; one K16 step = 8 columns), as written by tcgen05.st.32x32b.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.

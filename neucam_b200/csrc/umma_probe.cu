@@ -6,7 +6,8 @@
 //   D[128, N] (fp32) = A[128, K] * B[N, K]^T      N % 16 == 0, N <= 256, K % 64 == 0, K <= 256
 //
 // flags: bit0 A is MN-major (global [K,128]); bit1 B is MN-major (global [K,N], N % 64 == 0);
-//        bit2 A is bf16; bit3 B is bf16; bit4 A tile is written by threads (K-major only).
+//        bit2 A is bf16; bit3 B is bf16; bit4 A tile is written by threads (K-major only);
+//        bit5 A operand lives in TENSOR MEMORY (each thread tcgen05.st's its own row; K-major only).
 #include "host_util.h"
 #include "tc05.cuh"
 
@@ -33,6 +34,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const bool a_mn = flags & 1, b_mn = flags & 2;
   const bool a_bf16 = flags & 4, b_bf16 = flags & 8;
   const bool a_manual = flags & 16;
+  const bool a_tmem = flags & 32;
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bar_tma = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
@@ -43,13 +45,27 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     mbar_fence_init();
   }
   if (warp == 0) {
-    tmem_alloc(smem_u32(&tmem_base_slot), 256);
+    tmem_alloc(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_slot;
+  const uint32_t tmem_a = tmem_d + 256;   // A operand region (K / 2 columns)
+
+  if (a_tmem) {
+    // thread = row = TMEM lane: K fp16 values = K/2 packed 32-bit columns, 16 columns per store
+    const uint32_t row = tid;
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = *reinterpret_cast<const uint32_t*>(a_gmem + (size_t)row * K + 2 * (c0 + j));
+      tmem_st_32x32b_x16(tmem_a + ((warp * 32u) << 16) + (uint32_t)c0, w);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+  }
 
   if (a_manual) {
     // every thread copies its own row of A (K-major): 16-byte chunks, XOR-swizzled inside 128 B
@@ -65,9 +81,9 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
 
   if (tid == 0) {
-    const uint32_t tx = b_bytes + (a_manual ? 0u : a_bytes);
+    const uint32_t tx = b_bytes + ((a_manual || a_tmem) ? 0u : a_bytes);
     mbar_arrive_expect_tx(bar_tma, tx);
-    if (!a_manual) {
+    if (!a_manual && !a_tmem) {
       if (a_mn) {
         for (int a = 0; a < 2; ++a) tma_load_2d(a_smem + a * (K * 128), &tmap_a, bar_tma, a * 64, 0);
       } else {
@@ -93,7 +109,8 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       else      ad = make_sdesc_sw128(a_smem + (k16 >> 2) * (128 * 128) + (k16 & 3) * 32, 0, 1024);
       if (b_mn) bd = make_sdesc_sw128(b_smem + k16 * 2048, (uint32_t)K * 128u, 1024);
       else      bd = make_sdesc_sw128(b_smem + (k16 >> 2) * (N * 128) + (k16 & 3) * 32, 0, 1024);
-      umma_f16_ss(tmem_d, ad, bd, idesc, k16 > 0 ? 1u : 0u);
+      if (a_tmem) umma_f16_ts(tmem_d, tmem_a + (uint32_t)k16 * 8u, bd, idesc, k16 > 0 ? 1u : 0u);
+      else        umma_f16_ss(tmem_d, ad, bd, idesc, k16 > 0 ? 1u : 0u);
     }
     umma_commit(bar_mma);
   }
@@ -114,7 +131,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, 256);
+  if (warp == 0) tmem_dealloc(tmem_d, 512);
 }
 
 }  // namespace
@@ -125,7 +142,7 @@ extern "C" int neucam_umma_probe(const void* a, const void* b, float* d, int N, 
   NC_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0);
   NC_CHECK_ARG(K >= 64 && K <= 256 && K % 64 == 0);
   const bool a_mn = flags & 1, b_mn = flags & 2, a_manual = flags & 16;
-  NC_CHECK_ARG(!(a_mn && a_manual));
+  NC_CHECK_ARG(!(a_mn && (a_manual || (flags & 32))));
   NC_CHECK_ARG(!b_mn || N % 64 == 0);
 
   CUtensorMap ta, tb;
@@ -156,7 +173,8 @@ umma_rate_kernel(int N, int iters, int two_cta, int kblocks, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(8) uint64_t bar_dummy[2];
-  const int overhead = kblocks >> 8;   // bits 8..: per-iteration control overhead to emulate (1 = commit, 2 = wait+fence)
+  const int overhead = (kblocks >> 8) & 3;   // bits 8,9: per-iteration control overhead to emulate (1 = commit, 2 = wait+fence)
+  const bool a_in_tmem = (kblocks >> 10) & 1;   // bit 10: A operand from tensor memory (cta_group::1 only)
   kblocks &= 0xff;
   __shared__ uint32_t slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -194,6 +212,7 @@ umma_rate_kernel(int N, int iters, int two_cta, int kblocks, long long* out) {
 #pragma unroll
       for (int k16 = 0; k16 < 4; ++k16) {
         if (two_cta) umma_f16_ss_2cta(tm, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024), make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, 1u);
+        else if (a_in_tmem) umma_f16_ts(tm, tm + 256 + (it % kblocks) * 32 + k16 * 8, make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, 1u);
         else         umma_f16_ss(tm, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024), make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, 1u);
       }
       if (overhead & 1) {

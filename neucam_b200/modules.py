@@ -121,7 +121,7 @@ class _SineMLPFunction(torch.autograd.Function):
     """y = MLP(uv) through the fused tcgen05 chain; backward = dgrad chain + split-K wgrad kernels."""
 
     @staticmethod
-    def forward(ctx, uv, w0, b0, w1, b1, w2, b2, w3, b3, w4, b4):
+    def forward(ctx, grad_enabled, uv, w0, b0, w1, b1, w2, b2, w3, b3, w4, b4):
         Q = uv.shape[0]
         dev = uv.device
         w16 = torch.empty((3 * HID, HID), dtype=torch.float16, device=dev)
@@ -129,7 +129,8 @@ class _SineMLPFunction(torch.autograd.Function):
         w1c, w2c, w3c = w1.contiguous(), w2.contiguous(), w3.contiguous()
         ops.pack_hidden_weights(w1c, w2c, w3c, w16, wT16)
         b_hid = torch.stack((b1, b2, b3)).contiguous()
-        need_grad = any(ctx.needs_input_grad)
+        # needs_input_grad ignores torch.no_grad(), and grad mode is always off inside forward(): the caller samples it
+        need_grad = grad_enabled and any(ctx.needs_input_grad)
         uvc, w0c, b0c, w4c, b4c = uv.contiguous(), w0.contiguous(), b0.contiguous(), w4.contiguous(), b4.contiguous()
         if need_grad:
             act, cos, dz = ops.alloc_chain_workspace(Q, dev)
@@ -158,7 +159,7 @@ class _SineMLPFunction(torch.autograd.Function):
         ops.sine_mlp_wgrad(dz, act, scale, dws, dbs)
         ops.sine_mlp_head_wgrad(act, dy, dw4)
         db4 = dy.sum(0)
-        return duv, dw0, db0, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2], dw4, db4
+        return None, duv, dw0, db0, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2], dw4, db4
 
 
 class FCBlock(MetaModule):
@@ -211,7 +212,7 @@ class FCBlock(MetaModule):
         args = []
         for i in range(5):
             args += [sub[f"{i}.0.weight"], sub[f"{i}.0.bias"]]
-        y = _SineMLPFunction.apply(uv, *args)
+        y = _SineMLPFunction.apply(torch.is_grad_enabled(), uv, *args)
         return y.reshape(*lead, y.shape[-1])
 
 

@@ -30,7 +30,7 @@ _last_activations = []
 def eligible(module):
     """The shapes the chain kernels execute (every uv / alpha network of the shipped configs)."""
     L = module.num_layer
-    if module.in_dim != 3 or L < 3 or L > 9 or module.last_nonlinear not in OUT_KINDS:
+    if module.in_dim != 3 or L < 3 or L > 8 or module.last_nonlinear not in OUT_KINDS:
         return False
     E = module.positional_encoding.out_dim if module.use_encoding else module.in_dim
     if 2 * E > FEAT or (module.use_encoding and E != 3 + 6 * module.positional_encoding.num_frequencies):
@@ -72,7 +72,7 @@ def _u8(values):
 class _ReluMLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, meta, *params):
-        skips, out_kind, nf, E = meta
+        skips, out_kind, nf, E, grad_enabled = meta
         L = len(params) // 2
         H = L - 1
         ws, bs = params[0::2], params[1::2]
@@ -80,7 +80,8 @@ class _ReluMLPFunction(torch.autograd.Function):
         dev = x.device
         lib = _lib.lib()
         stream = _lib.cur_stream()
-        need_grad = any(ctx.needs_input_grad)
+        # needs_input_grad ignores torch.no_grad(), and grad mode is always off inside forward(): the caller samples it
+        need_grad = grad_enabled and any(ctx.needs_input_grad)
         want_dx = ctx.needs_input_grad[0]
 
         feat16 = torch.empty((Q, FEAT), dtype=torch.float16, device=dev)
@@ -119,7 +120,7 @@ class _ReluMLPFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, feat16, act16, y, wT_stages, gates, *ws = ctx.saved_tensors
-        skips, out_kind, nf, E = ctx.meta
+        skips, out_kind, nf, E, _ = ctx.meta
         H = len(ws) - 1
         Q = feat16.shape[0]
         dev = feat16.device
@@ -189,4 +190,4 @@ def fused_forward(module, x):
     for layer in module.layers:
         params += [layer.weight, layer.bias]
     x3 = x.reshape(-1, 3).float().contiguous()
-    return _ReluMLPFunction.apply(x3, (skips, OUT_KINDS[module.last_nonlinear], nf, E), *params)
+    return _ReluMLPFunction.apply(x3, (skips, OUT_KINDS[module.last_nonlinear], nf, E, torch.is_grad_enabled()), *params)

@@ -22,6 +22,8 @@ CASES = [
     (256, 128, 1 | 4 | 8, "a_mn_b_k_bf16"),
     (64, 64, 0, "n64"),
     (16, 64, 0, "n16"),
+    (128, 64, 32, "a_in_tmem_small"),      # A operand read from tensor memory (tcgen05.st-written rows)
+    (256, 256, 32, "a_in_tmem"),
 ]
 
 
