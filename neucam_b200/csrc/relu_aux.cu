@@ -82,19 +82,21 @@ struct PackPlan {
   StageDesc d[MAX_DESC];
 };
 
-// one CTA per stage: out[256 rows][64 cols] fp16
+// 8 CTAs per stage (blockIdx.y = 32-row slice for the forward blocks / 8-column slice for the transposed ones):
+// out[256 rows][64 cols] fp16
 __global__ void __launch_bounds__(256)
 pack_kernel(const __grid_constant__ PackPlan plan, int n_fwd, __half* __restrict__ w_stages,
             __half* __restrict__ wT_stages) {
   const StageDesc& d = plan.d[blockIdx.x];
   __half* out = (blockIdx.x < n_fwd ? w_stages + (size_t)blockIdx.x * WID * 64
                                     : wT_stages + (size_t)(blockIdx.x - n_fwd) * WID * 64);
-  for (int e = threadIdx.x; e < WID * 64; e += 256) {
+  const int e0 = blockIdx.y * (WID * 64 / 8);
+  for (int e = e0 + threadIdx.x; e < e0 + WID * 64 / 8; e += 256) {
     int n, k;
     float v = 0.f;
     if (d.kind == 2) {
-      // transposed: row n = input feature, column k = output neuron kb*64 + k; read along k? no: along n is the
-      // contiguous source direction (W[j][n]); make consecutive threads walk n
+      // transposed: row n = input feature, column k = output neuron kb*64 + k; the contiguous SOURCE direction is n
+      // (W[j][n]), so consecutive threads walk n
       n = e % WID; k = e / WID;
       if (n < d.in_rows) v = d.w[(size_t)(d.kb * 64 + k) * d.ld + n];
     } else {
@@ -160,7 +162,7 @@ extern "C" int neucam_relu_mlp_pack(const float* const* w, const int* ld, int L,
       d.in_rows = (l == 0) ? E : WID;
     }
   }
-  pack_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(plan, S, (__half*)w_stages, (__half*)wT_stages);
+  pack_kernel<<<dim3(n, 8), 256, 0, (cudaStream_t)stream>>>(plan, S, (__half*)w_stages, (__half*)wT_stages);
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
