@@ -282,9 +282,22 @@ class FusedTrainStep:
         return n
 
     # -- the step ------------------------------------------------------------------------------------------
-    def forward_backward(self, use_mask=False):
-        """Runs S2..S14 on the batch currently in the device buffers; gradients land in params.grad."""
+    def forward_backward(self, use_mask=False, events=None):
+        """Runs S2..S14 on the batch currently in the device buffers; gradients land in params.grad.
+        events: optional list; the three tensor-core kernels are then bracketed by CUDA events on the launch stream
+        and (name, start, end) tuples appended (bench.py: per-kernel durations inside real steps)."""
         o = self.opt
+
+        def timed(name, fn):
+            if events is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            events.append((name, e0, e1))
+            return out
+
         P = self.params
         P.zero_grad()
         self.scalars.zero_()
@@ -295,8 +308,9 @@ class FusedTrainStep:
             uv = self.uv.view(-1, 2)
         else:
             uv = self.coords[:, 1:3].contiguous()
-        ops.sine_mlp_fwd(uv, self.aw[0].data, self.ab[0].data, self.w16, self.b_hid, self.aw[4].data, self.ab[4].data,
-                         y=self.y.view(-1, self.out_dim), act16=self.act16, phase16=self.phase16)
+        timed("sine_chain_fwd", lambda: ops.sine_mlp_fwd(
+            uv, self.aw[0].data, self.ab[0].data, self.w16, self.b_hid, self.aw[4].data, self.ab[4].data,
+            y=self.y.view(-1, self.out_dim), act16=self.act16, phase16=self.phase16))
         ops.psf_crf_loss(self.y, self.kout if self.has_blur else None, self.coord_idx, self.exps.data, None, self.img,
                          self.gamma_w if o.use_random_gamma else None, self.mask_w if use_mask else None,
                          [p.data for p in self.tm_p], self.tm_g, self.shape, K, self.has_blur,
@@ -304,10 +318,12 @@ class FusedTrainStep:
                          3 * self.global_pixels, self.dy, self.dkw if self.has_blur else None, self.exps.grad,
                          self.ab[4].grad, self.sums, self.absmax_bits.view(torch.int32), self.scale)
         dyf = self.dy.view(-1, self.out_dim)
-        ops.sine_mlp_bwd(uv, self.aw[0].data, self.ab[0].data, self.wT16, self.w4T16, dyf, self.phase16, self.scale,
-                         self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2))
-        ops.sine_mlp_wgrad(self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
-                           [self.ab[i].grad for i in (1, 2, 3)])
+        timed("sine_chain_bwd", lambda: ops.sine_mlp_bwd(
+            uv, self.aw[0].data, self.ab[0].data, self.wT16, self.w4T16, dyf, self.phase16, self.scale,
+            self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2)))
+        timed("hidden_wgrad", lambda: ops.sine_mlp_wgrad(
+            self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
+            [self.ab[i].grad for i in (1, 2, 3)]))
         # the HBM-bound head wgrad and the FMA-bound blur backward are independent: run them side by side
         main = torch.cuda.current_stream(self.device)
         if self.has_blur:
