@@ -189,6 +189,17 @@ int neucam_psf_crf_loss(const float* y, const float* kout, const int64_t* coord_
                         uint32_t* dy_absmax_bits, float scale_target, float* scale_out, float* ldr_out,
                         void* stream);
 
+/* neucam_rigidity_loss (utils.get_rigidity_loss, utils.py:402-454, as called at training.py:203-217; value and
+ *   gradient in one pass): uv_ref [B,2] = the uv mapping at the step's pixels, uv_moved [2,B,2] = at the pixel one row
+ *   up / one column left.  ku = (H-1)/2 / uv_mapping_scale, kv = (W-1)/2 / uv_mapping_scale (the reference scales both
+ *   u differences by H-1 and both v differences by W-1).  *coef_dev (device scalar) = loss weight / B (x data-parallel
+ *   share x mean mask weight).  loss_sum[0] += coef * sum L_i; g_ref [B,2], g_moved [2,B,2] = coef * gradients.
+ * neucam_loss_scale: scale_out[0] = 2^floor(log2(target / max|x|)) clamped to [2^-20, 2^64] (1 if max|x| is 0 or not
+ *   finite): the loss scale of the fp16 backward chains, computed on the device. */
+int neucam_rigidity_loss(const float* uv_ref, const float* uv_moved, int B, float ku, float kv, const float* coef_dev,
+                         float* loss_sum, float* g_ref, float* g_moved, void* stream);
+int neucam_loss_scale(const float* x, int64_t n, float target, uint32_t* scratch_bits, float* scale_out, void* stream);
+
 /* neucam_tm_min_slope: the VALUE-ONLY CRF gradient regulariser of training.py:248-252 (TonemapNet.forward with
  *   output_grads=True, modules.py:249-251): min over M points of d mean(ldr)/d lnx for rad [M,3], expo [M,1].
  *   *min_bits receives an order-preserving uint32 encoding of the float minimum (decode: b & 0x80000000 ?

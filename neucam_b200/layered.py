@@ -89,6 +89,7 @@ class LayeredTrainStep:
         self._off_centre = torch.ones(self.K, 1, 1, device=self.device)
         self._off_centre[self.K // 2] = 0.0      # the centre tap stays on the pixel (training.py:120)
         self._black = (torch.zeros(1, 3, device=self.device), torch.zeros(1, 1, device=self.device))
+        self._one = torch.ones(1, device=self.device)
         self.step_index = 0
         self._losses = None
 
@@ -124,6 +125,13 @@ class LayeredTrainStep:
         pts = coords[0]
         moved = torch.cat((pts - self._one_row_up, pts - self._one_col_left), 0)
         uv_moved = ((self.models[slot](moved) + moved[:, 1:3]) * 0.5).view(2, -1, 2)
+        if self.params is not None:
+            # product path: value and analytic gradient of the 2x2 algebra in one kernel; the mean over pixels (and
+            # the reference's mean(loss) * mean(weights), utils.py:452-453) is folded into the device scalar `coef`
+            coef = self._one * (1.0 / pts.shape[0])
+            if mask is not None:
+                coef = coef * mask.mean()
+            return pixel_ops.rigidity_loss(uv_ref, uv_moved, coef, self.shape, self.opt.uv_mapping_scale)
         d_up, d_left = uv_ref.reshape(-1, 2) - uv_moved[0], uv_ref.reshape(-1, 2) - uv_moved[1]
         s = 1.0 / self.opt.uv_mapping_scale
         a, b = d_left[:, 0] * ((h - 1) / 2 * s), d_up[:, 0] * ((h - 1) / 2 * s)      # du/dx, du/dy

@@ -97,8 +97,13 @@ SCALE_TARGET = 16.0
 
 def loss_scale_from(dy):
     """Power-of-two loss scale 2^floor(log2(SCALE_TARGET / max|dy|)) as a device scalar (no host sync)."""
-    m = dy.abs().max().clamp_min(1e-30)
-    return torch.exp2(torch.floor(torch.log2(SCALE_TARGET / m))).clamp(2.0 ** -20, 2.0 ** 64).reshape(1).float()
+    _chk_cuda(dy)
+    dy = dy.contiguous()
+    out = torch.empty(2, dtype=torch.float32, device=dy.device)      # [scale, scratch bits]
+    rc = _lib.lib().neucam_loss_scale(_lib.ptr(dy), ctypes.c_int64(dy.numel()), ctypes.c_float(SCALE_TARGET),
+                                      _lib.ptr(out[1:]), _lib.ptr(out), _lib.cur_stream())
+    _lib.check(rc, "neucam_loss_scale")
+    return out[:1]
 
 
 def _ptr_array(tensors):

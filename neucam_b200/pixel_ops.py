@@ -6,9 +6,11 @@
   psf_crf_loss     PSF sum, exposure, TonemapNet, image_mse (+ random gamma, mask), ue_loss (training.py:157-188,
                    244-245): the kernel computes the loss AND every gradient in one pass; backward hands them out
 """
+import ctypes
+
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class _BlurTaps(torch.autograd.Function):
@@ -92,3 +94,33 @@ def psf_crf_loss(y, kw, exps, fixed_exps, tm_module, shape, K, fixed_value, ue_w
     by ue_weight (1 / world size)."""
     return _PsfCrfLoss.apply(y, kw, exps, fixed_exps, (tuple(shape), int(K), fixed_value, ue_weight, global_pixels),
                              coord_idx, gt, gamma_w, mask_w, gamma_dev, *tm_module.parameters())
+
+
+class _Rigidity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uv_ref, uv_moved, coef, ku, kv):
+        B = uv_ref.shape[0]
+        dev = uv_ref.device
+        out = torch.zeros(1, device=dev)
+        g_ref = torch.empty((B, 2), device=dev)
+        g_moved = torch.empty((2, B, 2), device=dev)
+        rc = _lib.lib().neucam_rigidity_loss(_lib.ptr(uv_ref), _lib.ptr(uv_moved), B, ctypes.c_float(ku),
+                                             ctypes.c_float(kv), _lib.ptr(coef), _lib.ptr(out), _lib.ptr(g_ref),
+                                             _lib.ptr(g_moved), _lib.cur_stream())
+        _lib.check(rc, "neucam_rigidity_loss")
+        ctx.save_for_backward(g_ref, g_moved)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        g_ref, g_moved = ctx.saved_tensors
+        return g_ref * g, g_moved * g, None, None, None
+
+
+def rigidity_loss(uv_ref, uv_moved, coef, shape, uv_mapping_scale):
+    """coef * sum over the B pixels of |J^T J|_F + |(J^T J + 0.001 I)^-1|_F (utils.py:402-454); uv_ref [B,2] is the
+    mapping at the pixels, uv_moved [2,B,2] at the pixels one row up / one column left; coef: device scalar [1]."""
+    n, h, w = shape
+    ku, kv = (h - 1) / 2.0 / uv_mapping_scale, (w - 1) / 2.0 / uv_mapping_scale
+    return _Rigidity.apply(uv_ref.reshape(-1, 2).contiguous(), uv_moved.reshape(2, -1, 2).contiguous(),
+                           coef.reshape(1).float().contiguous(), float(ku), float(kv))
