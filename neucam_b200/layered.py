@@ -25,7 +25,7 @@ from collections import OrderedDict
 
 import torch
 
-from . import _lib, ops, pixel_ops
+from . import _gradmode, _lib, ops, pixel_ops
 from .step import FlatParameters, StepOptions, flat_adam  # noqa: F401  (StepOptions re-exported)
 
 _LAYER_SLOTS = ("uv_b", "uv_f", "atlas_f", "alpha")
@@ -235,8 +235,10 @@ class LayeredTrainStep:
         if self.params is None:
             raise _lib.NeucamNativeError("LayeredTrainStep was built for host-logic tests only; no optimizer state")
         self.params.zero_grad()
-        losses = self.forward(model_input, gt, gamma, use_mask)
-        losses["total"].backward()
+        # the flat gradient buffer is preallocated and zeroed: the fused networks' weight-gradient kernels add into it
+        with _gradmode.accumulate_into_param_grad():
+            losses = self.forward(model_input, gt, gamma, use_mask)
+            losses["total"].backward()
         self._losses = OrderedDict((k, v.detach()) for k, v in losses.items())
         return self._losses
 

@@ -30,7 +30,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import _lib, ops
+from . import _gradmode, _lib, ops
 
 HID = ops.HID
 
@@ -121,7 +121,8 @@ class _SineMLPFunction(torch.autograd.Function):
     """y = MLP(uv) through the fused tcgen05 chain; backward = dgrad chain + split-K wgrad kernels."""
 
     @staticmethod
-    def forward(ctx, grad_enabled, uv, w0, b0, w1, b1, w2, b2, w3, b3, w4, b4):
+    def forward(ctx, opts, uv, w0, b0, w1, b1, w2, b2, w3, b3, w4, b4):
+        grad_enabled, ctx.grad_targets = opts
         Q = uv.shape[0]
         dev = uv.device
         w16 = torch.empty((3 * HID, HID), dtype=torch.float16, device=dev)
@@ -150,14 +151,23 @@ class _SineMLPFunction(torch.autograd.Function):
         dev = uv.device
         dy = dy.contiguous().float()
         scale = ops.loss_scale_from(dy)
-        dw0 = torch.zeros_like(w0)
-        db0 = torch.zeros_like(b0)
-        dws = [torch.zeros((HID, HID), dtype=torch.float32, device=dev) for _ in range(3)]
-        dbs = [torch.zeros((HID,), dtype=torch.float32, device=dev) for _ in range(3)]
-        dw4 = torch.zeros_like(w4)
+        tg = ctx.grad_targets
+        if tg is not None:
+            # the step owns preallocated gradient buffers: every kernel below ACCUMULATES, so let them add straight
+            # into param.grad and hand autograd nothing for the parameters
+            dw0, db0, dws, dbs, dw4 = tg[0], tg[1], [tg[2], tg[4], tg[6]], [tg[3], tg[5], tg[7]], tg[8]
+        else:
+            dw0 = torch.zeros_like(w0)
+            db0 = torch.zeros_like(b0)
+            dws = [torch.zeros((HID, HID), dtype=torch.float32, device=dev) for _ in range(3)]
+            dbs = [torch.zeros((HID,), dtype=torch.float32, device=dev) for _ in range(3)]
+            dw4 = torch.zeros_like(w4)
         duv = ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, cos, scale, dz, dw0, db0)
         ops.sine_mlp_wgrad(dz, act, scale, dws, dbs)
         ops.sine_mlp_head_wgrad(act, dy, dw4)
+        if tg is not None:
+            tg[9].add_(dy.sum(0))
+            return (None, duv) + (None,) * 10
         db4 = dy.sum(0)
         return None, duv, dw0, db0, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2], dw4, db4
 
@@ -212,7 +222,7 @@ class FCBlock(MetaModule):
         args = []
         for i in range(5):
             args += [sub[f"{i}.0.weight"], sub[f"{i}.0.bias"]]
-        y = _SineMLPFunction.apply(torch.is_grad_enabled(), uv, *args)
+        y = _SineMLPFunction.apply((torch.is_grad_enabled(), _gradmode.targets_of(args)), uv, *args)
         return y.reshape(*lead, y.shape[-1])
 
 

@@ -18,7 +18,7 @@ import ctypes
 
 import torch
 
-from . import _lib, ops
+from . import _gradmode, _lib, ops
 
 WID = 256
 FEAT = 64
@@ -72,7 +72,7 @@ def _u8(values):
 class _ReluMLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, meta, *params):
-        skips, out_kind, nf, E, grad_enabled = meta
+        skips, out_kind, nf, E, grad_enabled, ctx.grad_targets = meta
         L = len(params) // 2
         H = L - 1
         ws, bs = params[0::2], params[1::2]
@@ -120,7 +120,7 @@ class _ReluMLPFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, feat16, act16, y, wT_stages, gates, *ws = ctx.saved_tensors
-        skips, out_kind, nf, E, _ = ctx.meta
+        skips, out_kind, nf, E = ctx.meta[:4]
         H = len(ws) - 1
         Q = feat16.shape[0]
         dev = feat16.device
@@ -149,15 +149,21 @@ class _ReluMLPFunction(torch.autograd.Function):
             dx = torch.empty_like(x)
             _lib.check(lib.neucam_relu_mlp_encode_bwd(_lib.ptr(x), _lib.ptr(dfeat), ctypes.c_int64(Q), nf,
                                                       _lib.ptr(dx), stream), "neucam_relu_mlp_encode_bwd")
-        # weight gradients: one zero-filled buffer holds every dW / db plus the encoded-layout scratch tiles
-        sizes = [w.numel() for w in ws] + [w.shape[0] for w in ws]
+        # weight gradients.  The kernels ACCUMULATE: into param.grad directly when the step owns preallocated gradient
+        # buffers (nothing is then returned for the parameters), else into one zero-filled temporary.
         skip_slot = {l: 1 + i for i, l in enumerate(sorted(skips))}
         enc_numel = (1 + len(skips)) * WID * FEAT
-        buf = torch.zeros(sum(sizes) + enc_numel, dtype=torch.float32, device=dev)
-        parts = list(torch.split(buf, sizes + [enc_numel]))
-        dw = [parts[i].view_as(ws[i]) for i in range(H + 1)]
-        db = parts[H + 1:2 * (H + 1)]
-        enc = parts[-1].view(1 + len(skips), WID, FEAT)                        # dw_first, dw_skip...
+        tg = ctx.grad_targets
+        if tg is not None:
+            dw, db = list(tg[0::2]), list(tg[1::2])
+            enc = torch.zeros(enc_numel, dtype=torch.float32, device=dev).view(1 + len(skips), WID, FEAT)
+        else:
+            sizes = [w.numel() for w in ws] + [w.shape[0] for w in ws]
+            buf = torch.zeros(sum(sizes) + enc_numel, dtype=torch.float32, device=dev)
+            parts = list(torch.split(buf, sizes + [enc_numel]))
+            dw = [parts[i].view_as(ws[i]) for i in range(H + 1)]
+            db = list(parts[H + 1:2 * (H + 1)])
+            enc = parts[-1].view(1 + len(skips), WID, FEAT)                    # dw_first, dw_skip...
         arr = lambda items: (ctypes.c_void_p * len(items))(*[0 if t is None else t.data_ptr() for t in items])
         ldw = (ctypes.c_int * H)(*[int(w.shape[1]) for w in ws[:H]])
         rc = lib.neucam_relu_mlp_wgrad(_lib.ptr(dz16[0]), _lib.ptr(dz16[1]), _lib.ptr(act16[0]), _lib.ptr(act16[1]),
@@ -168,9 +174,14 @@ class _ReluMLPFunction(torch.autograd.Function):
         rc = lib.neucam_relu_mlp_head_wgrad(_lib.ptr(act16[0, H - 1]), _lib.ptr(act16[1, H - 1]), _lib.ptr(dpre),
                                             out_dim, ctypes.c_int64(Q), _lib.ptr(dw[H]), stream)
         _lib.check(rc, "neucam_relu_mlp_head_wgrad")
-        db = list(db)
-        db[H] = dpre.sum(0)
         fold = lambda e: e[:, :E] + e[:, E:2 * E]      # hi + lo halves of the features
+        if tg is not None:
+            db[H].add_(dpre.sum(0))
+            dw[0].add_(fold(enc[0]))
+            for l, slot in skip_slot.items():
+                dw[l][:, WID:].add_(fold(enc[slot]))
+            return (dx, None) + (None,) * (2 * (H + 1))
+        db[H] = dpre.sum(0)
         dw[0] = fold(enc[0])
         for l, slot in skip_slot.items():
             dw[l][:, WID:] = fold(enc[slot])
@@ -190,4 +201,5 @@ def fused_forward(module, x):
     for layer in module.layers:
         params += [layer.weight, layer.bias]
     x3 = x.reshape(-1, 3).float().contiguous()
-    return _ReluMLPFunction.apply(x3, (skips, OUT_KINDS[module.last_nonlinear], nf, E, torch.is_grad_enabled()), *params)
+    meta = (skips, OUT_KINDS[module.last_nonlinear], nf, E, torch.is_grad_enabled(), _gradmode.targets_of(params))
+    return _ReluMLPFunction.apply(x3, meta, *params)

@@ -54,11 +54,13 @@ def _record_call_scales(monkeypatch, models):
     orig = relu_mlp._ReluMLPFunction.backward
 
     def recording_backward(ctx, dy):
-        out = orig(ctx, dy)
+        # inside a training step the kernels add straight into param.grad (ctx.grad_targets) and return None
         slot = first_weight[ctx.saved_tensors[6].data_ptr()]
-        for i, g in enumerate(out[2:]):
+        before = [g.clone() for g in ctx.grad_targets]
+        out = orig(ctx, dy)
+        for i, (g0, g1) in enumerate(zip(before, ctx.grad_targets)):
             name = f"layers.{i // 2}.{'weight' if i % 2 == 0 else 'bias'}"
-            scales[(slot, name)] = scales.get((slot, name), 0.0) + g.double().norm().item()
+            scales[(slot, name)] = scales.get((slot, name), 0.0) + (g1 - g0).double().norm().item()
         return out
 
     monkeypatch.setattr(relu_mlp._ReluMLPFunction, "backward", staticmethod(recording_backward))
