@@ -219,3 +219,30 @@ def test_graph_step_equals_eager_step():
         # sign-step under a different atomics order, hence the 1e-4 bound on single entries and 2e-6 on the mean
         d = (results[1][key] - p).abs()
         assert d.max().item() < 1.5e-4 and d.mean().item() < 2e-6, (key, d.max().item(), d.mean().item())
+
+
+def test_layered_training_reduces_the_image_loss():
+    """60 graph-replayed steps of the two-layer video_hdr model set on a fixed synthetic target: the image loss has to
+    come down (end-to-end sanity of forward, backward, Adam and the CUDA-graph path together)."""
+    kind = "video_hdr"
+    shape = SHAPES[kind]
+    spec = harness.LAYERED_CONFIGS[kind]
+    models = harness.build_layered_models(kind, shape, seed=4)
+    opts = StepOptions(lr=1e-4, **spec["options"])
+    step = LayeredTrainStep(models, shape, opts, device="cuda")
+    g = torch.Generator().manual_seed(9)
+    grid = harness.mgrid(shape)
+    n, h, w = shape
+    # a smooth picture that moves slowly over the frames, in [-1, 1]
+    t, y, x = grid[:, 0], grid[:, 1], grid[:, 2]
+    target = torch.stack((torch.sin(3 * x + t), torch.cos(2 * y - t), torch.sin(2 * x * y)), -1) * 0.6
+    first = last = None
+    for it in range(60):
+        idx = torch.randint(0, grid.shape[0], (1024,), generator=g)
+        b = {"coords": grid[idx][None], "coord_idx": idx[None], "img": target[idx][None]}
+        losses = step.graph_step(b, {"img": b["img"]})
+        if it == 0:
+            first = losses["img_loss"].item()
+    last = losses["img_loss"].item()
+    assert torch.isfinite(torch.tensor(last))
+    assert last < 0.6 * first, (first, last)
