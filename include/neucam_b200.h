@@ -200,6 +200,18 @@ int neucam_rigidity_loss(const float* uv_ref, const float* uv_moved, int B, floa
                          float* loss_sum, float* g_ref, float* g_moved, void* stream);
 int neucam_loss_scale(const float* x, int64_t n, float target, uint32_t* scratch_bits, float* scale_out, void* stream);
 
+/* neucam_layer_blend_fwd / _bwd (training.py:143-153 layer blend with the alpha MLP's output; 220-238 sparsity and
+ *   alpha losses): back, front, out [K,B,3] (log radiance per tap), alpha [K,B]; a_ref = alpha of the centre tap.
+ *   sums[0] += c1 * sum_{k,b} (1-a_ref)^2 sum_c exp(front)^2, sums[1] += c2 * sum_b -1/(log(a_ref+1e-24)+log(1-a_ref+1e-24)),
+ *   sums[2] += c3 * sum_b a_ref  (the caller folds weights, means and the data-parallel share into c1..c3; 0 = off).
+ *   e2 [K,B] is scratch handed from forward to backward.  The backward takes dout = dL/d out and the device scalar
+ *   *g_reg = dL/d(the three sums) and writes d_back, d_front [K,B,3], d_alpha [K,B]. */
+int neucam_layer_blend_fwd(const float* back, const float* front, const float* alpha, int K, int B, float c1, float c2,
+                           float c3, float* out, float* e2, float* sums, void* stream);
+int neucam_layer_blend_bwd(const float* dout, const float* back, const float* front, const float* alpha,
+                           const float* e2, const float* g_reg, int K, int B, float c1, float c2, float c3,
+                           float* d_back, float* d_front, float* d_alpha, void* stream);
+
 /* neucam_tm_min_slope: the VALUE-ONLY CRF gradient regulariser of training.py:248-252 (TonemapNet.forward with
  *   output_grads=True, modules.py:249-251): min over M points of d mean(ldr)/d lnx for rad [M,3], expo [M,1].
  *   *min_bits receives an order-preserving uint32 encoding of the float minimum (decode: b & 0x80000000 ?

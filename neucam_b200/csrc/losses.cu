@@ -1,6 +1,8 @@
 // losses.cu -- the regularisers of the layered configs as single-pass kernels (value AND gradient), and the
 // device-side power-of-two loss scale the fp16 backward chains use.
 //
+//   layer blend     (1 - alpha) back + alpha front with the sparsity / alpha regularisers (training.py:143-153,
+//                   220-238), forward and backward kernels (second half of this file)
 //   rigidity loss   reference utils.get_rigidity_loss (utils.py:402-454, derivative_amount = 1), called at
 //                   training.py:203-217: backward-difference Jacobian J = d(u,v)/d(x,y) of the uv mapping between a
 //                   pixel and its upper / left neighbour, loss = |J^T J|_F + |(J^T J + 0.001 I)^-1|_F, in closed form
@@ -101,6 +103,125 @@ extern "C" int neucam_loss_scale(const float* x, int64_t n, float target, uint32
   absmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, scratch_bits);
   NC_CHECK_CUDA(cudaGetLastError());
   scale_from_bits_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scratch_bits, target, scale_out);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// layer blend + sparsity / alpha regularisers (reference training.py:143-153 and 220-234, alpha from the alpha MLP)
+//   out      = (1 - a) * back + a * front                      per tap (k, b)
+//   sparse1  = w1 * mean_{k,b} (1 - a_ref[b])^2 * sum_c exp(front[k,b,c])^2          (|(1-a) e^front|^2, 226-227)
+//   sparse2  =      mean_b  -1 / (log(a_ref + 1e-24) + log(1 - a_ref + 1e-24))        (231; the reference multiplies
+//                                                                                      by the boolean flag = 1)
+//   alpha    = w3 * mean_b a_ref[b]                                                    (236-238)
+// a_ref = alpha of the centre tap (training.py:153).  The caller folds the means and the data-parallel share into
+// c1 = w1 * share / (K B), c2 = share / B, c3 = w3 * share / B (0 switches a term off).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// thread = tap (k, b).  sums[0..2] += this block's share of sparse1, sparse2, alpha.
+__global__ void __launch_bounds__(256)
+blend_fwd_kernel(const float* __restrict__ back, const float* __restrict__ front, const float* __restrict__ alpha,
+                 int K, int B, float c1, float c2, float c3, float* __restrict__ out, float* __restrict__ e2,
+                 float* __restrict__ sums) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)K * B;
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < n) {
+    const int k = (int)(i / B), b = (int)(i % B);
+    const float a = alpha[i];
+    const float a_ref = alpha[(long long)(K / 2) * B + b];
+    const float* fb = back + 3 * i;
+    const float* ff = front + 3 * i;
+    float e = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out[3 * i + c] = (1.f - a) * fb[c] + a * ff[c];
+      const float x = expf(ff[c]);
+      e = fmaf(x, x, e);
+    }
+    e2[i] = e;
+    s1 = c1 * (1.f - a_ref) * (1.f - a_ref) * e;
+    if (k == K / 2) {
+      s2 = c2 * (-1.f / (logf(a_ref + 1e-24f) + logf(1.f - a_ref + 1e-24f)));
+      s3 = c3 * a_ref;
+    }
+  }
+  __shared__ float s_part[3][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_part[0][threadIdx.x >> 5] = s1;
+    s_part[1][threadIdx.x >> 5] = s2;
+    s_part[2][threadIdx.x >> 5] = s3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+
+// gradients of  <dout, out> + g * (sparse1 + sparse2 + alpha)  w.r.t. back, front and alpha
+__global__ void __launch_bounds__(256)
+blend_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ back, const float* __restrict__ front,
+                 const float* __restrict__ alpha, const float* __restrict__ e2, const float* __restrict__ g_reg,
+                 int K, int B, float c1, float c2, float c3, float* __restrict__ d_back, float* __restrict__ d_front,
+                 float* __restrict__ d_alpha) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)K * B) return;
+  const int k = (int)(i / B), b = (int)(i % B);
+  const float g = *g_reg;
+  const float a = alpha[i];
+  const float a_ref = alpha[(long long)(K / 2) * B + b];
+  const float w = g * c1 * (1.f - a_ref) * (1.f - a_ref);
+  float da = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float dy = dout[3 * i + c], fb = back[3 * i + c], ff = front[3 * i + c];
+    d_back[3 * i + c] = (1.f - a) * dy;
+    const float x = expf(ff);
+    d_front[3 * i + c] = a * dy + w * 2.f * x * x;
+    da = fmaf(ff - fb, dy, da);
+  }
+  if (k == K / 2) {
+    float esum = 0.f;
+    for (int kk = 0; kk < K; ++kk) esum += e2[(long long)kk * B + b];
+    const float l = logf(a_ref + 1e-24f) + logf(1.f - a_ref + 1e-24f);
+    const float ds2 = (1.f / (a_ref + 1e-24f) - 1.f / (1.f - a_ref + 1e-24f)) / (l * l);
+    da += g * (-2.f * c1 * (1.f - a_ref) * esum + c2 * ds2 + c3);
+  }
+  d_alpha[i] = da;
+}
+
+}  // namespace
+
+// back, front, out [K,B,3]; alpha [K,B]; e2 [K,B] scratch kept for the backward; sums[3] += (sparse1, sparse2, alpha).
+extern "C" int neucam_layer_blend_fwd(const float* back, const float* front, const float* alpha, int K, int B,
+                                      float c1, float c2, float c3, float* out, float* e2, float* sums, void* stream) {
+  NC_CHECK_ARG(back && front && alpha && out && e2 && sums && K >= 1 && B > 0);
+  const long long n = (long long)K * B;
+  blend_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(back, front, alpha, K, B, c1, c2, c3,
+                                                                                   out, e2, sums);
+  NC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dout [K,B,3] = dL/d out; *g_reg (device scalar) = dL/d(sparse1 + sparse2 + alpha).  Writes d_back, d_front [K,B,3]
+// and d_alpha [K,B].
+extern "C" int neucam_layer_blend_bwd(const float* dout, const float* back, const float* front, const float* alpha,
+                                      const float* e2, const float* g_reg, int K, int B, float c1, float c2, float c3,
+                                      float* d_back, float* d_front, float* d_alpha, void* stream) {
+  NC_CHECK_ARG(dout && back && front && alpha && e2 && g_reg && d_back && d_front && d_alpha && K >= 1 && B > 0);
+  const long long n = (long long)K * B;
+  blend_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dout, back, front, alpha, e2, g_reg, K,
+                                                                                   B, c1, c2, c3, d_back, d_front,
+                                                                                   d_alpha);
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,8 +12,10 @@ What runs where:
     image_mse (+gamma, mask) + ue_loss         psf_crf_loss -- forward and gradients in one pass)
   * Adam over every model                      ONE fused launch over the flat parameter buffer (adam.cu)
   * value-only grad_loss                       neucam_tm_min_slope
-  * warp = (mlp + position) / 2, layer blend,  torch elementwise ops on the device under autograd
-    rigidity / sparsity / alpha losses
+  * rigidity loss; layer blend + sparsity /    losses.cu through pixel_ops.py (values and analytic gradients)
+    alpha losses
+  * warp = (mlp + position) / 2, tap           torch elementwise ops on the device under autograd
+    assembly, final sums
 
 Nothing here has a CPU path: the scene networks raise on CPU tensors and the optimizer is the CUDA kernel.
 
@@ -166,6 +168,7 @@ class LayeredTrainStep:
             taps = torch.cat((coords[..., :1].expand(K, -1, -1), uv_taps), -1)
         else:
             taps, psf = self._taps(coords, coord_idx)
+        reg_total = reg_values = None
         uv_b = self._warp("uv_b", taps) if m.get("uv_b") is not None else taps[..., 1:]
         radiance = m["atlas_b"]({"coords": uv_b})["model_out"]                             # [K,B,3] log radiance
         alpha = front = uv_f = None
@@ -176,7 +179,15 @@ class LayeredTrainStep:
             if front is None:
                 raise ValueError("atlas_f without uv_f: the reference would fail at training.py:149 as well")
             alpha = m["alpha"](taps).view(K, -1, 1) if m.get("alpha") is not None else torch.sigmoid(front[..., -1:])
-            radiance = torch.lerp(radiance, front[..., 0:3], alpha)                        # training.py:152
+            if kernels and m.get("alpha") is not None and front.shape[-1] == 3:
+                # layer blend + sparsity / alpha regularisers (values and gradients) in one kernel pair
+                n_taps = float(K * B)
+                c1 = opt.sparsity_loss_w * share / n_taps if opt.sparsity_loss_w is not None else 0.0
+                c2 = share / B if opt.sparsity_loss_w is not None else 0.0
+                c3 = opt.alpha_loss_w * share / B if opt.alpha_loss_w is not None else 0.0
+                radiance, reg_total, reg_values = pixel_ops.layer_blend(radiance, front, alpha, c1, c2, c3)
+            else:
+                radiance = torch.lerp(radiance, front[..., 0:3], alpha)                    # training.py:152
             alpha = alpha[K // 2].unsqueeze(0)
         mask = model_input["weights"].to(dev, torch.float32).view(-1, 1) if use_mask else None
         losses = OrderedDict()
@@ -213,7 +224,12 @@ class LayeredTrainStep:
             if uv_f is not None:
                 rig = rig + self._rigidity("uv_f", coords, uv_f[K // 2], mask)
             losses["rigidity_loss"] = rig * (opt.rigidity_loss_w * share)
-        if uv_f is not None:                                                               # training.py:220-234
+        if reg_values is not None:                                                         # training.py:220-238
+            if opt.sparsity_loss_w is not None:
+                losses["sparsity_loss1"], losses["sparsity_loss2"] = reg_values[0], reg_values[1]
+            if opt.alpha_loss_w is not None:
+                losses["alpha_loss"] = reg_values[2]
+        elif uv_f is not None:
             if opt.sparsity_loss_w is not None:
                 hidden_front = (1 - alpha) * torch.exp(front)
                 losses["sparsity_loss1"] = hidden_front.square().sum(-1).mean() * (opt.sparsity_loss_w * share)
@@ -223,7 +239,10 @@ class LayeredTrainStep:
                 losses["alpha_loss"] = alpha.mean() * (opt.alpha_loss_w * share)
         if kernels:
             losses["ue_loss"] = ue_value
-            losses["total"] = pixel_total + sum(v for k, v in losses.items() if k not in ("img_loss", "ue_loss"))
+            detached = ("img_loss", "ue_loss") + (("sparsity_loss1", "sparsity_loss2", "alpha_loss") if reg_total is not None else ())
+            losses["total"] = pixel_total + sum(v for k, v in losses.items() if k not in detached)
+            if reg_total is not None:
+                losses["total"] = losses["total"] + reg_total
         else:
             black = m["tm"](*self._black)                                                  # training.py:244-245
             losses["ue_loss"] = (black - opt.fixed_value).abs().mean() / self.world

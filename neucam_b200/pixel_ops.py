@@ -124,3 +124,45 @@ def rigidity_loss(uv_ref, uv_moved, coef, shape, uv_mapping_scale):
     ku, kv = (h - 1) / 2.0 / uv_mapping_scale, (w - 1) / 2.0 / uv_mapping_scale
     return _Rigidity.apply(uv_ref.reshape(-1, 2).contiguous(), uv_moved.reshape(2, -1, 2).contiguous(),
                            coef.reshape(1).float().contiguous(), float(ku), float(kv))
+
+
+class _LayerBlend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, back, front, alpha, coefs):
+        K, B = alpha.shape
+        c1, c2, c3 = coefs
+        dev = back.device
+        out = torch.empty_like(back)
+        e2 = torch.empty((K, B), device=dev)
+        sums = torch.zeros(3, device=dev)
+        rc = _lib.lib().neucam_layer_blend_fwd(_lib.ptr(back), _lib.ptr(front), _lib.ptr(alpha), K, B,
+                                               ctypes.c_float(c1), ctypes.c_float(c2), ctypes.c_float(c3),
+                                               _lib.ptr(out), _lib.ptr(e2), _lib.ptr(sums), _lib.cur_stream())
+        _lib.check(rc, "neucam_layer_blend_fwd")
+        ctx.save_for_backward(back, front, alpha, e2)
+        ctx.coefs = coefs
+        ctx.mark_non_differentiable(sums)
+        return out, sums.sum(), sums
+
+    @staticmethod
+    def backward(ctx, d_out, g_reg, _):
+        back, front, alpha, e2 = ctx.saved_tensors
+        K, B = alpha.shape
+        c1, c2, c3 = ctx.coefs
+        d_back, d_front, d_alpha = torch.empty_like(back), torch.empty_like(front), torch.empty_like(alpha)
+        rc = _lib.lib().neucam_layer_blend_bwd(_lib.ptr(d_out.contiguous()), _lib.ptr(back), _lib.ptr(front),
+                                               _lib.ptr(alpha), _lib.ptr(e2), _lib.ptr(g_reg.reshape(1).contiguous()),
+                                               K, B, ctypes.c_float(c1), ctypes.c_float(c2), ctypes.c_float(c3),
+                                               _lib.ptr(d_back), _lib.ptr(d_front), _lib.ptr(d_alpha),
+                                               _lib.cur_stream())
+        _lib.check(rc, "neucam_layer_blend_bwd")
+        return d_back, d_front, d_alpha, None
+
+
+def layer_blend(back, front, alpha, c1, c2, c3):
+    """(1 - alpha) back + alpha front per tap, and the sparsity / alpha regularisers of the centre tap's alpha
+    (training.py:143-153, 220-238).  back, front [K,B,3]; alpha [K,B,1].  Returns (blend [K,B,3], the weighted sum
+    sparse1 + sparse2 + alpha with gradient, their three values [3] without)."""
+    K, B = back.shape[0], back.shape[1]
+    return _LayerBlend.apply(back.contiguous(), front.contiguous(), alpha.reshape(K, B).contiguous(),
+                             (float(c1), float(c2), float(c3)))
