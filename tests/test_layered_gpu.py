@@ -246,3 +246,26 @@ def test_layered_training_reduces_the_image_loss():
     last = losses["img_loss"].item()
     assert torch.isfinite(torch.tensor(last))
     assert last < 0.6 * first, (first, last)
+
+
+def test_two_layer_model_without_alpha_mlp(monkeypatch):
+    """`split_layer` without `alpha_mlp` (train_video.py:48-58: atlas_f gets a 4th output whose sigmoid is the alpha,
+    training.py:151): no shipped config uses it, the step still has to follow the reference."""
+    spec = dict(harness.LAYERED_CONFIGS["video_hdr"])
+    spec.pop("alpha")
+    monkeypatch.setitem(harness.LAYERED_CONFIGS, "video_hdr_sigmoid_alpha", spec)
+    monkeypatch.setitem(SHAPES, "video_hdr_sigmoid_alpha", (6, 36, 64))
+    models, state, opts, batch, cfg = _setup("video_hdr_sigmoid_alpha", 500, seed=2)
+    assert models["alpha"] is None and models["atlas_f"].net.dims[3] == 4
+    step = LayeredTrainStep(models, SHAPES["video_hdr_sigmoid_alpha"], opts, device="cuda")
+    losses = step.forward_backward(batch, {"img": batch["img"]})
+    torch.cuda.synchronize()
+    dev_state = {s: {k: v.cuda() for k, v in d.items()} for s, d in state.items()}
+    ref_l, ref_g = orc.step_grads(dev_state, {k: v.cuda() for k, v in batch.items()}, cfg)
+    assert set(losses) == set(ref_l)
+    for k, v in losses.items():
+        assert v.item() == pytest.approx(ref_l[k].item(), rel=1e-3, abs=1e-7), k
+    for slot in ("atlas_b", "atlas_f", "tm", "exp"):
+        for k, g_ref in ref_g[slot].items():
+            if g_ref.abs().max() > 0:
+                assert rel(dict(models[slot].named_parameters())[k].grad, g_ref) < 1e-2, (slot, k)
