@@ -283,6 +283,37 @@ class LayeredTrainStep:
     def losses(self):
         return self._losses
 
+    # -- device-resident data ----------------------------------------------------------
+    def attach_dataset(self, data, pixels_per_step, gamma_weights=None, mask_weights=None):
+        """Makes the video resident in HBM (data [N*H*W,3] = img*2-1, dataio.py:349) so that batches are formed on the
+        device by sample_resident() (neucam_sample_batch) instead of the CPU DataLoader."""
+        dev = self.device
+        B = int(pixels_per_step)
+        self.ds_data = data.reshape(-1, 3).to(dev, torch.float32).contiguous()
+        self.ds_gamma = None if gamma_weights is None else gamma_weights.reshape(-1).to(dev, torch.float32).contiguous()
+        self.ds_mask = None if mask_weights is None else mask_weights.reshape(-1).to(dev, torch.float32).contiguous()
+        self._ds = {"coords": torch.zeros(B, 3, device=dev), "coord_idx": torch.zeros(B, dtype=torch.int64, device=dev),
+                    "img": torch.zeros(B, 3, device=dev), "gamma_w": torch.zeros(B, device=dev),
+                    "mask_w": torch.zeros(B, device=dev), "idx_in": torch.zeros(B, dtype=torch.int64, device=dev)}
+
+    def sample_resident(self, seed=0, step=0, indices=None):
+        """Forms a batch on the device, Philox-sampled from (seed, step) or gathered at injected `indices`, and returns
+        it in the reference's DataLoader layout (device tensors): (model_input, gt) for step() / graph_step()."""
+        d = self._ds
+        idx = None
+        if indices is not None:
+            d["idx_in"].copy_(indices.reshape(-1), non_blocking=True)
+            idx = d["idx_in"]
+        ops.sample_batch(self.ds_data, self.ds_gamma, self.ds_mask, idx, self.shape, seed, step, d["coords"],
+                         d["coord_idx"], d["img"], d["gamma_w"] if self.ds_gamma is not None else None,
+                         d["mask_w"] if self.ds_mask is not None else None)
+        model_input = {"coords": d["coords"][None], "coord_idx": d["coord_idx"][None]}
+        if self.ds_gamma is not None:
+            model_input["gamma_weights"] = d["gamma_w"].view(1, -1, 1)
+        if self.ds_mask is not None:
+            model_input["weights"] = d["mask_w"].view(1, -1, 1)
+        return model_input, {"img": d["img"][None]}
+
     # -- CUDA graph ---------------------------------------------------------------------------------------------
     def capture(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None):
         """Captures forward + autograd backward + Adam over STATIC device copies of one batch into a CUDA graph

@@ -269,3 +269,37 @@ def test_two_layer_model_without_alpha_mlp(monkeypatch):
         for k, g_ref in ref_g[slot].items():
             if g_ref.abs().max() > 0:
                 assert rel(dict(models[slot].named_parameters())[k].grad, g_ref) < 1e-2, (slot, k)
+
+
+def test_device_resident_sampler_feeds_the_layered_step():
+    """neucam_sample_batch behind LayeredTrainStep: injected indices reproduce the host batch bit for bit, and a step
+    on the device-formed batch equals a step on the host-formed one."""
+    kind = "me_dynamic"
+    shape = SHAPES[kind]
+    B = 640
+    n, h, w = shape
+    g = torch.Generator().manual_seed(21)
+    grid = harness.mgrid(shape)
+    data = torch.rand(n * h * w, 3, generator=g) * 2 - 1
+    gw = torch.rand(n * h * w, generator=g)
+    idx = torch.randint(0, n * h * w, (B,), generator=g)
+    host = {"coords": grid[idx][None], "coord_idx": idx[None], "gamma_weights": gw[idx].view(1, -1, 1)}
+    losses = []
+    for device_side in (False, True):
+        models, _, opts, _, _ = _setup(kind, B, seed=6)
+        step = LayeredTrainStep(models, shape, opts, device="cuda")
+        if device_side:
+            step.attach_dataset(data, B, gamma_weights=gw)
+            inp, gt = step.sample_resident(indices=idx)
+            assert torch.equal(inp["coords"].cpu(), host["coords"]) and torch.equal(gt["img"].cpu(), data[idx][None])
+            assert torch.equal(inp["gamma_weights"].cpu(), host["gamma_weights"])
+        else:
+            inp, gt = host, {"img": data[idx][None]}
+        out = step.forward_backward(inp, gt, torch.tensor([20.0]))
+        losses.append({k: v.item() for k, v in out.items()})
+    assert losses[0] == pytest.approx(losses[1], rel=1e-6)
+    # Philox path: reproducible, in range
+    a, _ = step.sample_resident(seed=3, step=5)
+    a = a["coord_idx"].clone()
+    b, _ = step.sample_resident(seed=3, step=5)
+    assert torch.equal(a, b["coord_idx"]) and 0 <= int(a.min()) and int(a.max()) < n * h * w
