@@ -73,3 +73,44 @@ def render_frames(models, shape, chunk=65536, device="cuda"):
         e = exps[frame].view(-1, 1) if exps is not None else torch.zeros(hi - lo, 1, device=device)
         ldr[lo:hi] = tm(rgb, e) if tm is not None else rgb
     return (ldr / 2 + 0.5).view(n, h, w, 3), torch.exp(log_rad0).view(h, w, 3)
+
+
+@torch.no_grad()
+def render_layers(models, shape, chunk=65536, device="cuda", frames=None):
+    """Full-frame evaluation of any model set at the unshifted pixel positions (the centre tap: all-in-focus), as
+    utils.write_video_summary / render_video.py do it (utils.py:95-170): uv warps, both scene layers, alpha blend,
+    exposure + CRF.  Returns a dict of device tensors: 'ldr' [F,H,W,3] in [0,1], 'hdr' [F,H,W,3] linear radiance,
+    and, when the model set has them, 'alpha' [F,H,W,1], 'uv_b' / 'uv_f' [F,H,W,2].  Runs under no_grad: the fused
+    networks store nothing."""
+    n, h, w = shape
+    frames = list(range(n)) if frames is None else list(frames)
+    grid = harness.mgrid(shape).to(device).view(n, h * w, 3)
+    exps = models["exp"]() if models.get("exp") is not None else None
+    F_ = len(frames)
+    out = {"ldr": torch.empty(F_, h * w, 3, device=device), "hdr": torch.empty(F_, h * w, 3, device=device)}
+    if models.get("uv_b") is not None:
+        out["uv_b"] = torch.empty(F_, h * w, 2, device=device)
+    if models.get("uv_f") is not None:
+        out["uv_f"] = torch.empty(F_, h * w, 2, device=device)
+        out["alpha"] = torch.empty(F_, h * w, 1, device=device)
+    for fi, f in enumerate(frames):
+        for lo in range(0, h * w, chunk):
+            hi = min(lo + chunk, h * w)
+            pts = grid[f, lo:hi][None]                                              # [1,M,3]
+            pos = pts[..., 1:]
+            uv_b = (models["uv_b"](pts).view(1, -1, 2) + pos) * 0.5 if models.get("uv_b") is not None else pos
+            rad = models["atlas_b"]({"coords": uv_b})["model_out"]
+            if models.get("uv_f") is not None:
+                uv_f = (models["uv_f"](pts).view(1, -1, 2) + pos) * 0.5
+                front = models["atlas_f"]({"coords": uv_f})["model_out"]
+                alpha = (models["alpha"](pts).view(1, -1, 1) if models.get("alpha") is not None
+                         else torch.sigmoid(front[..., -1:]))
+                rad = (1 - alpha) * rad + alpha * front[..., 0:3]
+                out["uv_f"][fi, lo:hi], out["alpha"][fi, lo:hi] = uv_f[0], alpha[0]
+            if "uv_b" in out:
+                out["uv_b"][fi, lo:hi] = uv_b[0]
+            out["hdr"][fi, lo:hi] = torch.exp(rad[0])
+            e = exps[f].expand(hi - lo).view(-1, 1) if exps is not None else torch.zeros(hi - lo, 1, device=device)
+            ldr = models["tm"](rad.view(-1, 3), e) if models.get("tm") is not None else rad.view(-1, 3)
+            out["ldr"][fi, lo:hi] = ldr / 2 + 0.5
+    return {k: v.view(F_, h, w, v.shape[-1]) for k, v in out.items()}

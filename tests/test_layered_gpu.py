@@ -303,3 +303,25 @@ def test_device_resident_sampler_feeds_the_layered_step():
     a = a["coord_idx"].clone()
     b, _ = step.sample_resident(seed=3, step=5)
     assert torch.equal(a, b["coord_idx"]) and 0 <= int(a.min()) and int(a.max()) < n * h * w
+
+
+def test_render_layers_matches_a_plain_torch_evaluation(monkeypatch):
+    """Full-frame render of a two-layer model set (fused networks under no_grad) against the same modules evaluated
+    with plain fp32 torch ops (ReLU chain switched off, sine networks through a torch stand-in)."""
+    import test_layered_cpu as T
+    from neucam_b200 import modules, utils as nutils
+    kind = "video_deblur"
+    shape = (3, 20, 28)
+    models = harness.build_layered_models(kind, shape, seed=8)
+    for m in models.values():
+        if m is not None:
+            m.cuda()
+    fused = nutils.render_layers(models, shape, chunk=300)
+    with monkeypatch.context() as mp:
+        mp.setattr(relu_mlp, "eligible", lambda m: False)
+        mp.setattr(modules.FCBlock, "forward", T._torch_sine_block)
+        plain = nutils.render_layers(models, shape, chunk=560)
+    assert set(fused) == {"ldr", "hdr", "uv_b", "uv_f", "alpha"}
+    assert fused["ldr"].shape == (3, 20, 28, 3) and fused["alpha"].shape == (3, 20, 28, 1)
+    for k in fused:
+        assert rel(fused[k], plain[k]) < 1e-3, (k, rel(fused[k], plain[k]))
