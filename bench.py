@@ -133,6 +133,34 @@ def cpu_reference_steps(cfg, B_sample, steps, warmup, threads):
     return 9 * B_sample * len(times) / total, total / len(times) * 1e3
 
 
+def gpu_eager_reference_steps(cfg, B, steps, dev):
+    """The oracle port of the reference step (fp32 torch ops + autograd + Adam, TF32 off) on the SAME B200 at the
+    full workload size: the same-box eager baseline.  Returns (samples/s, ms/step)."""
+    from neucam_b200 import harness
+    from oracle import neucam_oracle as orc
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    models = harness.build_static_models(cfg["shape"], cfg["focal_list"], hidden=512, seed=0)
+    state = {s: {k: v.detach().clone().to(dev) for k, v in m.state_dict().items()} for s, m in models.items() if m is not None}
+    ocfg = orc.StepConfig(cfg["shape"], use_random_gamma=cfg["use_random_gamma"], with_grad_loss=False)
+    mom = {s: {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in d.items()} for s, d in state.items()}
+    batches = [{k: v.to(dev) for k, v in b.items()} for b in make_host_batches(cfg, B, 2, seed=1, pin=False)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(steps + 1):
+        if i == 1:
+            e0.record()
+        b = batches[i % 2]
+        _, grads = orc.step_grads(state, b, ocfg, b["gamma"] if cfg["use_random_gamma"] else None)
+        for s, d in state.items():
+            for k in d:
+                d[k], m, v = orc.adam_update(d[k], grads[s][k], mom[s][k][0], mom[s][k][1], i + 1, 1e-4)
+                mom[s][k] = (m, v)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return 9 * B / (ms * 1e-3), ms
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -304,6 +332,13 @@ def run_ours(args, cfg):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cpu_baseline:
+            del step, resident
+            torch.cuda.empty_cache()
+            sps, ms = gpu_eager_reference_steps(cfg, B, 3, dev)
+            line["gpu_eager_baseline"] = {"value": sps, "unit": "samples/s", "ms_per_step": ms, "kind": "port",
+                                          "what": "oracle port of training.py:95-271 (torch eager fp32, TF32 off, autograd "
+                                                  "+ Adam) on the same B200 at the full workload size, 3 steps"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
