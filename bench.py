@@ -11,8 +11,13 @@ value  : whole-job samples/s, step inputs already resident in HBM (device-timed 
           max over ranks).  A step = forward + backward + (all-reduce) + Adam.
 e2e    : same metric through the public API (FusedTrainStep.step) with pinned HOST batches: the H2D copy of
           every step's inputs and a D2H read of the loss are inside the timed region.
-roofline: dominant tensor-core kernel, algorithmic FLOPs / CUDA-event time vs MEASURED_PEAKS.json.
-cpu_baseline: the oracle port of the reference step timed on the host cores on a bounded sample.
+roofline: dominant tensor-core kernel, algorithmic FLOPs / CUDA-event time (events around the kernel inside real
+          eager steps) vs MEASURED_PEAKS.json's sustained peak.
+cpu_baseline: the oracle port of the reference step timed on the host cores on a bounded sample; the same baseline
+          leg also reports gpu_eager_baseline = that port in torch eager fp32 on the same B200 at the full workload
+          size (SURVEY.md section 8d "same-box number to beat").  Both run AFTER the product measurement, on their own
+          copies of the models; `--no-cpu-baseline` skips the leg.
+--config me_dynamic | video_deblur | video_hdr: the uv-mapping / two-layer workloads (LayeredTrainStep), px/s.
 
 `--impl reference` times the reference's CPU implementation of the same step: /root/reference is Python and
 cannot travel to the GPU box, so this arm runs the oracle port (oracle/neucam_oracle.py, pinned to the
