@@ -542,12 +542,14 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                   const int i = q * 8 + jj * 2;
                   const int j = col + i;
                   const float z0 = __uint_as_float(r[i]), z1 = __uint_as_float(r[i + 1]);
-                  const float h0 = __sinf(fmaf(z0, 30.f, b30[j])), h1 = __sinf(fmaf(z1, 30.f, b30[j + 1]));
+                  const float t0 = fmaf(z0, 30.f, b30[j]), t1 = fmaf(z1, 30.f, b30[j + 1]);
+                  const float h0 = __sinf(t0), h1 = __sinf(t1);
                   w[q * 4 + jj] = pack_h2(h0, h1);
                   if (store_ph) {
-                    // phase in revolutions * 65536, rounded on the FMA pipe (1.5 * 2^23 magic number)
-                    const uint32_t p0 = __float_as_uint(fmaf(z0, 30.f * PH_PER_RAD, fmaf(b30[j], PH_PER_RAD, MAGIC)));
-                    const uint32_t p1 = __float_as_uint(fmaf(z1, 30.f * PH_PER_RAD, fmaf(b30[j + 1], PH_PER_RAD, MAGIC)));
+                    // phase in revolutions * 65536, rounded on the FMA pipe (1.5 * 2^23 magic number): one FFMA from
+                    // the angle the sine already needed
+                    const uint32_t p0 = __float_as_uint(fmaf(t0, PH_PER_RAD, MAGIC));
+                    const uint32_t p1 = __float_as_uint(fmaf(t1, PH_PER_RAD, MAGIC));
                     pw[jj] = __byte_perm(p0, p1, 0x5410);
                   }
                   if (g == 2) {
