@@ -74,17 +74,20 @@ class _PsfCrfLoss(torch.autograd.Function):
                          absmax.view(torch.int32), scale)
         img = sums[0] / float(3 * int(global_pixels))
         ue = sums[1] * float(ue_weight)
-        ctx.save_for_backward(dy, dkw, dexps, *tm_g)
-        ctx.exps_shape = exps.shape if exps is not None else None
+        ctx.save_for_backward(dy, dkw, buf)
+        ctx.layout = (sizes, [p.shape for p in tm], exps.shape if exps is not None else None)
         ctx.mark_non_differentiable(img, ue)
         return img + ue, img, ue
 
     @staticmethod
     def backward(ctx, g_total, _g_img, _g_ue):
-        dy, dkw, dexps, *tm_g = ctx.saved_tensors
-        d_exps = (dexps[:ctx.exps_shape.numel()].view(ctx.exps_shape) * g_total) if ctx.exps_shape is not None else None
+        dy, dkw, buf = ctx.saved_tensors
+        sizes, tm_shapes, exps_shape = ctx.layout
+        parts = torch.split(buf * g_total, sizes)          # one launch scales every small gradient
+        tm_g = [g.view(shape) for g, shape in zip(parts, tm_shapes)]
+        d_exps = parts[len(tm_shapes)][:exps_shape.numel()].view(exps_shape) if exps_shape is not None else None
         return (dy * g_total, dkw * g_total if dkw is not None else None, d_exps, None, None, None, None, None, None,
-                None, *[g * g_total for g in tm_g])
+                None, *tm_g)
 
 
 def psf_crf_loss(y, kw, exps, fixed_exps, tm_module, shape, K, fixed_value, ue_weight, global_pixels, coord_idx, gt,
