@@ -9,8 +9,9 @@
 // TENSOR MEMORY as the A operand of tcgen05.mma (lane = sample row, two fp16 per 32-bit column: 128 columns for the
 // hi parts, 128 for the lo parts, next to the 256 accumulator columns = all 512 columns of the SM).  Every layer is
 // a sequence of weight "stages" of 256 x 64 fp16 streamed through a 4-deep TMA ring (128 KB of shared memory),
-// accumulated by M128 x N256 x K16 MMAs, drained by 4 epilogue warps (thread = sample row) that apply bias + ReLU
-// (forward) or the forward's gate bits (backward), write the next operand tile back into tensor memory with
+// accumulated by M128 x N256 x K16 MMAs, drained by 16 epilogue warps (32 sample rows x 64 hidden units each) that
+// apply bias + ReLU (forward) or the forward's gate bits (backward), write the next operand tile back into tensor
+// memory with
 // tcgen05.st and TMA-store it to HBM for the weight-gradient GEMMs through a 4 KB staging tile per warp (32 rows x
 // 32 columns, hi and lo; direct st.global from the row-per-thread layout cost 32 L1 tag requests per instruction and
 // 8 k cycles per GEMM).  The encoded input (raw coordinates + NeRF positional
@@ -28,9 +29,10 @@
 // loss scale on dz.
 //
 // Warp roles: 0..15 epilogue (warp e: TMEM lane quadrant e & 3 = 32 sample rows, column quarter e >> 2 = 64 of the
-// 256 hidden units), 16 TMA producer, 17 MMA issuer + TMEM owner (control warps have the highest ids).  With only 4
-// epilogue warps (one per scheduler) the per-element work ran at IPC ~0.3 and was 75 % of the kernel (measured with
-// the dbg flags: 218 of 293 us with no MMA, no loads, no TMEM traffic at all).
+// 256 hidden units), 16 TMA producer, 17 MMA issuer + TMEM owner (control warps have the highest ids).
+// Measured (Q = 165 888, 3 GEMM layers; ReluParams::dbg ablations and neucam_debug_set_relu_trace): forward 214 us with
+// the stores, 174 us without; of those 174 us, 70 us are MMAs (8.8 k cycles per hidden GEMM = 183 cycles per MMA) and
+// 104 us everything else: a tile's epilogue and its MMAs are serial because all 512 TMEM columns hold ONE tile.
 #include "host_util.h"
 #include "tc05.cuh"
 
