@@ -1,5 +1,7 @@
+"""Basin statistics of the fp32 oracle under tiny gradient noise (companion of tools/psnr_spread.py)."""
 import os, sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import test_psnr_parity as T
 from neucam_b200 import harness
 torch.backends.cuda.matmul.allow_tf32 = False
