@@ -84,6 +84,8 @@ struct ReluParams {
   const float* b_last;                 // [out_dim]
   int out_dim, out_kind;               // 0 none, 1 tanh, 2 sigmoid
   int store;                           // TMA-store the operand tiles (activations / dz) to HBM
+  int store_lo;                        // ... their lo parts too
+  int lo_operand;                      // backward: carry dz as hi + lo (forward always does for the activations)
   float* y;                            // forward [Q,out_dim]
   const float* dpre;                   // backward [Q,out_dim]: dL/d(pre-activation of the last layer)
   uint32_t* gates_out;                 // forward [H][Q][8]: one bit per hidden unit, set where h > 0 (or null)
@@ -113,7 +115,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // must have finished READING the tile before it is rewritten.
 __device__ __forceinline__ void store_chunk_tma(const CUtensorMap* m_hi, const CUtensorMap* m_lo, uint32_t stage,
                                                 uint32_t lane, int col0, int row0, const uint32_t (&w)[16],
-                                                const uint32_t (&wl)[16]) {
+                                                const uint32_t (&wl)[16], bool with_lo) {
   if (lane == 0) tma_store_wait_read0();
   __syncwarp();
   const uint32_t hi = stage + lane * 64u, lo = hi + 2048u;
@@ -121,13 +123,13 @@ __device__ __forceinline__ void store_chunk_tma(const CUtensorMap* m_hi, const C
 #pragma unroll
   for (uint32_t q = 0; q < 4; ++q) {
     st_shared_v4(hi + ((q ^ sw) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-    st_shared_v4(lo + ((q ^ sw) << 4), wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+    if (with_lo) st_shared_v4(lo + ((q ^ sw) << 4), wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
   }
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
     tma_store_2d(m_hi, stage, col0, row0);
-    tma_store_2d(m_lo, stage + 2048u, col0, row0);
+    if (with_lo) tma_store_2d(m_lo, stage + 2048u, col0, row0);
     tma_store_commit();
   }
 }
@@ -305,10 +307,10 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
           }
           tmem_st_32x32b_x16(t_row + TM_AHI + c * 16, w);
-          tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
+          if (p.lo_operand) tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
           if (p.store)
             store_chunk_tma(&maps.out_hi[p.H - 1], &maps.out_lo[p.H - 1], stage, lane, (int)c * 32,
-                            tile * TILE_M + (int)quad * 32, w, wl);
+                            tile * TILE_M + (int)quad * 32, w, wl, p.store_lo != 0);
         }
         tmem_st_wait();
         tc_fence_before_sync();
@@ -393,13 +395,13 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           }
           if (!(p.dbg & 1)) {
             tmem_st_32x32b_x16(t_row + TM_AHI + c * 16, w);
-            tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
+            if (!BWD || p.lo_operand) tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
           } else if (w[3] == 0x12345678u && wl[5] == 0x9abcdef0u) {
             p.y[0] = 1.f;   // keeps the math alive
           }
           if (p.store)
             store_chunk_tma(&maps.out_hi[layer], &maps.out_lo[layer], stage, lane, (int)c * 32,
-                            tile * TILE_M + (int)quad * 32, w, wl);
+                            tile * TILE_M + (int)quad * 32, w, wl, p.store_lo != 0);
         }
         tmem_st_wait();
         tc_fence_before_sync();
@@ -480,7 +482,7 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   NC_CHECK_ARG(feat16 && w_stages && stage_begin && a_src && a_src2 && bias && w_last && b_last && y);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && out_kind >= 0 && out_kind <= 2);
   NC_CHECK_ARG(check_stage_plan(n_gemm, stage_begin) == 0);
-  NC_CHECK_ARG((act16 == nullptr) == (act_lo16 == nullptr) && (act16 == nullptr) == (gates == nullptr));
+  NC_CHECK_ARG((act16 == nullptr) == (gates == nullptr) && (act_lo16 == nullptr || act16 != nullptr));
   ReluMaps maps;
   ReluParams p{};
   const int S = stage_begin[n_gemm];
@@ -493,8 +495,12 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
     if (act16) {
       rc = nchost::make_tmap_16b_sw64(&maps.out_hi[g], (const __half*)act16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
       if (rc) return rc;
-      rc = nchost::make_tmap_16b_sw64(&maps.out_lo[g], (const __half*)act_lo16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
-      if (rc) return rc;
+      if (act_lo16) {
+        rc = nchost::make_tmap_16b_sw64(&maps.out_lo[g], (const __half*)act_lo16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+        if (rc) return rc;
+      } else {
+        maps.out_lo[g] = maps.out_hi[g];
+      }
     } else {
       maps.out_hi[g] = maps.feat;
       maps.out_lo[g] = maps.feat;
@@ -519,6 +525,8 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   p.out_dim = out_dim;
   p.out_kind = out_kind;
   p.store = act16 != nullptr;
+  p.store_lo = act_lo16 != nullptr;
+  p.lo_operand = 1;
   p.gates_out = (uint32_t*)gates;
   p.y = y;
   p.dbg = g_relu_dbg;
@@ -541,11 +549,12 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
 // wT_stages: per backward GEMM (layer H-1 down to 1, then layer 0 when dfeat != NULL) the four 256 x 64 K-blocks of
 // the TRANSPOSED weight (rows = input feature, zero padded to 256), each as a hi stage followed by a lo stage;
 // scale_dev: power-of-two loss scale applied to dz;
-// dz16 / dz_lo16 [H,Q,256] fp16 out (scaled; hi and lo parts); dfeat [Q,64] fp32 out or NULL.
+// dz16 [H,Q,256] fp16 out (scaled); dz_lo16: its lo parts, or NULL = carry dz in single fp16 (per-sample rounding is
+// random and averages out over the samples of a weight gradient; the WEIGHT stages stay split); dfeat [Q,64] fp32 or NULL.
 extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_stages, int H, const float* w_last,
                                    int out_dim, const void* gates, const float* scale_dev, void* dz16,
                                    void* dz_lo16, float* dfeat, void* stream) {
-  NC_CHECK_ARG(dpre && wT_stages && w_last && gates && scale_dev && dz16 && dz_lo16);
+  NC_CHECK_ARG(dpre && wT_stages && w_last && gates && scale_dev && dz16);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && out_dim >= 1 && out_dim <= 4 && H >= 1 && H <= MAX_GEMM);
   NC_CHECK_ARG(H - 1 + (dfeat ? 1 : 0) <= MAX_GEMM);
   const int n_gemm = (H - 1) + (dfeat ? 1 : 0);
@@ -560,7 +569,9 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
   for (int s = 0; s < 8 * n_gemm; ++s) {
     const int kb = (s >> 1) & 3;
     p.a_src[s] = (uint8_t)kb;
-    p.a_src2[s] = (s & 1) ? (uint8_t)255 : (uint8_t)(5 + kb);
+    // with dz_lo16: dz is carried as hi + lo and the hi weight stage multiplies both; without: only the transposed
+    // weights are split (their rounding is common to all samples and would not average out)
+    p.a_src2[s] = ((s & 1) || dz_lo16 == nullptr) ? (uint8_t)255 : (uint8_t)(5 + kb);
   }
   p.Q = (int)Q;
   p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
@@ -572,14 +583,20 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
     if (l < H) {
       rc = nchost::make_tmap_16b_sw64(&maps.out_hi[l], (const __half*)dz16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
       if (rc) return rc;
-      rc = nchost::make_tmap_16b_sw64(&maps.out_lo[l], (const __half*)dz_lo16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
-      if (rc) return rc;
+      if (dz_lo16) {
+        rc = nchost::make_tmap_16b_sw64(&maps.out_lo[l], (const __half*)dz_lo16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+        if (rc) return rc;
+      } else {
+        maps.out_lo[l] = maps.out_hi[l];
+      }
     } else {
       maps.out_hi[l] = maps.w;
       maps.out_lo[l] = maps.w;
     }
   }
   p.store = 1;
+  p.store_lo = dz_lo16 != nullptr;
+  p.lo_operand = dz_lo16 != nullptr;
   p.dpre = dpre;
   p.gates = (const uint32_t*)gates;
   p.scale = scale_dev;

@@ -300,12 +300,13 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
 //   dz16 / dz_lo16 [H,Q,256], act16 / act_lo16 [H,Q,256] (hi and lo fp16 parts), feat16 [Q,64] fp16.
 //   Layer 0: dw_first [256,64] (encoded-input layout) and db[0]; layers l = 1..H-1: dw[l] with row pitch ldw[l]
 //   (its first 256 columns are written) and db[l]; a layer with dw_skip[l] != NULL also gets that [256,64] =
-//   dz_l^T feat.  Every product is split: (dz_hi + dz_lo)^T h_hi + dz_hi^T h_lo.  All accumulated into (caller zeroes).
+//   dz_l^T feat.  With the lo tensors every product is split: (dz_hi + dz_lo)^T h_hi + dz_hi^T h_lo; dz_lo16 / act_lo16
+//   may be NULL (single fp16 operands: their per-sample rounding averages out over Q).  All accumulated into.
 extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, const void* act16, const void* act_lo16,
                                      const void* feat16, int64_t Q, int H, const float* scale_dev, float* dw_first,
                                      float* const* dw, const int* ldw, float* const* db, float* const* dw_skip,
                                      void* stream) {
-  NC_CHECK_ARG(dz16 && dz_lo16 && act16 && act_lo16 && feat16 && scale_dev && dw_first && dw && ldw && db && dw_skip);
+  NC_CHECK_ARG(dz16 && act16 && feat16 && scale_dev && dw_first && dw && ldw && db && dw_skip);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && H >= 1 && H <= 8);
   constexpr int W = 256;
   WgradJobs jobs;
@@ -316,22 +317,22 @@ extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, cons
   };
   for (int l = 0; l < H; ++l) {
     const __half* dzh = (const __half*)dz16 + (size_t)l * Q * W;
-    const __half* dzl = (const __half*)dz_lo16 + (size_t)l * Q * W;
+    const __half* dzl = dz_lo16 ? (const __half*)dz_lo16 + (size_t)l * Q * W : nullptr;
     int rc = 0;
     if (l == 0) {
       NC_CHECK_ARG(db[0]);
       rc = add(dzh, feat16, 64, dw_first, db[0], 64, 64);
-      if (!rc) rc = add(dzl, feat16, 64, dw_first, db[0], 64, 64);
+      if (!rc && dzl) rc = add(dzl, feat16, 64, dw_first, db[0], 64, 64);
     } else {
       NC_CHECK_ARG(dw[l] && db[l] && ldw[l] >= W);
       const __half* ah = (const __half*)act16 + (size_t)(l - 1) * Q * W;
-      const __half* al = (const __half*)act_lo16 + (size_t)(l - 1) * Q * W;
+      const __half* al = act_lo16 ? (const __half*)act_lo16 + (size_t)(l - 1) * Q * W : nullptr;
       rc = add(dzh, ah, W, dw[l], db[l], ldw[l], 256);
-      if (!rc) rc = add(dzl, ah, W, dw[l], db[l], ldw[l], 256);
-      if (!rc) rc = add(dzh, al, W, dw[l], nullptr, ldw[l], 256);
+      if (!rc && dzl) rc = add(dzl, ah, W, dw[l], db[l], ldw[l], 256);
+      if (!rc && al) rc = add(dzh, al, W, dw[l], nullptr, ldw[l], 256);
       if (!rc && dw_skip[l]) {
         rc = add(dzh, feat16, 64, dw_skip[l], nullptr, 64, 64);
-        if (!rc) rc = add(dzl, feat16, 64, dw_skip[l], nullptr, 64, 64);
+        if (!rc && dzl) rc = add(dzl, feat16, 64, dw_skip[l], nullptr, 64, 64);
       }
     }
     if (rc) return rc;
@@ -366,9 +367,9 @@ extern "C" int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, in
 // (h, h_lo fp16 [Q,256]; c < 4).
 extern "C" int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, const float* dpre, int out_dim,
                                           int64_t Q, float* dw_last, void* stream) {
-  NC_CHECK_ARG(h16 && h_lo16 && dpre && dw_last);
+  NC_CHECK_ARG(h16 && dpre && dw_last);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
   int rc = launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, stream);
-  if (rc) return rc;
+  if (rc || h_lo16 == nullptr) return rc;
   return launch_skinny<256>(h_lo16, dpre, out_dim, Q, dw_last, stream);
 }

@@ -23,6 +23,11 @@ from . import _gradmode, _lib, ops
 WID = 256
 FEAT = 64
 OUT_KINDS = {"none": 0, "tanh": 1, "sigmoid": 2}
+# Carry dz and the SAVED activations as hi + lo fp16 pairs through the backward chain and the weight-gradient GEMMs.
+# Off: their rounding is random per sample and averages out over the Q samples of a weight gradient (measured: it did
+# not move the rigidity-cancellation error at all, 1.7308e-2 -> 1.7257e-2), whereas the split of the WEIGHTS (forward
+# and transposed) and of the forward's activations is what parity needs -- those stay on unconditionally.
+SPLIT_BACKWARD_OPERANDS = False
 _KEEP_LAST_ACTIVATIONS = False      # diagnostics (tools/relu_diag.py): keep the saved activations of each call
 _last_activations = []
 
@@ -101,14 +106,15 @@ class _ReluMLPFunction(torch.autograd.Function):
         bias = torch.stack(bs[:H]).contiguous()
         w_last, b_last = ws[H].contiguous(), bs[H].contiguous()
         out_dim = w_last.shape[0]
-        act16 = torch.empty((2, H, Q, WID), dtype=torch.float16, device=dev) if need_grad else None   # hi, lo
+        n_parts = 2 if SPLIT_BACKWARD_OPERANDS else 1
+        act16 = torch.empty((n_parts, H, Q, WID), dtype=torch.float16, device=dev) if need_grad else None   # hi[, lo]
         gates = torch.empty((H, Q, 8), dtype=torch.int32, device=dev) if need_grad else None
         y = torch.empty((Q, out_dim), dtype=torch.float32, device=dev)
         rc = lib.neucam_relu_mlp_fwd(_lib.ptr(feat16), ctypes.c_int64(Q), _lib.ptr(w_stages), H,
                                      (ctypes.c_int * len(begin))(*begin), _u8(a_src), _u8(a_src2), _lib.ptr(bias),
                                      _lib.ptr(w_last), _lib.ptr(b_last), out_dim, out_kind, _lib.ptr(y),
                                      _lib.ptr(act16[0] if need_grad else None),
-                                     _lib.ptr(act16[1] if need_grad else None), _lib.ptr(gates), stream)
+                                     _lib.ptr(act16[1] if need_grad and n_parts == 2 else None), _lib.ptr(gates), stream)
         _lib.check(rc, "neucam_relu_mlp_fwd")
         if need_grad:
             ctx.save_for_backward(x, feat16, act16, y, wT_stages, gates, *ws)
@@ -138,11 +144,13 @@ class _ReluMLPFunction(torch.autograd.Function):
         want_dx = ctx.needs_input_grad[0]
         w_last = ws[H].contiguous()
         out_dim = w_last.shape[0]
-        dz16 = torch.empty((2, H, Q, WID), dtype=torch.float16, device=dev)   # hi, lo
+        n_parts = act16.shape[0]
+        dz16 = torch.empty((n_parts, H, Q, WID), dtype=torch.float16, device=dev)   # hi[, lo]
+        lo = lambda t: t[1] if n_parts == 2 else None
         dfeat = torch.empty((Q, FEAT), dtype=torch.float32, device=dev) if want_dx else None
         rc = lib.neucam_relu_mlp_bwd(_lib.ptr(dpre), ctypes.c_int64(Q), _lib.ptr(wT_stages), H, _lib.ptr(w_last),
                                      out_dim, _lib.ptr(gates), _lib.ptr(scale), _lib.ptr(dz16[0]),
-                                     _lib.ptr(dz16[1]), _lib.ptr(dfeat), stream)
+                                     _lib.ptr(lo(dz16)), _lib.ptr(dfeat), stream)
         _lib.check(rc, "neucam_relu_mlp_bwd")
         dx = None
         if want_dx:
@@ -166,12 +174,13 @@ class _ReluMLPFunction(torch.autograd.Function):
             enc = parts[-1].view(1 + len(skips), WID, FEAT)                    # dw_first, dw_skip...
         arr = lambda items: (ctypes.c_void_p * len(items))(*[0 if t is None else t.data_ptr() for t in items])
         ldw = (ctypes.c_int * H)(*[int(w.shape[1]) for w in ws[:H]])
-        rc = lib.neucam_relu_mlp_wgrad(_lib.ptr(dz16[0]), _lib.ptr(dz16[1]), _lib.ptr(act16[0]), _lib.ptr(act16[1]),
+        rc = lib.neucam_relu_mlp_wgrad(_lib.ptr(dz16[0]), _lib.ptr(lo(dz16)), _lib.ptr(act16[0]), _lib.ptr(lo(act16)),
                                        _lib.ptr(feat16), ctypes.c_int64(Q), H, _lib.ptr(scale), _lib.ptr(enc[0]),
                                        arr([None] + dw[1:H]), ldw, arr(db[:H]),
                                        arr([enc[skip_slot[l]] if l in skip_slot else None for l in range(H)]), stream)
         _lib.check(rc, "neucam_relu_mlp_wgrad")
-        rc = lib.neucam_relu_mlp_head_wgrad(_lib.ptr(act16[0, H - 1]), _lib.ptr(act16[1, H - 1]), _lib.ptr(dpre),
+        rc = lib.neucam_relu_mlp_head_wgrad(_lib.ptr(act16[0, H - 1]),
+                                            _lib.ptr(act16[1, H - 1] if n_parts == 2 else None), _lib.ptr(dpre),
                                             out_dim, ctypes.c_int64(Q), _lib.ptr(dw[H]), stream)
         _lib.check(rc, "neucam_relu_mlp_head_wgrad")
         fold = lambda e: e[:, :E] + e[:, E:2 * E]      # hi + lo halves of the features

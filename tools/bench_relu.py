@@ -31,5 +31,6 @@ for ev in prof.key_averages():
         us = ev.device_time_total / ev.count
         extra = ""
         if "relu_chain" in ev.key or "hidden_wgrad" in ev.key:
-            extra = f"  {flop_pass / us / 1e6:7.1f} TFLOP/s algorithmic, x3 issued"
+            issued = 3 if "<false>" in ev.key or "ILb0" in ev.key else (2 if "relu_chain" in ev.key else 1)
+            extra = f"  {flop_pass / us / 1e6:7.1f} TFLOP/s algorithmic, x{issued} issued"
         print(f"{ev.key[:70]:70s} {ev.count:3d} x {us:8.1f} us{extra}")
