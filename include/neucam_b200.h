@@ -104,7 +104,9 @@ int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, 
  * the encoded input) followed by the out_dim <= 4 output layer and its nonlinearity on CUDA cores.
  *
  * The forward runs SPLIT-fp16 (hi + lo pairs for activations and weights, three MMAs per product) because a ReLU
- * network's gradient is discontinuous in its pre-activations; see csrc/relu_chain.cu.
+ * network's gradient is discontinuous in its pre-activations; the backward splits the transposed weights (their
+ * rounding is common to all samples).  The "lo" parts of the per-sample tensors (act_lo16, dz_lo16) are OPTIONAL
+ * everywhere: NULL = single fp16 (their rounding averages out over the samples); see csrc/relu_chain.cu.
  *
  * neucam_relu_mlp_fwd: w_stages [S*256,64] fp16 = for every GEMM in order its 256(out) x 64(in) K-blocks (hi
  *   and lo parts of the weights as separate stages); stage_begin[n_gemm+1] delimits them; a_src[S] says what each
