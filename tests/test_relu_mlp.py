@@ -71,3 +71,22 @@ def test_blur_network_keeps_the_generic_path():
     net = modules.SimpleMLP(hidden_dim=64, num_layer=4, in_dim=3, out_dim=27, use_encoding=False,
                             num_frequencies=7, skip_layer=[4], nonlinear="both")
     assert not relu_mlp.eligible(net)
+
+
+def test_split_backward_operands_option(monkeypatch):
+    """relu_mlp.SPLIT_BACKWARD_OPERANDS carries dz and the saved activations as hi + lo pairs as well (three wgrad GEMMs
+    per layer): per-call gradients then agree with fp32 torch to ~1e-6 instead of ~1e-5..6e-4."""
+    torch.manual_seed(7)
+    net = modules.SimpleMLP(hidden_dim=256, num_layer=6, in_dim=3, out_dim=2, use_encoding=True, num_frequencies=3,
+                            skip_layer=[4], nonlinear="tanh").cuda()
+    Q = 3000
+    x = torch.rand(Q, 3, device="cuda") * 2 - 1
+    upstream = torch.randn(Q, 2, device="cuda") * 1e-4
+    y0, dx0, g0 = run(net, x, upstream, False, monkeypatch)
+    errs = {}
+    for split in (False, True):
+        monkeypatch.setattr(relu_mlp, "SPLIT_BACKWARD_OPERANDS", split)
+        y1, dx1, g1 = run(net, x, upstream, True, monkeypatch)
+        errs[split] = max(rel(g1[k], g0[k]) for k in g0)
+        assert rel(y1, y0) < 1e-5 and errs[split] < 1e-2 and rel(dx1, dx0) < 1e-2
+    assert errs[True] <= errs[False]
