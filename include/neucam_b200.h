@@ -10,7 +10,14 @@
  *     frees or retains them (PyTorch owns every buffer);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
  *   - return value: 0 = ok, >0 = cudaError_t, <0 = NEUCAM_ERR_*;
- *   - there is no CPU fallback: a non-sm_100 device or a missing driver entry point is an error.
+ *   - there is no CPU fallback: a non-sm_100 device or a missing driver entry point is an error;
+ *   - NO FLOAT ATOMICS: every entry point that reduces over thread blocks (gradients of shared parameters, loss
+ *     sums) takes a scratch workspace `ws` of at least neucam_reduce_ws_bytes(kind, ...) bytes, writes one partial
+ *     record per block there and adds the records up in block order in a second kernel.  Same binary + same
+ *     inputs = bit-identical outputs.  The workspace is scratch: its contents are dead when the stream reaches the
+ *     end of the call, so calls on ONE stream can share it; concurrent streams need their own.
+ *   - global state: a cache of encoded TMA descriptors keyed by (device, pointer, geometry), the per-device
+ *     "dynamic shared memory attribute set" marks, and a launch counter (neucam_launch_count).  Nothing else.
  */
 #ifndef NEUCAM_B200_H_
 #define NEUCAM_B200_H_
@@ -21,12 +28,13 @@
 extern "C" {
 #endif
 
-#define NEUCAM_ABI_VERSION 5
+#define NEUCAM_ABI_VERSION 6
 
 #define NEUCAM_ERR_BAD_ARG (-1)
 #define NEUCAM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point unavailable */
 #define NEUCAM_ERR_TMAP (-3)      /* tensor-map encoding rejected */
 #define NEUCAM_ERR_ARCH (-4)      /* device is not compute capability 10.x */
+#define NEUCAM_ERR_WORKSPACE (-5) /* reduction workspace missing or smaller than neucam_reduce_ws_bytes says */
 
 /* ABI version of this header; bumped on any signature change. */
 int neucam_abi_version(void);
@@ -34,16 +42,20 @@ int neucam_abi_version(void);
 /* 0 if the current device can run the library (compute capability 10.x), NEUCAM_ERR_ARCH otherwise. */
 int neucam_check_device(void);
 
-/* Building-block self test (tests/test_umma_probe.py): one 128xN tcgen05 tile GEMM,
- * D[128,N] = A[128,K] * B[N,K]^T with fp32 accumulation.  flags: bit0 A MN-major (A given as [K,128]),
- * bit1 B MN-major (B given as [K,N]), bit2 A is bf16 (else fp16), bit3 B is bf16,
- * bit4 A tile staged by threads instead of TMA. */
-int neucam_umma_probe(const void* a, const void* b, float* d, int N, int K, int flags, void* stream);
+/* Bytes of reduction workspace an entry point needs on the current device.  kind = NEUCAM_WS_*;
+ * n / aux: SINE_BWD, WGRAD (both wgrad entry points), HEAD_WGRAD (both): unused; PSF_CRF and BLUR_BWD: n = B pixels,
+ * aux = N frames; RIGIDITY: n = B; BLEND: n = K * B. */
+#define NEUCAM_WS_SINE_BWD 0
+#define NEUCAM_WS_WGRAD 1
+#define NEUCAM_WS_HEAD_WGRAD 2
+#define NEUCAM_WS_PSF_CRF 3
+#define NEUCAM_WS_BLUR_BWD 4
+#define NEUCAM_WS_RIGIDITY 5
+#define NEUCAM_WS_BLEND 6
+int neucam_reduce_ws_bytes(int kind, int64_t n, int aux, int64_t* bytes_out);
 
-/* Tensor-pipe issue-rate microbenchmark (tools/umma_rate.py): `grid` CTAs in pairs; the leader of each pair
- * issues iters x 4 back-to-back MMAs (cta_group::2 M256xNxK16 if two_cta else cta_group::1 M128xNxK16) on
- * resident smem tiles; out_dev[2*cta] = issue cycles, out_dev[2*cta+1] = cycles until completion. */
-int neucam_umma_rate(int N, int iters, int two_cta, int kblocks, int grid, long long* out_dev, void* stream);
+/* Number of CUDA kernels this library has launched so far in this process (bench.py's `gpu_launches`). */
+int neucam_launch_count(int64_t* count_out);
 
 /* ---- scene sine-MLP (replaces SingleBVPNet.forward -> FCBlock.forward -> BatchLinear/Sine chain,
  * modules.py:455-475, 90-95, 17-35, for the shipped shape 2 -> 512 x4 -> out_dim, and its autograd
@@ -62,14 +74,6 @@ int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float
                         const float* b_hid, const float* w4, const float* b4, int out_dim, float* y,
                         void* act16, void* phase16, void* stream);
 
-/* Debug aid: CTA 0 of subsequent neucam_sine_mlp_fwd/bwd launches records clock64 stamps of its warp roles
- * into trace_dev (int64[576], device); pass NULL to switch it off.  See tools/chain_timeline.py. */
-int neucam_debug_set_chain_trace(long long* trace_dev);
-/* Debug experiments (outputs become garbage): bit0 = chain kernels issue no MMAs, bit1 = no weight TMA loads. */
-int neucam_debug_set_chain_flags(int flags);
-int neucam_debug_set_relu_trace(void* trace);  /* CTA 0 event/clock trace of the next ReLU-chain forward launches */
-int neucam_debug_set_relu_flags(int flags);   /* timing experiments on the ReLU chain (forward); results invalid */
-
 /* neucam_sine_mlp_bwd:  given dy[Q,out_dim] computes duv[Q,2], ACCUMULATES the first layer's
  *   gradients into dw0 [512,2] / db0 [512] and writes dz16 = fp16 [3,Q,512] holding
  *   (*scale_dev) * dL/dz_l for l = 1..3 (consumed by neucam_sine_mlp_wgrad).
@@ -81,17 +85,19 @@ int neucam_debug_set_relu_flags(int flags);   /* timing experiments on the ReLU 
  */
 int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0, const void* wT_hid16,
                         const void* w4T16, int out_dim, const float* dy, const void* phase16,
-                        const float* scale_dev, void* dz16, float* duv, float* dw0, float* db0, void* stream);
+                        const float* scale_dev, void* dz16, float* duv, float* dw0, float* db0, void* ws,
+                        int64_t ws_bytes, void* stream);
 
 /* neucam_sine_mlp_wgrad: ACCUMULATES dW_l [512,512] += dz_l^T a_l / scale and db_l [512] += colsum(dz_l) / scale
  *   for the hidden layers l = 1..3 (autograd MmBackward/sum of BatchLinear.forward, modules.py:24-25).
  *   dz16 = [3,Q,512] from neucam_sine_mlp_bwd, act16 = [4,Q,512] from neucam_sine_mlp_fwd. */
 int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const float* scale_dev, float* dw1,
-                          float* db1, float* dw2, float* db2, float* dw3, float* db3, void* stream);
+                          float* db1, float* dw2, float* db2, float* dw3, float* db3, void* ws, int64_t ws_bytes,
+                          void* stream);
 
 /* neucam_sine_mlp_head_wgrad: ACCUMULATES dW4 [out_dim,512] += dy^T a4 (a4 = act16 slot 3). */
-int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q, float* dw4,
-                               void* stream);
+int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q, float* dw4, void* ws,
+                               int64_t ws_bytes, void* stream);
 
 /* ---- 256-wide ReLU MLPs: the uv-mapping and alpha networks of the layered configs --------------------------
  * Replaces SimpleMLP.forward (modules.py:282-306) as called at training.py:131-137 (uv_b / uv_f), 148-150
@@ -132,9 +138,10 @@ int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_stages, int
                         void* stream);
 int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, const void* act16, const void* act_lo16,
                           const void* feat16, int64_t Q, int H, const float* scale_dev, float* dw_first,
-                          float* const* dw, const int* ldw, float* const* db, float* const* dw_skip, void* stream);
+                          float* const* dw, const int* ldw, float* const* db, float* const* dw_skip, void* ws,
+                          int64_t ws_bytes, void* stream);
 int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, const float* dpre, int out_dim, int64_t Q,
-                               float* dw_last, void* stream);
+                               float* dw_last, void* ws, int64_t ws_bytes, void* stream);
 
 /* Helpers around the chain (csrc/relu_aux.cu).
  * neucam_relu_mlp_encode: x [Q,3] fp32 -> feat16 [Q,64] fp16 = [ hi(E) | lo(E) | 0 ], E = 3 + 6*num_freq, the
@@ -170,7 +177,7 @@ int neucam_blur_fwd(const float* coords, const int64_t* coord_idx, const float* 
 int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, const float* focus,
                     const float* const* blur_params, float* const* blur_grads, float* dfocus, int B, int K, int N,
                     int H, int W, float offset_size, const float* kout, const float* hid, const float* dkw,
-                    const float* duv, void* stream);
+                    const float* duv, void* ws, int64_t ws_bytes, void* stream);
 
 /* neucam_psf_crf_loss (training.py:157-188, 244-245 forward AND backward in one pass): PSF-weighted tap sum,
  *   exposure dt = 3 tanh(exps[frame]) (LearnExps, modules.py:407-408) or fixed_exps [B], TonemapNet
@@ -182,14 +189,15 @@ int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, const float* 
  *   Outputs: dy [K,B,3], dkw [K,B]; ACCUMULATES tm_grads (12 pointers), dexps [N], db4 [3] (atlas output bias), sums[0] += sum of squared
  *   errors, sums[1] += ue_loss; atomically maxes |dy| into dy_absmax_bits and then writes
  *   scale_out = 2^floor(log2(scale_target / max|dy|)) (the loss scale of neucam_sine_mlp_bwd).
- *   ldr_out [B,3] optional (tone-mapped prediction). */
+ *   ldr_out [B,3] optional (tone-mapped prediction).  tm_width = hidden width of the TonemapNet the 12 pointers
+ *   belong to: must be 128 (TonemapNet's default and the only width any config uses), anything else is rejected. */
 int neucam_psf_crf_loss(const float* y, const float* kout, const int64_t* coord_idx, const float* exps,
                         const float* fixed_exps, const float* gt, const float* gamma_w, const float* mask_w,
                         const float* const* tm_params, float* const* tm_grads, int B, int K, int N, int H, int W,
                         int has_blur, const float* gamma_dev, float fixed_value, float ue_weight,
                         int64_t global_count, float* dy, float* dkw, float* dexps, float* db4, float* sums,
                         uint32_t* dy_absmax_bits, float scale_target, float* scale_out, float* ldr_out,
-                        void* stream);
+                        int tm_width, void* ws, int64_t ws_bytes, void* stream);
 
 /* neucam_rigidity_loss (utils.get_rigidity_loss, utils.py:402-454, as called at training.py:203-217; value and
  *   gradient in one pass): uv_ref [B,2] = the uv mapping at the step's pixels, uv_moved [2,B,2] = at the pixel one row
@@ -199,7 +207,7 @@ int neucam_psf_crf_loss(const float* y, const float* kout, const int64_t* coord_
  * neucam_loss_scale: scale_out[0] = 2^floor(log2(target / max|x|)) clamped to [2^-20, 2^64] (1 if max|x| is 0 or not
  *   finite): the loss scale of the fp16 backward chains, computed on the device. */
 int neucam_rigidity_loss(const float* uv_ref, const float* uv_moved, int B, float ku, float kv, const float* coef_dev,
-                         float* loss_sum, float* g_ref, float* g_moved, void* stream);
+                         float* loss_sum, float* g_ref, float* g_moved, void* ws, int64_t ws_bytes, void* stream);
 int neucam_loss_scale(const float* x, int64_t n, float target, uint32_t* scratch_bits, float* scale_out, void* stream);
 
 /* neucam_layer_blend_fwd / _bwd (training.py:143-153 layer blend with the alpha MLP's output; 220-238 sparsity and
@@ -209,7 +217,7 @@ int neucam_loss_scale(const float* x, int64_t n, float target, uint32_t* scratch
  *   e2 [K,B] is scratch handed from forward to backward.  The backward takes dout = dL/d out and the device scalar
  *   *g_reg = dL/d(the three sums) and writes d_back, d_front [K,B,3], d_alpha [K,B]. */
 int neucam_layer_blend_fwd(const float* back, const float* front, const float* alpha, int K, int B, float c1, float c2,
-                           float c3, float* out, float* e2, float* sums, void* stream);
+                           float c3, float* out, float* e2, float* sums, void* ws, int64_t ws_bytes, void* stream);
 int neucam_layer_blend_bwd(const float* dout, const float* back, const float* front, const float* alpha,
                            const float* e2, const float* g_reg, int K, int B, float c1, float c2, float c3,
                            float* d_back, float* d_front, float* d_alpha, void* stream);
@@ -245,6 +253,63 @@ int neucam_pack_hidden_weights(const float* w1, const float* w2, const float* w3
                                void* stream);
 /* w4 fp32 [out_dim,512] -> w4T16 fp16 [512,64] (row j = W4[0..out_dim-1][j], zero padded). */
 int neucam_pack_head_weights(const float* w4, int out_dim, void* w4T16, void* stream);
+
+/* ---- the whole static step from ONE call (SURVEY.md section 8b "minimum set") ---------------------------------
+ * neucam_step_fwd_bwd runs training.py:95-270 for the static multi-focus / multi-exposure model set (atlas_b +
+ * blur + focal + exp + tm; K = 9 taps with the blur model, K = 1 without): blur taps -> scene MLP forward -> PSF sum +
+ * exposure + CRF + image_mse (+ gamma / mask) + ue_loss and their backward -> scene MLP backward -> weight gradients
+ * of every network, i.e. exactly the sequence neucam_blur_fwd, neucam_sine_mlp_fwd, neucam_psf_crf_loss,
+ * neucam_sine_mlp_bwd, neucam_sine_mlp_wgrad, neucam_sine_mlp_head_wgrad || neucam_blur_bwd.  Every pointer is a
+ * device pointer owned by the caller; gradients are ACCUMULATED into the g_* tensors after `zero_ptr[0 .. zero_bytes)`
+ * (normally the flat gradient buffer all g_* live in) and `sums` have been cleared.  Outputs: gradients, sums[0] =
+ * sum of squared errors, sums[1] = ue_loss, and the scratch tensors (y, dy, uv, ...) as the individual calls leave
+ * them.  `side_stream` (optional) runs the blur backward concurrently with the head weight gradient; the call joins
+ * it back into `stream` before returning.  Set struct_bytes = sizeof(neucam_step_args). */
+#define NEUCAM_STEP_TO_HIDDEN_WGRAD 1 /* clear, taps, forward, loss, backward chain, hidden-layer weight gradients */
+#define NEUCAM_STEP_TAILS 2           /* head weight gradient || blur-MLP backward */
+typedef struct neucam_step_args {
+  uint32_t struct_bytes;
+  int phases;                   /* 0 or 3 = the whole step; NEUCAM_STEP_* bits select a part, so that a data-parallel
+                                   caller can start reducing the (large) atlas gradients while the tails still run */
+  int B, K, N, H, W;            /* pixels, taps per pixel (9 | 1), frames, frame height / width */
+  int out_dim;                  /* atlas output channels (3) */
+  int tm_width;                 /* TonemapNet hidden width (128) */
+  float offset_size, fixed_value, ue_weight;
+  int64_t global_count;         /* 3 * pixels of the GLOBAL batch (mean normaliser) */
+  /* step inputs */
+  const float* coords;          /* [B,3] (t,y,x) */
+  const int64_t* coord_idx;     /* [B] */
+  const float* img;             /* [B,3] */
+  const float* gamma_w;         /* [B] or NULL (no random-gamma augmentation) */
+  const float* gamma_dev;       /* device scalar or NULL */
+  const float* mask_w;          /* [B] or NULL */
+  /* parameters (fp32 masters) and their tensor-core operand copies */
+  const float* focus;           /* [N] (NULL when K == 1) */
+  const float* blur_params[8];  /* neucam_blur_fwd order (unused when K == 1) */
+  const float *w0, *b0, *b_hid, *w4, *b4;
+  const void *w_hid16, *wT_hid16, *w4T16;
+  const float* exps;            /* [N] */
+  const float* tm_params[12];
+  /* gradients (accumulated into) */
+  float* g_focus;
+  float* g_blur[8];
+  float *g_w0, *g_b0, *g_w[3], *g_b[3], *g_w4, *g_b4;
+  float* g_exps;
+  float* g_tm[12];
+  void* zero_ptr;
+  int64_t zero_bytes;
+  /* scratch owned by the caller */
+  float *uv, *kout, *hid, *y, *dy, *dkw, *duv;    /* [K,B,2] [27,B] [192,B] [K,B,3] [K,B,3] [K,B] [K,B,2] */
+  void *act16, *phase16, *dz16;
+  float* sums;                  /* [4] */
+  uint32_t* absmax_bits;        /* [1] */
+  float* scale;                 /* [1] loss scale (written) */
+  void* ws;                     /* reduction workspace for the main stream: >= max over the NEUCAM_WS_* kinds used */
+  int64_t ws_bytes;
+  void* ws_side;                /* reduction workspace of the blur backward (side stream): NEUCAM_WS_BLUR_BWD */
+  int64_t ws_side_bytes;
+} neucam_step_args;
+int neucam_step_fwd_bwd(const neucam_step_args* args, void* stream, void* side_stream);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,7 @@ extern "C" int neucam_pack_head_weights(const float* w4, int out_dim, void* w4T1
   NC_CHECK_ARG(w4 && w4T16 && out_dim >= 1 && out_dim <= 4);
   pack_head_kernel<<<128, 256, 0, (cudaStream_t)stream>>>(w4, out_dim, (__half*)w4T16);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -104,6 +105,7 @@ extern "C" int neucam_adam_tick(float* state, float beta1, float beta2, void* st
   NC_CHECK_ARG(state != nullptr);
   adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -118,6 +120,7 @@ extern "C" int neucam_adam_step(float* p, const float* g, float* m, float* v, in
   adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (long long)n, state, lr, beta1, beta2, eps,
                                                             grad_scale);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -126,5 +129,6 @@ extern "C" int neucam_pack_hidden_weights(const float* w1, const float* w2, cons
   NC_CHECK_ARG(w1 && w2 && w3 && w16 && wT16);
   pack_hidden_kernel<<<dim3(16, 16, 3), 256, 0, (cudaStream_t)stream>>>(w1, w2, w3, (__half*)w16, (__half*)wT16);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }

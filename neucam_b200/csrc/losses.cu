@@ -53,7 +53,7 @@ rigidity_kernel(const float* __restrict__ uv_ref, const float* __restrict__ uv_m
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += s_part[w];
-    atomicAdd(loss_sum, t);
+    loss_sum[4 * blockIdx.x] = t;   // this block's partial record; summed in block order by reduce.cu
   }
 }
 
@@ -85,12 +85,20 @@ __global__ void scale_from_bits_kernel(const unsigned int* bits, float target, f
 // loss_sum[0] += coef * sum_i L_i;  g_ref [B,2] = coef * dL/d uv_ref;  g_moved [2,B,2] = coef * dL/d uv_moved.
 // ku = (H-1)/2 / uv_mapping_scale, kv = (W-1)/2 / uv_mapping_scale; coef: device scalar.
 extern "C" int neucam_rigidity_loss(const float* uv_ref, const float* uv_moved, int B, float ku, float kv,
-                                    const float* coef_dev, float* loss_sum, float* g_ref, float* g_moved, void* stream) {
+                                    const float* coef_dev, float* loss_sum, float* g_ref, float* g_moved, void* ws,
+                                    int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(uv_ref && uv_moved && coef_dev && loss_sum && g_ref && g_moved && B > 0);
-  rigidity_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(uv_ref, uv_moved, B, ku, kv, coef_dev, loss_sum,
-                                                                    g_ref, g_moved);
+  NC_CHECK_WS(ws, ws_bytes, nchost::ws_bytes_rigidity(B));
+  const int grid = (B + 255) / 256;
+  rigidity_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(uv_ref, uv_moved, B, ku, kv, coef_dev,
+                                                           reinterpret_cast<float*>(ws), g_ref, g_moved);
   NC_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  NC_COUNT_LAUNCH(1);
+  nchost::ReduceSegs segs{};
+  segs.nseg = 1;
+  segs.seg[0] = {loss_sum, 0, 1};
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), grid, 4, segs, nullptr,
+                                        (cudaStream_t)stream);
 }
 
 // scale_out[0] = power-of-two loss scale that brings max|x| into [target/2, target); scratch_bits: 4 bytes.
@@ -104,6 +112,7 @@ extern "C" int neucam_loss_scale(const float* x, int64_t n, float target, uint32
   NC_CHECK_CUDA(cudaGetLastError());
   scale_from_bits_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scratch_bits, target, scale_out);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(2);
   return 0;
 }
 
@@ -163,7 +172,7 @@ blend_fwd_kernel(const float* __restrict__ back, const float* __restrict__ front
   if (threadIdx.x < 3) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
-    atomicAdd(sums + threadIdx.x, t);
+    sums[4 * blockIdx.x + threadIdx.x] = t;   // this block's partial record; summed in block order by reduce.cu
   }
 }
 
@@ -203,13 +212,21 @@ blend_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ back,
 
 // back, front, out [K,B,3]; alpha [K,B]; e2 [K,B] scratch kept for the backward; sums[3] += (sparse1, sparse2, alpha).
 extern "C" int neucam_layer_blend_fwd(const float* back, const float* front, const float* alpha, int K, int B,
-                                      float c1, float c2, float c3, float* out, float* e2, float* sums, void* stream) {
+                                      float c1, float c2, float c3, float* out, float* e2, float* sums, void* ws,
+                                      int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(back && front && alpha && out && e2 && sums && K >= 1 && B > 0);
   const long long n = (long long)K * B;
-  blend_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(back, front, alpha, K, B, c1, c2, c3,
-                                                                                   out, e2, sums);
+  NC_CHECK_WS(ws, ws_bytes, nchost::ws_bytes_blend(n));
+  const int grid = (int)((n + 255) / 256);
+  blend_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(back, front, alpha, K, B, c1, c2, c3, out, e2,
+                                                            reinterpret_cast<float*>(ws));
   NC_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  NC_COUNT_LAUNCH(1);
+  nchost::ReduceSegs segs{};
+  segs.nseg = 1;
+  segs.seg[0] = {sums, 0, 3};
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), grid, 4, segs, nullptr,
+                                        (cudaStream_t)stream);
 }
 
 // dout [K,B,3] = dL/d out; *g_reg (device scalar) = dL/d(sparse1 + sparse2 + alpha).  Writes d_back, d_front [K,B,3]
@@ -223,5 +240,6 @@ extern "C" int neucam_layer_blend_bwd(const float* dout, const float* back, cons
                                                                                    B, c1, c2, c3, d_back, d_front,
                                                                                    d_alpha);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }

@@ -177,18 +177,28 @@ struct MidParams {
   const float* mask_w;    // [B] or null
   float* dy;              // [K,B,3]
   float* dkw;             // [K,B]   d loss / d PSF weight
-  float* dexps;           // [N]     accumulated
   float* sums;            // [4]: sum sq err (img_loss * 3B), ue_loss, unused, unused  (accumulated)
-  float* db4;             // [3] gradient of the atlas output bias = sum over samples of dy (accumulated)
-  unsigned int* dy_absmax_bits;   // atomicMax target
+  float* part;            // per-block partial records (layout: REC_* below), summed in block order by reduce.cu
+  int rec;                // floats per record
+  unsigned int* dy_absmax_bits;   // atomicMax target (max is order-independent)
   float* ldr_out;         // optional [B,3] tone-mapped prediction (for summaries), or null
 };
+
+// partial record of one block: CRF gradients gu | ga | gv per channel, then the scalars, then the per-frame exposure
+// gradients
+constexpr int REC_TM = 0;                 // [3 channels][gu 128 | ga 128 | gv 128]
+constexpr int REC_GD = 3 * 3 * TMW;       // gd[3]
+constexpr int REC_SQ = REC_GD + 3;        // sum of squared errors
+constexpr int REC_DB4 = REC_GD + 4;       // db4[3]
+constexpr int REC_DEXP = REC_GD + 8;      // dexps[N]
+static_assert(REC_GD == nchost::WS_TM_GRADS, "workspace layout");
 
 __global__ void __launch_bounds__(PB)
 psf_crf_loss_kernel(MidParams mp, TmParams tm) {
   __shared__ float s_u[3][TMW], s_a[3][TMW], s_v[3][TMW];
   __shared__ float s_x[3][PB + 1], s_g[3][PB + 1];
-  __shared__ float s_dexp[128];
+  __shared__ float s_de[PB];
+  __shared__ int s_fr[PB];
   __shared__ float s_red[PB / 32][8];
   const int tid = threadIdx.x;
   for (int c = 0; c < 3; ++c) {
@@ -196,7 +206,9 @@ psf_crf_loss_kernel(MidParams mp, TmParams tm) {
     s_a[c][tid] = tm.a[c][tid];
     s_v[c][tid] = tm.v[c][tid];
   }
-  s_dexp[tid] = 0.f;
+  s_fr[tid] = -1;
+  s_de[tid] = 0.f;
+  float* rec = mp.part + (size_t)blockIdx.x * mp.rec;
   __syncthreads();
 
   const int B = mp.B, K = mp.K;
@@ -290,12 +302,23 @@ psf_crf_loss_kernel(MidParams mp, TmParams tm) {
       }
     }
     if (mp.exps != nullptr) {
-      const float de = LN2 * (dlnx[0] + dlnx[1] + dlnx[2]) * dtanh;
-      if (mp.N <= 128) atomicAdd(&s_dexp[frame], de);
-      else atomicAdd(mp.dexps + frame, de);
+      s_fr[tid] = frame;
+      s_de[tid] = LN2 * (dlnx[0] + dlnx[1] + dlnx[2]) * dtanh;
     }
   }
   __syncthreads();
+  // exposure gradients of this block: thread = frame, pixels in order (no atomics)
+  if (mp.exps != nullptr) {
+    for (int f0 = 0; f0 < mp.N; f0 += PB) {
+      const int f = f0 + tid;
+      if (f < mp.N) {
+        float t = 0.f;
+        for (int q = 0; q < PB; ++q)
+          if (s_fr[q] == f) t += s_de[q];
+        rec[REC_DEXP + f] = t;
+      }
+    }
+  }
 
   // CRF parameter gradients: thread = hidden unit, loop over the block's pixels (no cross-thread reduce)
   {
@@ -316,9 +339,9 @@ psf_crf_loss_kernel(MidParams mp, TmParams tm) {
           ga += t;
         }
       }
-      atomicAdd(tm.gu[c] + i, gu);
-      atomicAdd(tm.ga[c] + i, ga);
-      atomicAdd(tm.gv[c] + i, gv);
+      rec[REC_TM + c * 3 * TMW + i] = gu;
+      rec[REC_TM + c * 3 * TMW + TMW + i] = ga;
+      rec[REC_TM + c * 3 * TMW + 2 * TMW + i] = gv;
     }
   }
   // block reductions: d bias of the CRF output layer, loss sums, max |dy|
@@ -344,12 +367,9 @@ psf_crf_loss_kernel(MidParams mp, TmParams tm) {
   if (tid < 7) {
     float t = 0.f;
     for (int w = 0; w < PB / 32; ++w) t += s_red[w][tid];
-    if (tid < 3) atomicAdd(tm.gd[tid], t);
-    else if (tid == 3) atomicAdd(mp.sums + 0, t);
-    else atomicAdd(mp.db4 + (tid - 4), t);
+    rec[REC_GD + tid] = t;     // gd[0..2] | sum sq | db4[0..2]
   }
-  if (is_ue) atomicAdd(mp.sums + 1, ue);
-  if (mp.exps != nullptr && mp.N <= 128 && tid < mp.N && s_dexp[tid] != 0.f) atomicAdd(mp.dexps + tid, s_dexp[tid]);
+  if (is_ue) mp.sums[1] += ue;   // the one virtual pixel of the grid: a single writer
 }
 
 // scale = 2^floor(log2(target / max|dy|)): keeps the scaled gradients of the atlas backward in fp16 range
@@ -369,8 +389,13 @@ __global__ void loss_scale_kernel(const unsigned int* absmax_bits, float target,
 // blur MLP backward
 // ------------------------------------------------------------------------------------------------
 struct BlurGrads {
-  float *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *focus;   // accumulated into
+  float *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *focus;   // accumulated into (by the reduction pass)
 };
+// offsets of the tensors inside one block's partial record
+constexpr int BR_W1 = 0, BR_B1 = BR_W1 + BH * 3, BR_W2 = BR_B1 + BH, BR_B2 = BR_W2 + BH * BH, BR_W3 = BR_B2 + BH,
+              BR_B3 = BR_W3 + BH * BH, BR_W4 = BR_B3 + BH, BR_B4 = BR_W4 + BO * BH, BR_END = BR_B4 + BO;
+static_assert(BR_END == nchost::WS_BLUR_PARAMS, "workspace layout");
+constexpr int BR_FOCUS = (BR_END + 3) & ~3;
 
 // Tiles of the blur backward live in smem as [pixel][feature] with a 68-float row pitch: a pixel-thread
 // writes/reads its own row with conflict-free 128-bit accesses, and the block-level outer products read
@@ -404,7 +429,7 @@ __device__ __forceinline__ void block_outer_accum(const float* s_dz, const float
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
-      if (o0 + a < NOUT && i0 + b < NIN) atomicAdd(gw + (o0 + a) * NIN + i0 + b, acc[a][b]);
+      if (o0 + a < NOUT && i0 + b < NIN) gw[(o0 + a) * NIN + i0 + b] = acc[a][b];   // this block's partial record
 }
 
 // gb[o] += sum_q dz[q][o]
@@ -413,15 +438,15 @@ __device__ __forceinline__ void block_bias_accum(const float* s_dz, int np, floa
   if (tid < NOUT) {
     float t = 0.f;
     for (int q = 0; q < np; ++q) t += s_dz[q * TP + tid];
-    atomicAdd(gb + tid, t);
+    gb[tid] = t;
   }
 }
 
 __global__ void __launch_bounds__(PB)
 blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ coord_idx,
-                const float* __restrict__ focus, BlurParams bp, BlurGrads bg, int B, int HW, int N, float sy,
-                float sx, float offset_size, const float* __restrict__ kout, const float* __restrict__ hid,
-                const float* __restrict__ dkw, const float* __restrict__ duv) {
+                const float* __restrict__ focus, BlurParams bp, float* __restrict__ part, int rec_floats, int B, int HW,
+                int N, float sy, float sx, float offset_size, const float* __restrict__ kout,
+                const float* __restrict__ hid, const float* __restrict__ dkw, const float* __restrict__ duv) {
   extern __shared__ __align__(16) float sm[];
   float* s_w2 = sm;                    // [64][64] (out, in) as stored
   float* s_w3 = s_w2 + BH * BH;        // [64][64]
@@ -429,7 +454,9 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
   float* s_dz = s_w4 + 28 * BH;        // [PB][TP]  current layer's d(pre-activation)
   float* s_h = s_dz + PB * TP;         // [PB][TP]  that layer's input activation
   float* s_red = s_h + PB * TP;        // [PB]
+  int* s_fr = reinterpret_cast<int*>(s_red + PB);   // [PB]
   const int tid = threadIdx.x;
+  float* rec = part + (size_t)blockIdx.x * rec_floats;
   for (int i = tid; i < BH * BH; i += PB) {
     s_w2[i] = bp.w2[i];
     s_w3[i] = bp.w3[i];
@@ -481,8 +508,8 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
 #pragma unroll
   for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_h + i) = make_float4(hcur[i], hcur[i + 1], hcur[i + 2], hcur[i + 3]);
   __syncthreads();
-  block_outer_accum<BO, BH>(s_dz, s_h, np, bg.w4, tid);
-  block_bias_accum<BO>(s_dz, np, bg.b4, tid);
+  block_outer_accum<BO, BH>(s_dz, s_h, np, rec + BR_W4, tid);
+  block_bias_accum<BO>(s_dz, np, rec + BR_B4, tid);
   float dh[BH];
 #pragma unroll
   for (int i = 0; i < BH; ++i) dh[i] = 0.f;
@@ -509,8 +536,8 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
 #pragma unroll
     for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_h + i) = make_float4(hcur[i], hcur[i + 1], hcur[i + 2], hcur[i + 3]);
     __syncthreads();
-    float* gw = (l == 2) ? bg.w3 : bg.w2;
-    float* gb = (l == 2) ? bg.b3 : bg.b2;
+    float* gw = rec + ((l == 2) ? BR_W3 : BR_W2);
+    float* gb = rec + ((l == 2) ? BR_B3 : BR_B2);
     const float* sw = (l == 2) ? s_w3 : s_w2;
     block_outer_accum<BH, BH>(s_dz, s_h, np, gw, tid);
     block_bias_accum<BH>(s_dz, np, gb, tid);
@@ -542,17 +569,20 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
   }
   *reinterpret_cast<float4*>(my_h) = make_float4(in0, in1, in2, 0.f);
   __syncthreads();
-  block_outer_accum<BH, 3>(s_dz, s_h, np, bg.w1, tid);
-  block_bias_accum<BH>(s_dz, np, bg.b1, tid);
-  // focus gradient: per-frame scatter (training.py:104-108 backward)
-  if (N <= PB) {
-    s_red[tid] = 0.f;
-    __syncthreads();
-    if (valid) atomicAdd(&s_red[(int)(coord_idx[p] / HW)], dfocus);
-    __syncthreads();
-    if (tid < N && s_red[tid] != 0.f) atomicAdd(bg.focus + tid, s_red[tid]);
-  } else if (valid) {
-    atomicAdd(bg.focus + (int)(coord_idx[p] / HW), dfocus);
+  block_outer_accum<BH, 3>(s_dz, s_h, np, rec + BR_W1, tid);
+  block_bias_accum<BH>(s_dz, np, rec + BR_B1, tid);
+  // focus gradient: per-frame gather over the block's pixels in order (training.py:104-108 backward; no atomics)
+  s_red[tid] = dfocus;
+  s_fr[tid] = valid ? (int)(coord_idx[p] / HW) : -1;
+  __syncthreads();
+  for (int f0 = 0; f0 < N; f0 += PB) {
+    const int f = f0 + tid;
+    if (f < N) {
+      float t = 0.f;
+      for (int q = 0; q < PB; ++q)
+        if (s_fr[q] == f) t += s_red[q];
+      rec[BR_FOCUS + f] = t;
+    }
   }
 }
 
@@ -667,6 +697,7 @@ extern "C" int neucam_tm_min_slope(const float* const* tm_params, const float* r
   NC_CHECK_CUDA(cudaMemsetAsync(min_bits, 0xFF, 4, (cudaStream_t)stream));
   tm_min_slope_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tm, rad, expo, M, min_bits);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -682,6 +713,7 @@ extern "C" int neucam_sample_batch(const float* data, const float* gamma_w_all, 
       data, gamma_w_all, mask_w_all, (const long long*)idx_in, N, H, W, B, (unsigned long long)seed,
       (unsigned long long)step, coords, (long long*)coord_idx, img, gamma_w, mask_w);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -699,41 +731,45 @@ extern "C" int neucam_blur_fwd(const float* coords, const int64_t* coord_idx, co
   BlurParams bp{blur_params[0], blur_params[1], blur_params[2], blur_params[3],
                 blur_params[4], blur_params[5], blur_params[6], blur_params[7]};
   const size_t smem = sizeof(float) * (2 * BH * BH + BH * 28 + BH * 4 + 64 + 64 + 28 + BH * PB);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(blur_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  int rc = nchost::ensure_dyn_smem((const void*)blur_fwd_kernel, (int)smem);
+  if (rc) return rc;
   const int grid = (B + PB - 1) / PB;
   blur_fwd_kernel<<<grid, PB, smem, (cudaStream_t)stream>>>(
       coords, (const long long*)coord_idx, focus, bp, B, H * W, 2.f / (H - 1), 2.f / (W - 1), offset_size, uv,
       kout, hid);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
 extern "C" int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, const float* focus,
                                const float* const* blur_params, float* const* blur_grads, float* dfocus, int B,
                                int K, int N, int H, int W, float offset_size, const float* kout,
-                               const float* hid, const float* dkw, const float* duv, void* stream) {
+                               const float* hid, const float* dkw, const float* duv, void* ws, int64_t ws_bytes,
+                               void* stream) {
   NC_CHECK_ARG(coords && coord_idx && focus && blur_params && blur_grads && dfocus && kout && hid && dkw && duv);
   NC_CHECK_ARG(K == KT && B > 0 && N > 0 && H > 1 && W > 1);
+  NC_CHECK_WS(ws, ws_bytes, nchost::ws_bytes_blur_bwd(B, N));
   BlurParams bp{blur_params[0], blur_params[1], blur_params[2], blur_params[3],
                 blur_params[4], blur_params[5], blur_params[6], blur_params[7]};
-  BlurGrads bg{blur_grads[0], blur_grads[1], blur_grads[2], blur_grads[3],
-               blur_grads[4], blur_grads[5], blur_grads[6], blur_grads[7], dfocus};
-  const size_t smem = sizeof(float) * (2 * BH * BH + 28 * BH + 2 * PB * TP + PB);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(blur_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = sizeof(float) * (2 * BH * BH + 28 * BH + 2 * PB * TP + 2 * PB);
+  int rc = nchost::ensure_dyn_smem((const void*)blur_bwd_kernel, (int)smem);
+  if (rc) return rc;
   const int grid = (B + PB - 1) / PB;
+  const int rec = nchost::ws_rec_blur_bwd(N);
   blur_bwd_kernel<<<grid, PB, smem, (cudaStream_t)stream>>>(
-      coords, (const long long*)coord_idx, focus, bp, bg, B, H * W, N, 2.f / (H - 1), 2.f / (W - 1), offset_size,
-      kout, hid, dkw, duv);
+      coords, (const long long*)coord_idx, focus, bp, reinterpret_cast<float*>(ws), rec, B, H * W, N, 2.f / (H - 1),
+      2.f / (W - 1), offset_size, kout, hid, dkw, duv);
   NC_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  NC_COUNT_LAUNCH(1);
+  nchost::ReduceSegs segs{};
+  const int offs[8] = {BR_W1, BR_B1, BR_W2, BR_B2, BR_W3, BR_B3, BR_W4, BR_B4};
+  const int lens[8] = {BH * 3, BH, BH * BH, BH, BH * BH, BH, BO * BH, BO};
+  for (int i = 0; i < 8; ++i) segs.seg[i] = {blur_grads[i], offs[i], lens[i]};
+  segs.seg[8] = {dfocus, BR_FOCUS, N};
+  segs.nseg = 9;
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), grid, rec, segs, nullptr,
+                                        (cudaStream_t)stream);
 }
 
 extern "C" int neucam_psf_crf_loss(const float* y, const float* kout, const int64_t* coord_idx,
@@ -743,8 +779,10 @@ extern "C" int neucam_psf_crf_loss(const float* y, const float* kout, const int6
                                    const float* gamma_dev, float fixed_value, float ue_weight,
                                    int64_t global_count, float* dy, float* dkw, float* dexps, float* db4, float* sums,
                                    uint32_t* dy_absmax_bits, float scale_target, float* scale_out,
-                                   float* ldr_out, void* stream) {
+                                   float* ldr_out, int tm_width, void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(y && coord_idx && gt && tm_params && tm_grads && dy && db4 && sums && dy_absmax_bits && scale_out);
+  NC_CHECK_ARG(tm_width == TMW);   // the kernels are built for TonemapNet(W=128), the only width any config uses
+  NC_CHECK_WS(ws, ws_bytes, nchost::ws_bytes_psf_crf(B, N));
   const int use_gamma = gamma_dev != nullptr;
   NC_CHECK_ARG((exps != nullptr) != (fixed_exps != nullptr));
   NC_CHECK_ARG(exps == nullptr || dexps != nullptr);
@@ -754,11 +792,12 @@ extern "C" int neucam_psf_crf_loss(const float* y, const float* kout, const int6
   MidParams mp{};
   mp.B = B; mp.K = K; mp.HW = H * W; mp.N = N;
   mp.use_gamma = use_gamma; mp.use_mask = mask_w != nullptr; mp.has_blur = has_blur;
-  mp.gamma = gamma_dev; mp.fixed_value = fixed_value; mp.ue_weight = ue_weight; mp.db4 = db4;
+  mp.gamma = gamma_dev; mp.fixed_value = fixed_value; mp.ue_weight = ue_weight;
+  mp.part = reinterpret_cast<float*>(ws); mp.rec = nchost::ws_rec_psf_crf(N);
   mp.inv_count = 1.f / (float)global_count;
   mp.y = y; mp.kout = kout; mp.coord_idx = (const long long*)coord_idx; mp.exps = exps;
   mp.fixed_exps = fixed_exps; mp.gt = gt; mp.gamma_w = gamma_w; mp.mask_w = mask_w;
-  mp.dy = dy; mp.dkw = dkw; mp.dexps = dexps; mp.sums = sums; mp.dy_absmax_bits = dy_absmax_bits;
+  mp.dy = dy; mp.dkw = dkw; mp.sums = sums; mp.dy_absmax_bits = dy_absmax_bits;
   mp.ldr_out = ldr_out;
   TmParams tm{};
   for (int c = 0; c < 3; ++c) {
@@ -772,5 +811,20 @@ extern "C" int neucam_psf_crf_loss(const float* y, const float* kout, const int6
   NC_CHECK_CUDA(cudaGetLastError());
   loss_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dy_absmax_bits, scale_target, scale_out);
   NC_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  NC_COUNT_LAUNCH(2);
+  // fixed-order sum of the blocks' records into the (accumulated) gradient tensors and loss sums
+  nchost::ReduceSegs segs{};
+  int n = 0;
+  for (int c = 0; c < 3; ++c) {
+    segs.seg[n++] = {tm.gu[c], REC_TM + c * 3 * TMW, TMW};
+    segs.seg[n++] = {tm.ga[c], REC_TM + c * 3 * TMW + TMW, TMW};
+    segs.seg[n++] = {tm.gv[c], REC_TM + c * 3 * TMW + 2 * TMW, TMW};
+    segs.seg[n++] = {tm.gd[c], REC_GD + c, 1};
+  }
+  segs.seg[n++] = {sums, REC_SQ, 1};
+  segs.seg[n++] = {db4, REC_DB4, 3};
+  if (exps != nullptr) segs.seg[n++] = {dexps, REC_DEXP, N};
+  segs.nseg = n;
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), grid, mp.rec, segs, nullptr,
+                                        (cudaStream_t)stream);
 }

@@ -1,0 +1,81 @@
+// reduce.cu -- the second pass of every cross-block reduction in the library.
+//
+// No kernel of this library uses float atomics: a kernel that reduces over blocks (weight gradients, bias gradients,
+// loss sums) writes one partial record per block into a caller-provided workspace, and the kernel below adds the
+// records up IN BLOCK ORDER into the destination tensors.  Two runs of the same binary on the same inputs therefore
+// produce bit-identical gradients, losses and parameters -- which is what makes "same PSNR after the same number of
+// iterations" (BASELINE.json north_star) a testable statement for a chaotic training trajectory.
+#include "host_util.h"
+
+namespace {
+
+// thread = one element of the record; sums the nparts records with four interleaved accumulators combined in a fixed
+// order (deterministic, and 4 loads in flight per thread).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ ws, int nparts, long long stride, nchost::ReduceSegs segs, int total,
+                       const float* __restrict__ inv_scale_of) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float* dst = nullptr;
+#pragma unroll 1
+  for (int s = 0; s < segs.nseg; ++s) {
+    const int r = i - segs.seg[s].off;
+    if (r >= 0 && r < segs.seg[s].n) dst = segs.seg[s].dst + r;
+  }
+  if (dst == nullptr) return;   // padding between segments
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* p = ws + i;
+  int q = 0;
+  for (; q + 4 <= nparts; q += 4) {
+    a0 += p[(long long)(q + 0) * stride];
+    a1 += p[(long long)(q + 1) * stride];
+    a2 += p[(long long)(q + 2) * stride];
+    a3 += p[(long long)(q + 3) * stride];
+  }
+  for (; q < nparts; ++q) a0 += p[(long long)q * stride];
+  float t = (a0 + a1) + (a2 + a3);
+  if (inv_scale_of != nullptr) t *= 1.f / *inv_scale_of;
+  *dst += t;
+}
+
+}  // namespace
+
+namespace nchost {
+
+int launch_reduce_partials(const float* ws, int nparts, int64_t stride, const ReduceSegs& segs,
+                           const float* inv_scale_of, cudaStream_t stream) {
+  int total = 0;
+  for (int s = 0; s < segs.nseg; ++s)
+    if (segs.seg[s].off + segs.seg[s].n > total) total = segs.seg[s].off + segs.seg[s].n;
+  if (total == 0 || nparts <= 0) return 0;
+  reduce_partials_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, nparts, (long long)stride, segs, total,
+                                                                  inv_scale_of);
+  NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
+  return 0;
+}
+
+}  // namespace nchost
+
+extern "C" int neucam_reduce_ws_bytes(int kind, int64_t n, int aux, int64_t* bytes_out) {
+  NC_CHECK_ARG(bytes_out != nullptr && n >= 0 && aux >= 0);
+  int64_t b = 0;
+  switch (kind) {
+    case NEUCAM_WS_SINE_BWD: b = nchost::ws_bytes_sine_bwd(); break;
+    case NEUCAM_WS_WGRAD: b = nchost::ws_bytes_wgrad(); break;
+    case NEUCAM_WS_HEAD_WGRAD: b = nchost::ws_bytes_skinny(); break;
+    case NEUCAM_WS_PSF_CRF: b = nchost::ws_bytes_psf_crf(n, aux); break;
+    case NEUCAM_WS_BLUR_BWD: b = nchost::ws_bytes_blur_bwd(n, aux); break;
+    case NEUCAM_WS_RIGIDITY: b = nchost::ws_bytes_rigidity(n); break;
+    case NEUCAM_WS_BLEND: b = nchost::ws_bytes_blend(n); break;
+    default: NC_CHECK_ARG(!"unknown workspace kind");
+  }
+  *bytes_out = b;
+  return 0;
+}
+
+extern "C" int neucam_launch_count(int64_t* count_out) {
+  NC_CHECK_ARG(count_out != nullptr);
+  *count_out = (int64_t)nchost::launch_counter().load();
+  return 0;
+}

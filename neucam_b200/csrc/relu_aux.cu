@@ -121,6 +121,7 @@ extern "C" int neucam_relu_mlp_encode(const float* x, int64_t Q, int num_freq, v
   NC_CHECK_ARG(x && feat16 && Q > 0 && num_freq >= 0 && 2 * (3 + 6 * num_freq) <= FEAT);
   encode_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, Q, num_freq, (__half*)feat16);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -130,6 +131,7 @@ extern "C" int neucam_relu_mlp_encode_bwd(const float* x, const float* dfeat, in
   NC_CHECK_ARG(x && dfeat && dx && Q > 0 && num_freq >= 0 && 2 * (3 + 6 * num_freq) <= FEAT);
   encode_bwd_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, dfeat, Q, num_freq, dx);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -164,5 +166,6 @@ extern "C" int neucam_relu_mlp_pack(const float* const* w, const int* ld, int L,
   }
   pack_kernel<<<dim3(n, 8), 256, 0, (cudaStream_t)stream>>>(plan, S, (__half*)w_stages, (__half*)wT_stages);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }

@@ -116,7 +116,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void store_chunk_tma(const CUtensorMap* m_hi, const CUtensorMap* m_lo, uint32_t stage,
                                                 uint32_t lane, int col0, int row0, const uint32_t (&w)[16],
                                                 const uint32_t (&wl)[16], bool with_lo) {
-  if (lane == 0) tma_store_wait_read0();
+  if (elect_one()) tma_store_wait_read0();
   __syncwarp();
   const uint32_t hi = stage + lane * 64u, lo = hi + 2048u;
   const uint32_t sw = (lane >> 1) & 3u;   // SWIZZLE_64B: piece index ^ ((row >> 1) & 3): bank-conflict free
@@ -127,7 +127,7 @@ __device__ __forceinline__ void store_chunk_tma(const CUtensorMap* m_hi, const C
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (elect_one()) {
     tma_store_2d(m_hi, stage, col0, row0);
     if (with_lo) tma_store_2d(m_lo, stage + 2048u, col0, row0);
     tma_store_commit();
@@ -135,6 +135,11 @@ __device__ __forceinline__ void store_chunk_tma(const CUtensorMap* m_hi, const C
 }
 
 // trace[role][0] = number of events; events at trace[role][1 + 2 i] = id, [2 + 2 i] = clock64.  256 events per role.
+#ifndef NEUCAM_DEBUG
+#define stamp(...) ((void)0)
+#define RELU_DBG(bit) false
+#else
+#define RELU_DBG(bit) ((p.dbg & (bit)) != 0)
 __device__ __forceinline__ void stamp(long long* trace, int role, int id) {
   if (trace == nullptr || blockIdx.x != 0 || (threadIdx.x & 31) != 0) return;
   long long* t = trace + role * 520;
@@ -145,6 +150,7 @@ __device__ __forceinline__ void stamp(long long* trace, int role, int id) {
     t[0] = n + 1;
   }
 }
+#endif
 
 template <bool BWD>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -192,7 +198,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
       if (!BWD) {
         mbar_wait(bar(BAR_FEMPTY), fph ^ 1);
         fph ^= 1;
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar(BAR_FFULL), KB_BYTES);
           tma_load_2d(base + OFF_F, &maps.feat, bar(BAR_FFULL), 0, tile * TILE_M);
         }
@@ -201,8 +207,8 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
       for (int s = 0; s < S; ++s) {
         mbar_wait_backoff(bar(BAR_WEMPTY + slot), ph ^ 1, 32);
         stamp(p.trace, 0, 100 + s);
-        if (lane == 0) {
-          if (p.dbg & 4) {
+        if (elect_one()) {
+          if (RELU_DBG(4)) {
             mbar_arrive(bar(BAR_WFULL + slot));
           } else {
             mbar_arrive_expect_tx(bar(BAR_WFULL + slot), STAGE_BYTES);
@@ -231,7 +237,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         for (int s = p.stage_begin[g]; s < p.stage_begin[g + 1]; ++s) {
           mbar_wait(bar(BAR_WFULL + slot), ph);
           tc_fence_after_sync();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t b_addr = base + OFF_W + slot * STAGE_BYTES;
             const uint32_t srcs[2] = {p.a_src[s], p.a_src2[s]};
 #pragma unroll
@@ -242,7 +248,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
               const uint32_t a_tm = tmem_base + (src < 4 ? TM_AHI + src * 32 : TM_ALO + (src - 5) * 32);
 #pragma unroll
               for (int k16 = 0; k16 < 4; ++k16) {
-                if (p.dbg & 2) continue;
+                if (RELU_DBG(2)) continue;
                 const uint32_t acc = (s > p.stage_begin[g] || t > 0 || k16 > 0) ? 1u : 0u;
                 const uint64_t bd = make_sdesc_sw128(b_addr + k16 * 32, 0, 1024);
                 if (src == 4) umma_f16_ss(tmem_base + TM_ACC, make_sdesc_sw128(base + OFF_F + k16 * 32, 0, 1024), bd, idesc, acc);
@@ -254,7 +260,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           __syncwarp();
           if (++slot == NSTAGE) { slot = 0; ph ^= 1; }
         }
-        if (lane == 0) {
+        if (elect_one()) {
           if (!BWD && g == p.feat_last_gemm) umma_commit(bar(BAR_FEMPTY));
           umma_commit(bar(BAR_ACC));
         }
@@ -351,7 +357,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
 #pragma unroll 1
         for (uint32_t c = c_lo; c < c_hi; ++c) {
           uint32_t r[32];
-          if (!(p.dbg & 8)) {
+          if (!RELU_DBG(8)) {
             tmem_ld_32x32b_x32(t_row + TM_ACC + c * 32, r);
             tmem_ld_wait();
           } else {
@@ -393,7 +399,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
               wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
             }
           }
-          if (!(p.dbg & 1)) {
+          if (!RELU_DBG(1)) {
             tmem_st_32x32b_x16(t_row + TM_AHI + c * 16, w);
             if (!BWD || p.lo_operand) tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
           } else if (w[3] == 0x12345678u && wl[5] == 0x9abcdef0u) {
@@ -434,7 +440,7 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         }
       }
     }
-    if (lane == 0) tma_store_wait0();
+    if (elect_one()) tma_store_wait0();
   }
 
   tc_fence_before_sync();
@@ -442,8 +448,10 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
   if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
+#ifdef NEUCAM_DEBUG
 int g_relu_dbg = 0;
 long long* g_relu_trace = nullptr;
+#endif
 
 int check_stage_plan(int n_gemm, const int* stage_begin) {
   if (n_gemm < 1 || n_gemm > MAX_GEMM) return 1;
@@ -455,6 +463,7 @@ int check_stage_plan(int n_gemm, const int* stage_begin) {
 
 }  // namespace
 
+#ifdef NEUCAM_DEBUG
 // Timing experiments on the ReLU chain (results are garbage): see ReluParams::dbg.
 extern "C" int neucam_debug_set_relu_flags(int flags) {
   g_relu_dbg = flags;
@@ -467,6 +476,7 @@ extern "C" int neucam_debug_set_relu_trace(void* trace) {
   g_relu_trace = (long long*)trace;
   return 0;
 }
+#endif
 
 // forward of one ReLU MLP.  feat16 [Q,64] fp16 (encoded input, zero padded); w_stages [S*256,64] fp16 (per GEMM:
 // its 256 x 64 K-blocks in order); stage_begin[n_gemm+1]; a_src[S] (0..3 operand k-block, 4 encoded input) and
@@ -529,18 +539,17 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   p.lo_operand = 1;
   p.gates_out = (uint32_t*)gates;
   p.y = y;
+#ifdef NEUCAM_DEBUG
   p.dbg = g_relu_dbg;
   p.trace = g_relu_trace;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(relu_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM_BYTES));
-    attr_set = true;
-  }
+#endif
+  rc = nchost::ensure_dyn_smem((const void*)relu_chain_kernel<false>, (int)SMEM_BYTES);
+  if (rc) return rc;
   const int sms = nchost::sm_count();
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   relu_chain_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
@@ -601,15 +610,12 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
   p.gates = (const uint32_t*)gates;
   p.scale = scale_dev;
   p.dfeat = dfeat;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(relu_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  rc = nchost::ensure_dyn_smem((const void*)relu_chain_kernel<true>, (int)SMEM_BYTES);
+  if (rc) return rc;
   const int sms = nchost::sm_count();
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   relu_chain_kernel<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }

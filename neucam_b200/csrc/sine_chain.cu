@@ -57,6 +57,11 @@ constexpr int FIRST_EPI_WARP = 0;
 // producer / MMA-issuer / relay / store threads must never queue behind the 16 busy epilogue warps (measured:
 // with control warps at ids 0..3 every mbarrier poll of the MMA thread took 100-900 ns).
 constexpr int WARP_PRODUCER = 16, WARP_MMA = 17, WARP_ALLOC = 18, WARP_STORE = 19;
+#ifndef CHAIN_SETMAXNREG
+#define CHAIN_SETMAXNREG 0
+#endif
+#define CHAIN_REGS_CONTROL 40
+#define CHAIN_REGS_EPILOGUE 112
 constexpr int PAIR = 2;                            // CTAs per cluster (tcgen05 cta_group::2)
 constexpr uint16_t PAIR_MASK = 0x3;
 
@@ -101,13 +106,17 @@ struct ChainParams {
   float* y;              // forward out [Q,out_dim]
   const float* dy;       // backward in [Q,out_dim]
   float* duv;            // backward out [Q,2]
-  float* dw0;            // backward out [512,2] (accumulated into)
-  float* db0;            // backward out [512]   (accumulated into)
+  float* part;           // backward out: per-CTA partial record [gridDim.x][dW0 512x2 | db0 512] (reduce.cu sums them)
   const float* scale;    // backward: device scalar, power-of-two loss scale
+#ifdef NEUCAM_DEBUG
   long long* trace;      // optional debug timeline of CTA 0 (clock64 stamps), or null
   int dbg;               // debug experiments: bit0 = do not issue MMAs, bit1 = do not issue weight loads
+#endif
 };
 
+// The in-kernel timeline and the "no MMA / no TMA / no epilogue math" experiments exist only in the debug build
+// (-DNEUCAM_DEBUG -> libneucam_b200_debug.so); the product library compiles them out.
+#ifdef NEUCAM_DEBUG
 // trace layout: [role 0=mma,1=epi half0,2=epi half1 | +3 for the peer CTA][tile 0..1][g 0..2][step 0..7][4 stamps]
 // (globaltimer so that the two SMs of the pair share a time base)
 __device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i, int g, int step, int k) {
@@ -117,6 +126,11 @@ __device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i,
     tr[((((role + 3 * (int)blockIdx.x) * 2 + tile_i) * 3 + g) * 8 + step) * 4 + k] = (long long)t;
   }
 }
+#define CHAIN_DBG(bit) ((p.dbg & (bit)) != 0)
+#else
+#define trace_stamp(...) ((void)0)
+#define CHAIN_DBG(bit) false
+#endif
 
 struct ChainMaps {
   CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T), box 64 x 128
@@ -231,22 +245,34 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   // only the peer's tile is past the end it runs a phantom tile (all rows invalid, no global traffic).
   const int lead0 = (int)(blockIdx.x & ~1u);
 
+  // Register re-partitioning: 640 threads cap the launch allocation at 96 registers per thread, which the epilogue
+  // warps overflow (spills into a tiny L1 next to 227 KB of shared memory) while the four single-lane control warps
+  // need a fraction of it.  The control warpgroup (warps 16..19) hands registers back, the four epilogue warpgroups
+  // take them: 4 x 128 x (96 - 40) freed + 4096 unallocated >= 16 x 32 x (112 - 96).
+#if CHAIN_SETMAXNREG
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS_CONTROL));
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS_EPILOGUE));
+  }
+#endif
   if (warp == WARP_PRODUCER) {
     // ===================== TMA weight producer =====================
     // (the whole warp runs the loop and the waits; only the issue instructions are predicated to lane 0, so the
     //  warp never sits diverged against lanes parked at the final barrier)
     {
       uint32_t s = 0, ph = 0;
-      uint32_t full_bar[NSTAGE];   // the leader's w_full barriers (shared::cluster addresses)
-      for (uint32_t k = 0; k < NSTAGE; ++k) full_bar[k] = mapa_shared(bar(BAR_WFULL + k), 0);
+      // the leader's w_full barriers as shared::cluster addresses (mapa is linear inside a CTA's window: stage s is
+      // at + 8 s; an indexed local array here would put a local-memory load on the producer's critical path)
+      const uint32_t full_bar0 = mapa_shared(bar(BAR_WFULL), 0);
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
         if (BWD) {
           // head dgrad dh4 = dy W4 runs on the tensor cores too: one K = 16 step per 256-column half
           for (int h = 0; h < 2; ++h) {
             mbar_wait(bar(BAR_WEMPTY + s), ph ^ 1);
-            if (lane == 0) {
+            if (elect_one()) {
               if (leader) mbar_arrive_expect_tx(bar(BAR_WFULL + s), 2 * STAGE_BYTES);
-              tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w4t, full_bar[s], 0, h * 256 + (int)crank * 128);
+              tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w4t, full_bar0 + 8u * s, 0, h * 256 + (int)crank * 128);
             }
             __syncwarp();
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
@@ -257,13 +283,13 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int h = 0; h < 2; ++h) {
             for (int kb = 0; kb < 8; ++kb) {
               mbar_wait(bar(BAR_WEMPTY + s), ph ^ 1);
-              if (lane == 0) {
-                if (p.dbg & 2) {
+              if (elect_one()) {
+                if (CHAIN_DBG(2)) {
                   if (leader) mbar_arrive(bar(BAR_WFULL + s));
                 } else {
                   // the leader's barrier collects both halves of the 256-row weight tile
                   if (leader) mbar_arrive_expect_tx(bar(BAR_WFULL + s), 2 * STAGE_BYTES);
-                  tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w, full_bar[s], kb * 64,
+                  tma_load_2d_2cta(base + OFF_W + s * STAGE_BYTES, &maps.w, full_bar0 + 8u * s, kb * 64,
                                    wl * HID + h * 256 + (int)crank * 128);
                 }
               }
@@ -279,7 +305,9 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     if (leader) {
       const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
       uint32_t s = 0, ph = 0, ev = 0;   // ev = operand-write event counter (a_ready parity)
+#ifdef NEUCAM_DEBUG
       long long* trm = (lane == 0) ? p.trace : nullptr;
+#endif
       int tile_i = 0;
       uint32_t dyp = 0;   // parity of the dy-operand barriers (one phase per tile)
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
@@ -290,7 +318,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int h = 0; h < 2; ++h) {
             mbar_wait(bar(BAR_WFULL + s), ph);
             tc_fence_after_sync();
-            if (lane == 0) {
+            if (elect_one()) {
               // A = the dy operand in k-block slot 7 (columns 0..15), B = this half of W4^T: a single K = 16 MMA
               umma_f16_ss_2cta(tmem_base + h * 256, make_sdesc_sw128(base + OFF_A + 7 * A_BLOCK_BYTES, 0, 1024),
                                make_sdesc_sw128(base + OFF_W + s * STAGE_BYTES, 0, 1024), idesc, 0u);
@@ -329,12 +357,12 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               }
               mbar_wait(bar(BAR_WFULL + s), ph);
               tc_fence_after_sync();
-              if (lane == 0) {
+              if (elect_one()) {
                 const uint32_t a_addr = base + OFF_A + kb * A_BLOCK_BYTES;
                 const uint32_t b_addr = base + OFF_W + s * STAGE_BYTES;
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16) {
-                  if (p.dbg & 1) break;
+                  if (CHAIN_DBG(1)) break;
                   umma_f16_ss_2cta(tmem_base + h * 256, make_sdesc_sw128(a_addr + k16 * 32, 0, 1024),
                                    make_sdesc_sw128(b_addr + k16 * 32, 0, 1024), idesc, (kb | k16) != 0 ? 1u : 0u);
                 }
@@ -345,7 +373,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               __syncwarp();
               if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
-            if (lane == 0) {
+            if (elect_one()) {
               umma_commit_2cta(bar(BAR_ACC + 2 * h), PAIR_MASK);
               umma_commit_2cta(bar(BAR_ACC + 2 * h + 1), PAIR_MASK);
             }
@@ -358,9 +386,10 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     } else {
       // peer CTA: this warp has no MMAs to issue; it relays "operand k-block ready" to the leader
       uint32_t ev = 0;
-      uint32_t peer_bar[8];
-      for (uint32_t k = 0; k < 8; ++k) peer_bar[k] = mapa_shared(bar(BAR_PEER + k), 0);
+      const uint32_t peer_bar0 = mapa_shared(bar(BAR_PEER), 0);
+#ifdef NEUCAM_DEBUG
       long long* trm = (lane == 0) ? p.trace : nullptr;
+#endif
       int tile_i = 0;
       const uint32_t peer_dy = mapa_shared(bar(BAR_PEERDY), 0);
       uint32_t dyp = 0;
@@ -368,13 +397,13 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         if (BWD) {
           mbar_wait(bar(BAR_DYR), dyp);
           dyp ^= 1;
-          if (lane == 0) mbar_arrive_cluster(peer_dy);
+          if (elect_one()) mbar_arrive_cluster(peer_dy);
           __syncwarp();
         }
         for (int e3 = 0; e3 < 3; ++e3) {
           for (int kb = 0; kb < 8; ++kb) {
             mbar_wait(bar(BAR_AREADY + kb), ev & 1);
-            if (lane == 0) mbar_arrive_cluster(peer_bar[kb]);
+            if (elect_one()) mbar_arrive_cluster(peer_bar0 + 8u * kb);
             __syncwarp();
             // debug timeline: relay times of the event consumed by layer e3 (stored under "MMA role" of the peer)
             trace_stamp(trm, 0, tile_i, e3, 4 + (kb >> 2), kb & 3);
@@ -395,7 +424,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int kb = 0; kb < 8; ++kb) {
             if (e4 < 3) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
             else        mbar_wait(bar(BAR_AOUT + kb), tcount & 1);
-            if (lane == 0) {
+            if (elect_one()) {
               if (do_store) {
                 tma_store_2d(&maps.act[e4], base + OFF_A + kb * A_BLOCK_BYTES, kb * 64, tile * TILE_M);
                 tma_store_commit();
@@ -405,7 +434,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             }
             __syncwarp();
           }
-          if (lane == 0) {
+          if (elect_one()) {
             if (do_store) tma_store_wait_read0();
             mbar_arrive(bar(BAR_STORED + 7));
           }
@@ -413,7 +442,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           if (e4 < 3) ++ev;
         }
       }
-      if (lane == 0 && do_store_any) tma_store_wait0();
+      if (do_store_any && elect_one()) tma_store_wait0();
     }
   } else if (warp < 16) {
     // ===================== prologue / epilogue warps =====================
@@ -433,8 +462,10 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const uint32_t et = tid - FIRST_EPI_WARP * 32;          // 0..511: column owned in the dW0 column pass
     float gw0[3] = {0.f, 0.f, 0.f};                         // layer-0 weight-gradient partials (backward)
     const size_t ph_layer_stride = (size_t)p.ntiles * TILE_M * HID;
+#ifdef NEUCAM_DEBUG
     long long* tr = (quad == 0 && lane == 0 && (sub & 1) == 0) ? p.trace : nullptr;
     const int role = 1 + (int)(sub >> 1);
+#endif
     int tile_i = 0;
 
     for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tile_i) {
@@ -529,7 +560,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_row + col, r);
             tmem_ld_wait();
-            if (p.dbg & 4) {
+            if (CHAIN_DBG(4)) {
               // debug: no epilogue math (isolates tensor-pipe rate from SIMT/LDS contention)
 #pragma unroll
               for (int i = 0; i < 16; ++i) w[i] = r[2 * i];
@@ -662,10 +693,11 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       }
     }
     if (BWD) {
-      const float inv = 1.f / gscale;
-      atomicAdd(p.dw0 + et * 2 + 0, gw0[0] * inv);
-      atomicAdd(p.dw0 + et * 2 + 1, gw0[1] * inv);
-      atomicAdd(p.db0 + et, gw0[2] * inv);
+      // this CTA's share of dW0 / db0 (still carrying the loss scale): one record per CTA, summed in CTA order by
+      // reduce_partials_kernel -- no float atomics, bit-reproducible
+      float* rec = p.part + (size_t)blockIdx.x * (3 * HID);
+      *reinterpret_cast<float2*>(rec + 2 * et) = make_float2(gw0[0], gw0[1]);
+      rec[2 * HID + et] = gw0[2];
     }
   }
 
@@ -696,27 +728,30 @@ int build_maps(ChainMaps* m, const void* w16, void* const act[4], int64_t Q, boo
   return 0;
 }
 
+#ifdef NEUCAM_DEBUG
 long long* g_trace = nullptr;
 int g_dbg = 0;
+#endif
+
+int chain_grid(int ntiles) {
+  int grid = nchost::sm_count();
+  if (grid > ntiles) grid = ntiles;
+  return (grid + PAIR - 1) / PAIR * PAIR;   // whole pairs; an odd tile count gives one pair a phantom tile
+}
 
 template <bool BWD>
 int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(sine_chain_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM_BYTES));
-    attr_set = true;
-  }
-  int grid = nchost::sm_count();
-  if (grid > p.ntiles) grid = p.ntiles;
-  grid = (grid + PAIR - 1) / PAIR * PAIR;   // whole pairs; an odd tile count gives one pair a phantom tile
-  sine_chain_kernel<BWD><<<grid, NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  int rc = nchost::ensure_dyn_smem((const void*)sine_chain_kernel<BWD>, (int)SMEM_BYTES);
+  if (rc) return rc;
+  sine_chain_kernel<BWD><<<chain_grid(p.ntiles), NTHREADS, SMEM_BYTES, stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
   return 0;
 }
 
 }  // namespace
 
+#ifdef NEUCAM_DEBUG
 // Debug: when non-null, CTA 0 of the next chain launches writes clock64 stamps of its MMA / epilogue roles
 // into trace[6*2*3*8*4] (tools/chain_timeline.py decodes it).
 extern "C" int neucam_debug_set_chain_trace(long long* trace_dev) {
@@ -728,6 +763,7 @@ extern "C" int neucam_debug_set_chain_flags(int flags) {
   g_dbg = flags;
   return 0;
 }
+#endif
 
 extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, const float* b0,
                                    const void* w_hid16, const float* b_hid, const float* w4,
@@ -745,8 +781,10 @@ extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, 
   p.uv = uv; p.w0 = w0; p.b0 = b0; p.b_hid = b_hid; p.w4 = w4; p.b4 = b4;
   p.phase = reinterpret_cast<uint16_t*>(phase16);
   p.y = y;
+#ifdef NEUCAM_DEBUG
   p.trace = g_trace;
   p.dbg = g_dbg;
+#endif
   ChainMaps maps;
   void* act[4];
   for (int i = 0; i < 4; ++i) act[i] = act16 ? (void*)((__half*)act16 + (size_t)i * Q * HID) : nullptr;
@@ -758,10 +796,11 @@ extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, 
 extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0,
                                    const void* wT_hid16, const void* w4T16, int out_dim, const float* dy,
                                    const void* phase16, const float* scale_dev, void* dz16, float* duv,
-                                   float* dw0, float* db0, void* stream) {
+                                   float* dw0, float* db0, void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(uv && w0 && b0 && wT_hid16 && w4T16 && dy && phase16 && scale_dev && dz16 && duv && dw0 && db0);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - TILE_M);
   NC_CHECK_ARG(out_dim == 3 || out_dim == 4);
+  NC_CHECK_WS(ws, ws_bytes, nchost::ws_bytes_sine_bwd());
   ChainParams p{};
   p.Q = (int)Q;
   p.ntiles = (int)((Q + TILE_M - 1) / TILE_M);
@@ -769,10 +808,11 @@ extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, 
   p.store_act = 1;
   p.uv = uv; p.w0 = w0; p.b0 = b0; p.w4 = nullptr;
   p.phase = reinterpret_cast<uint16_t*>(const_cast<void*>(phase16));
-  p.dy = dy; p.duv = duv; p.scale = scale_dev; p.dw0 = dw0; p.db0 = db0;
+  p.dy = dy; p.duv = duv; p.scale = scale_dev; p.part = reinterpret_cast<float*>(ws);
+#ifdef NEUCAM_DEBUG
   p.trace = g_trace;
   p.dbg = g_dbg;
-  p.dbg = g_dbg;
+#endif
   ChainMaps maps;
   // store order of the backward chain: dz3 (prologue), dz2, dz1 -> dz16 = [3,Q,512] holding dz_1..dz_3
   // (dz0 never leaves the SM: its weight gradient is reduced in-kernel)
@@ -781,5 +821,13 @@ extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, 
   act[3] = act[2];
   int rc = build_maps(&maps, wT_hid16, act, Q, true, w4T16);
   if (rc) return rc;
-  return launch<true>(maps, p, (cudaStream_t)stream);
+  rc = launch<true>(maps, p, (cudaStream_t)stream);
+  if (rc) return rc;
+  // dW0 += sum over CTAs (in CTA order) of their records / loss scale; same for db0
+  nchost::ReduceSegs segs{};
+  segs.nseg = 2;
+  segs.seg[0] = {dw0, 0, 2 * HID};
+  segs.seg[1] = {db0, 2 * HID, HID};
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), chain_grid(p.ntiles), 3 * HID, segs,
+                                        scale_dev, (cudaStream_t)stream);
 }

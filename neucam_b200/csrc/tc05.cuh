@@ -76,8 +76,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > TC05_WAIT_TIMEOUT_CYCLES) {
+#ifdef NEUCAM_DEBUG
       printf("tc05: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }
@@ -94,8 +96,10 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
     __nanosleep(sleep_ns);
     if (mbar_try_wait(bar, parity)) return;
     if ((++polls & 1023u) == 0 && clock64() - t0 > TC05_WAIT_TIMEOUT_CYCLES) {
+#ifdef NEUCAM_DEBUG
       printf("tc05: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
+#endif
       __trap();
     }
   }
@@ -399,8 +403,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > TC05_WAIT_TIMEOUT_CYCLES) {
+#ifdef NEUCAM_DEBUG
       printf("tc05: cluster mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }

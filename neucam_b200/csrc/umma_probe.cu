@@ -8,6 +8,9 @@
 // flags: bit0 A is MN-major (global [K,128]); bit1 B is MN-major (global [K,N], N % 64 == 0);
 //        bit2 A is bf16; bit3 B is bf16; bit4 A tile is written by threads (K-major only);
 //        bit5 A operand lives in TENSOR MEMORY (each thread tcgen05.st's its own row; K-major only).
+// Built only into the debug library (-DNEUCAM_DEBUG -> libneucam_b200_debug.so; declared in
+// include/neucam_b200_debug.h): building-block self tests and microbenchmarks, not part of the product ABI.
+#ifdef NEUCAM_DEBUG
 #include "host_util.h"
 #include "tc05.cuh"
 
@@ -247,3 +250,5 @@ extern "C" int neucam_umma_rate(int N, int iters, int two_cta, int kblocks, int 
   NC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#endif  // NEUCAM_DEBUG

@@ -4,9 +4,10 @@
 //   hidden layers l = 1..3:  dW_l[j,k] = sum_r dz_l[r,j] * a_l[r,k],   db_l[j] = sum_r dz_l[r,j]
 //     a split-K tcgen05 GEMM on CTA pairs (cta_group::2): both operands are read as MN-major tiles straight
 //     out of the row-major [Q,512] fp16 buffers the chain kernels TMA-stored (no transposes anywhere); each
-//     pair owns one 256 x 256 output tile of one layer for one slice of the Q axis and reduces into the fp32
-//     gradient with red.global.add.  The bias gradient rides along as a 16-column MMA against an all-ones tile.
-//   head:  dW4[c,k] = sum_r dy[r,c] * a4[r,k]  (c < 4) -- an HBM-bound SIMT column reduction.
+//     pair owns one 256 x 256 output tile of one layer for one slice of the Q axis and writes it as a partial record
+//     into the reduction workspace; wgrad_reduce_kernel then adds the slices up in slice order (no float atomics:
+//     bit-reproducible).  The bias gradient rides along as a 16-column MMA against an all-ones tile.
+//   head:  dW4[c,k] = sum_r dy[r,c] * a4[r,k]  (c < 4) -- an HBM-bound SIMT column reduction, per-block partials.
 //
 // dz carries the power-of-two loss scale of the backward chain; it is divided out here.
 #include "host_util.h"
@@ -48,8 +49,11 @@ struct WgradParams {
   int Q;
   int nkb;              // ceil(Q / 64)
   int kb_per_split;
+  int splits;
   const float* scale;   // device scalar: loss scale carried by dz
+  float* part;          // workspace: [job][split][256 x 256 tile | 256 bias sums] partial records (still loss-scaled)
 };
+constexpr int REC = nchost::WS_WGRAD_REC;
 
 // A CTA pair (cluster of 2, cta_group::2) owns one 256 x 256 tile of one layer's dW for one slice of the Q
 // axis: each CTA stages its 128 dz-columns (A, M side) and its 128 activation-columns (B, N side) per 64-row
@@ -106,7 +110,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
       uint32_t s = 0, ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t full_leader = mapa_shared(bar_full + 8 * s, 0);
           if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);
           const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
@@ -125,7 +129,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after_sync();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_st = base + s * STAGE_BYTES, b_st = a_st + A_STAGE;
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
@@ -140,17 +144,18 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
           __syncwarp();
           if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
-        if (lane == 0) umma_commit_2cta(bar_acc, PAIR_MASK);
+        if (elect_one()) umma_commit_2cta(bar_acc, PAIR_MASK);
         __syncwarp();
       }
     } else {
       // epilogue warps 0..3 (control warps 4,5 have the highest ids = scheduling priority): TMEM lane quadrant = warp; this CTA owns dW rows m0.., all 256 columns of the tile
       const uint32_t quad = warp & 3;
       const uint32_t row = quad * 32 + lane;
-      const float inv = 1.f / *p.scale;
       mbar_wait(bar_acc, 0);
       tc_fence_after_sync();
-      float* out = job.dw + (size_t)(m0 + row) * job.ldw + job.n0;
+      // partial record of this (job, Q-slice): tile row = dW row (m0 - job.m0 + row), 256 columns; then 256 bias sums
+      float* rec = p.part + ((size_t)blockIdx.y * p.splits + split) * REC;
+      float* out = rec + (size_t)(crank * 128 + row) * 256;
       const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
       const int nchunk = job.n_valid >> 5;
       for (int i = 0; i < nchunk; ++i) {
@@ -158,15 +163,23 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
         tmem_ld_32x32b_x32(t_row + i * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(out + i * 32 + j, __uint_as_float(r[j]) * inv);
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(out + i * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
       if (with_bias) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_row + 256, r);
         tmem_ld_wait();
-        atomicAdd(job.db + m0 + row, __uint_as_float(r[0]) * inv);
+        rec[256 * 256 + crank * 128 + row] = __uint_as_float(r[0]);
       }
     }
+  } else if (warp < 4) {
+    // an empty trailing Q-slice still owns a record: zero it so that the reduction reads defined values
+    float* rec = p.part + ((size_t)blockIdx.y * p.splits + split) * REC;
+    const uint32_t row = (warp & 3) * 32 + lane;
+    float* out = rec + (size_t)(crank * 128 + row) * 256;
+    for (int j = 0; j < job.n_valid; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (with_bias) rec[256 * 256 + crank * 128 + row] = 0.f;
   }
 
   tc_fence_before_sync();
@@ -175,12 +188,51 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
   if (warp == 4) tmem_dealloc_2cta(tmem_base, 512);
 }
 
-// out[c][k] += sum_r s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
+// Second pass of the split-K weight gradients: element (i, j) of the 256 x 256 tile space (and the 256 bias sums) is
+// owned by one thread, which walks the jobs IN ORDER and, per job, its Q-slices in order:
+//   dw[m0 + i, n0 + j] += (sum_s part[job][s][i][j]) / scale.
+// Jobs that target the same tile of the same tensor (the optional hi / lo operand splits of the ReLU MLPs) are thus
+// serialised inside one thread: no atomics, no races, a fixed summation order.
+struct ReduceJob {
+  float* dw;
+  float* db;
+  int m0, n0, ldw, n_valid;
+};
+struct ReduceJobs {
+  ReduceJob job[MAX_JOBS];
+};
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int n_jobs, int splits,
+                    const float* __restrict__ scale) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. REC-1
+  if (e >= REC) return;
+  const float inv = 1.f / *scale;
+  const bool bias = e >= 256 * 256;
+  const int i = bias ? (e - 256 * 256) : (e >> 8), j = e & 255;
+#pragma unroll 1
+  for (int jb = 0; jb < n_jobs; ++jb) {
+    const ReduceJob& J = jobs.job[jb];
+    if (bias ? (J.db == nullptr) : (j >= J.n_valid)) continue;
+    const float* src = part + (size_t)jb * splits * REC + e;
+    float a0 = 0.f, a1 = 0.f;
+    int s = 0;
+    for (; s + 2 <= splits; s += 2) {
+      a0 += src[(size_t)s * REC];
+      a1 += src[(size_t)(s + 1) * REC];
+    }
+    if (s < splits) a0 += src[(size_t)s * REC];
+    const float t = (a0 + a1) * inv;
+    if (bias) J.db[J.m0 + i] += t;
+    else J.dw[(size_t)(J.m0 + i) * J.ldw + J.n0 + j] += t;
+  }
+}
+
+// part[block][c][k] = sum over the block's rows of s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
 // 512 threads = 8 row lanes x 64 column groups of 8 (one 16-byte load each), 4 rows in flight per thread.
 template <int WIDTH>
 __global__ void __launch_bounds__(512)
 skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int nc, int Q,
-                    int rows_per_block, float* __restrict__ out) {
+                    int rows_per_block, float* __restrict__ part) {
   constexpr int HID = WIDTH;                 // row length of x
   constexpr int CG = WIDTH / 8;              // column groups of 8 (one 16-byte load each)
   constexpr int RL = 512 / CG;               // row lanes
@@ -235,14 +287,15 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
     float t = 0.f;
 #pragma unroll
     for (int l = 0; l < RL; ++l) t += s_acc[l][c][k];
-    atomicAdd(out + c * HID + k, t);
+    part[(size_t)blockIdx.x * nchost::WS_SKINNY_REC + e] = t;   // reduced over blocks, in block order, by reduce.cu
   }
 }
 
 }  // namespace
 
-// shared launch: n_jobs pair tiles x Q-slices filling the machine's CTA pairs
-static int launch_wgrad_jobs(WgradJobs& jobs, int n_jobs, int64_t Q, const float* scale_dev, void* stream) {
+// shared launch: n_jobs pair tiles x Q-slices filling the machine's CTA pairs, then the fixed-order slice reduction
+static int launch_wgrad_jobs(WgradJobs& jobs, int n_jobs, int64_t Q, const float* scale_dev, void* ws,
+                             int64_t ws_bytes, void* stream) {
   WgradParams p{};
   p.Q = (int)Q;
   p.nkb = (int)((Q + 63) / 64);
@@ -250,16 +303,23 @@ static int launch_wgrad_jobs(WgradJobs& jobs, int n_jobs, int64_t Q, const float
   if (splits < 1) splits = 1;
   if (splits > p.nkb) splits = p.nkb;
   p.kb_per_split = (p.nkb + splits - 1) / splits;
+  p.splits = splits;
   p.scale = scale_dev;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(hidden_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  p.part = reinterpret_cast<float*>(ws);
+  NC_CHECK_WS(ws, ws_bytes, (int64_t)n_jobs * splits * REC * 4);
+  int rc = nchost::ensure_dyn_smem((const void*)hidden_wgrad_kernel, (int)SMEM_BYTES);
+  if (rc) return rc;
   dim3 grid(2 * splits, n_jobs, 1);
   hidden_wgrad_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(jobs, p);
   NC_CHECK_CUDA(cudaGetLastError());
+  ReduceJobs rj;
+  for (int i = 0; i < n_jobs; ++i) {
+    const WgradJob& j = jobs.job[i];
+    rj.job[i] = ReduceJob{j.dw, j.db, j.m0, j.n0, j.ldw, j.n_valid};
+  }
+  wgrad_reduce_kernel<<<(REC + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p.part, rj, n_jobs, splits, scale_dev);
+  NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(2);
   return 0;
 }
 
@@ -275,7 +335,7 @@ static int fill_job(WgradJob& j, const void* dz, int dz_cols, const void* act, i
 
 extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const float* scale_dev,
                                      float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
-                                     void* stream) {
+                                     void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(dz16 && act16 && scale_dev && dw1 && db1 && dw2 && db2 && dw3 && db3);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128);
   float* dw[3] = {dw1, dw2, dw3};
@@ -293,7 +353,7 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
         if (rc) return rc;
       }
   }
-  return launch_wgrad_jobs(jobs, n, Q, scale_dev, stream);
+  return launch_wgrad_jobs(jobs, n, Q, scale_dev, ws, ws_bytes, stream);
 }
 
 // Weight gradients of one 256-wide ReLU MLP (reference modules.py:255-306) from the buffers the chain kernels stored.
@@ -305,7 +365,7 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
 extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, const void* act16, const void* act_lo16,
                                      const void* feat16, int64_t Q, int H, const float* scale_dev, float* dw_first,
                                      float* const* dw, const int* ldw, float* const* db, float* const* dw_skip,
-                                     void* stream) {
+                                     void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(dz16 && act16 && feat16 && scale_dev && dw_first && dw && ldw && db && dw_skip);
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128 && H >= 1 && H <= 8);
   constexpr int W = 256;
@@ -337,39 +397,44 @@ extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, cons
     }
     if (rc) return rc;
   }
-  return launch_wgrad_jobs(jobs, n, Q, scale_dev, stream);
+  return launch_wgrad_jobs(jobs, n, Q, scale_dev, ws, ws_bytes, stream);
 }
 
 template <int WIDTH>
-static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, float* out, void* stream) {
+static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, float* out, void* ws, int64_t ws_bytes,
+                         void* stream) {
   const int blocks = nchost::sm_count() * 2;
   int rows = (int)((Q + blocks - 1) / blocks);
   if (rows < 32) rows = 32;
   const int grid = (int)((Q + rows - 1) / rows);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NC_CHECK_CUDA(cudaFuncSetAttribute(skinny_wgrad_kernel<WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    attr_set = true;
-  }
-  skinny_wgrad_kernel<WIDTH><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows, out);
+  NC_CHECK_WS(ws, ws_bytes, (int64_t)grid * nchost::WS_SKINNY_REC * 4);
+  int rc = nchost::ensure_dyn_smem((const void*)skinny_wgrad_kernel<WIDTH>, 65536);
+  if (rc) return rc;
+  skinny_wgrad_kernel<WIDTH><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows,
+                                                                         reinterpret_cast<float*>(ws));
   NC_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  NC_COUNT_LAUNCH(1);
+  nchost::ReduceSegs segs{};
+  segs.nseg = 1;
+  segs.seg[0] = {out, 0, nc * WIDTH};
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), grid, nchost::WS_SKINNY_REC, segs, nullptr,
+                                        (cudaStream_t)stream);
 }
 
 extern "C" int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q,
-                                          float* dw4, void* stream) {
+                                          float* dw4, void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(a4_16 && dy && dw4);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  return launch_skinny<512>(a4_16, dy, out_dim, Q, dw4, stream);
+  return launch_skinny<512>(a4_16, dy, out_dim, Q, dw4, ws, ws_bytes, stream);
 }
 
 // dw_last[c,k] += sum_r dpre[r,c] * (h[r,k] + h_lo[r,k]) for the last layer of a 256-wide ReLU MLP
 // (h, h_lo fp16 [Q,256]; c < 4).
 extern "C" int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, const float* dpre, int out_dim,
-                                          int64_t Q, float* dw_last, void* stream) {
+                                          int64_t Q, float* dw_last, void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(h16 && dpre && dw_last);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  int rc = launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, stream);
+  int rc = launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);
   if (rc || h_lo16 == nullptr) return rc;
-  return launch_skinny<256>(h_lo16, dpre, out_dim, Q, dw_last, stream);
+  return launch_skinny<256>(h_lo16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);   // stream order: ws is free again
 }

@@ -70,6 +70,10 @@ class LayeredTrainStep:
             self.world = dist.get_world_size(process_group)
         self.global_pixels = global_pixels
         self.params = None if _host_logic_only else FlatParameters(models, self.device)
+        if self.params is not None:
+            ops.check_tm_shapes(list(models["tm"].parameters()))   # the CRF kernels execute TonemapNet(W=128) only
+            if self.world > 1:
+                self.params.broadcast_from_rank0(self.pg)          # replicas start bit-identical by construction
         n, h, w = self.shape
         self.K = int(options.patch_size) if models.get("blur") is not None else 1
         if self.K not in (1, 9, 25):
@@ -316,9 +320,9 @@ class LayeredTrainStep:
 
     # -- CUDA graph ---------------------------------------------------------------------------------------------
     def capture(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None):
-        """Captures forward + autograd backward + Adam over STATIC device copies of one batch into a CUDA graph
-        (two graphs around the eager gradient all-reduce when distributed); `run_resident()` replays it after
-        `load_resident()` refreshed the static buffers.  The rigidity window is decided at capture time."""
+        """Captures forward + autograd backward + gradient all-reduce (NCCL collectives are captured like any other
+        stream work) + Adam over STATIC device copies of one batch into ONE CUDA graph; `run_resident()` replays it
+        after `load_resident()` refreshed the static buffers.  The rigidity window is decided at capture time."""
         dev = self.device
         self._static_in = {k: v.to(dev).clone() for k, v in model_input.items() if torch.is_tensor(v)}
         self._static_gt = {"img": gt["img"].to(dev).clone()}
@@ -338,14 +342,8 @@ class LayeredTrainStep:
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             self.forward_backward(self._static_in, self._static_gt, self._static_gamma, use_mask)
-            if self.world == 1:
-                self.optimizer_step(reduce=False, lr_groups=lr_groups)
-        g2 = None
-        if self.world > 1:
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                self.optimizer_step(reduce=False, lr_groups=lr_groups)
-        self._graph = (g1, g2)
+            self.optimizer_step(reduce=True, lr_groups=lr_groups)
+        self._graph = g1
         return self._graph
 
     def graph_step(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None):
@@ -369,11 +367,7 @@ class LayeredTrainStep:
             self._static_gamma.copy_(torch.as_tensor(gamma, dtype=torch.float32).view(1), non_blocking=non_blocking)
 
     def run_resident(self):
-        g1, g2 = self._graph
-        g1.replay()
-        if g2 is not None:
-            self.reduce_gradients()
-            g2.replay()
+        self._graph.replay()
         self.step_index += 1
         return self._losses
 

@@ -107,9 +107,10 @@ class _Rigidity(torch.autograd.Function):
         out = torch.zeros(1, device=dev)
         g_ref = torch.empty((B, 2), device=dev)
         g_moved = torch.empty((2, B, 2), device=dev)
+        ws = ops.new_ws(ops.WS_RIGIDITY, B, device=dev)
         rc = _lib.lib().neucam_rigidity_loss(_lib.ptr(uv_ref), _lib.ptr(uv_moved), B, ctypes.c_float(ku),
                                              ctypes.c_float(kv), _lib.ptr(coef), _lib.ptr(out), _lib.ptr(g_ref),
-                                             _lib.ptr(g_moved), _lib.cur_stream())
+                                             _lib.ptr(g_moved), *ops._ws_args(ws), _lib.cur_stream())
         _lib.check(rc, "neucam_rigidity_loss")
         ctx.save_for_backward(g_ref, g_moved)
         return out.reshape(())
@@ -138,9 +139,11 @@ class _LayerBlend(torch.autograd.Function):
         out = torch.empty_like(back)
         e2 = torch.empty((K, B), device=dev)
         sums = torch.zeros(3, device=dev)
+        ws = ops.new_ws(ops.WS_BLEND, K * B, device=dev)
         rc = _lib.lib().neucam_layer_blend_fwd(_lib.ptr(back), _lib.ptr(front), _lib.ptr(alpha), K, B,
                                                ctypes.c_float(c1), ctypes.c_float(c2), ctypes.c_float(c3),
-                                               _lib.ptr(out), _lib.ptr(e2), _lib.ptr(sums), _lib.cur_stream())
+                                               _lib.ptr(out), _lib.ptr(e2), _lib.ptr(sums), *ops._ws_args(ws),
+                                               _lib.cur_stream())
         _lib.check(rc, "neucam_layer_blend_fwd")
         ctx.save_for_backward(back, front, alpha, e2)
         ctx.coefs = coefs

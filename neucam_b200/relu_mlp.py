@@ -174,14 +174,18 @@ class _ReluMLPFunction(torch.autograd.Function):
             enc = parts[-1].view(1 + len(skips), WID, FEAT)                    # dw_first, dw_skip...
         arr = lambda items: (ctypes.c_void_p * len(items))(*[0 if t is None else t.data_ptr() for t in items])
         ldw = (ctypes.c_int * H)(*[int(w.shape[1]) for w in ws[:H]])
+        # per-block partial records + fixed-order second pass (no float atomics); one workspace serves both calls,
+        # which run back to back on this stream
+        red_ws = ops.new_ws(ops.WS_WGRAD, device=dev)
         rc = lib.neucam_relu_mlp_wgrad(_lib.ptr(dz16[0]), _lib.ptr(lo(dz16)), _lib.ptr(act16[0]), _lib.ptr(lo(act16)),
                                        _lib.ptr(feat16), ctypes.c_int64(Q), H, _lib.ptr(scale), _lib.ptr(enc[0]),
                                        arr([None] + dw[1:H]), ldw, arr(db[:H]),
-                                       arr([enc[skip_slot[l]] if l in skip_slot else None for l in range(H)]), stream)
+                                       arr([enc[skip_slot[l]] if l in skip_slot else None for l in range(H)]),
+                                       *ops._ws_args(red_ws), stream)
         _lib.check(rc, "neucam_relu_mlp_wgrad")
         rc = lib.neucam_relu_mlp_head_wgrad(_lib.ptr(act16[0, H - 1]),
                                             _lib.ptr(act16[1, H - 1] if n_parts == 2 else None), _lib.ptr(dpre),
-                                            out_dim, ctypes.c_int64(Q), _lib.ptr(dw[H]), stream)
+                                            out_dim, ctypes.c_int64(Q), _lib.ptr(dw[H]), *ops._ws_args(red_ws), stream)
         _lib.check(rc, "neucam_relu_mlp_head_wgrad")
         fold = lambda e: e[:, :E] + e[:, E:2 * E]      # hi + lo halves of the features
         if tg is not None:

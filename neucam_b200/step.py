@@ -14,6 +14,7 @@ All parameters of all models are re-homed as views into ONE flat fp32 buffer (sa
 Adam moments) so the optimizer and the all-reduce see a single tensor; module attribute names and
 state_dict keys are untouched, so utils.save_model-style checkpoints keep the reference's layout.
 """
+import ctypes
 import math
 from collections import OrderedDict
 
@@ -74,6 +75,18 @@ class FlatParameters:
         self.exp_avg_sq.zero_()
         self.adam_state.zero_()
 
+    def broadcast_from_rank0(self, process_group):
+        """Data parallel relies on every rank holding bit-identical parameters and optimizer state: the summed
+        gradient is applied to each rank's own copy.  Make that true by construction instead of by convention."""
+        import torch.distributed as dist
+        for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.adam_state):
+            dist.broadcast(t, src=dist.get_global_rank(process_group, 0), group=process_group)
+
+    def checksum(self):
+        """Order-independent fingerprint of the parameters (sum of the raw bit patterns as int64): equal across ranks
+        iff the replicas are bit-identical.  Device scalar."""
+        return self.flat.view(torch.int32).to(torch.int64).sum()
+
 
 class StepOptions:
     """The fields of the reference's `opt` namespace (configs.py) that the hot path reads."""
@@ -93,8 +106,17 @@ class StepOptions:
         self.sparsity_loss_w = sparsity_loss_w
         self.alpha_loss_w = alpha_loss_w
 
+    # reference options that change the objective (training.py:97-110, 190-238) and that no shipped config switches
+    # on: refuse them instead of silently training something else
+    UNSUPPORTED_FLAGS = ("flow_loss", "mask_loss", "use_depth", "patch_sample", "denoise")
+
     @classmethod
     def from_opt(cls, opt):
+        for flag in cls.UNSUPPORTED_FLAGS:
+            if getattr(opt, flag, False):
+                raise NotImplementedError(
+                    f"option '{flag}' is outside the NeuCam hot path built here (every shipped config leaves it off); "
+                    "refusing to train with a different objective than the reference would")
         on = lambda flag, w: float(getattr(opt, w)) if getattr(opt, flag, False) else None
         return cls(patch_size=getattr(opt, "patch_size", 9), offset_size=getattr(opt, "offset_size", 5),
                    use_random_gamma=bool(getattr(opt, "use_random_gamma", False)),
@@ -207,8 +229,18 @@ class FusedTrainStep:
         self.absmax_bits = self.scalars[4:5]
         self.scale = torch.ones(1, device=dev)
         self._side = torch.cuda.Stream(device=self.device)
+        # reduction workspaces (fixed-order second pass instead of float atomics): the main stream's calls run back to
+        # back and share one; the blur backward runs concurrently on the side stream and has its own
+        N = self.shape[0]
+        main_bytes = max(ops.reduce_ws_bytes(ops.WS_SINE_BWD), ops.reduce_ws_bytes(ops.WS_WGRAD),
+                         ops.reduce_ws_bytes(ops.WS_HEAD_WGRAD), ops.reduce_ws_bytes(ops.WS_PSF_CRF, B, N))
+        self.ws_main = torch.empty(main_bytes, dtype=torch.uint8, device=dev)
+        self.ws_side = torch.empty(max(ops.reduce_ws_bytes(ops.WS_BLUR_BWD, B, N), 16), dtype=torch.uint8, device=dev)
         self._bind()
+        if self.world > 1:
+            self.params.broadcast_from_rank0(self.pg)
         self.repack()
+        self._args = {}
 
     # -- parameter / gradient pointer tables -----------------------------------------------------------
     def _bind(self):
@@ -224,6 +256,7 @@ class FusedTrainStep:
         for ch in "rgb":
             self.tm_p += [tm[f"layers_{ch}.0.weight"], tm[f"layers_{ch}.0.bias"], tm[f"layers_{ch}.2.weight"],
                           tm[f"layers_{ch}.2.bias"]]
+        ops.check_tm_shapes(self.tm_p)      # the CRF kernels are built for TonemapNet(W=128): anything else raises
         self.tm_g = [p.grad for p in self.tm_p]
         self.exps = m["exp"].exps
         if self.has_blur:
@@ -235,11 +268,62 @@ class FusedTrainStep:
             self.focus = m["focal"].focus
 
     def repack(self):
-        """fp16 tensor-core operand copies of the atlas hidden weights (+ packed hidden biases)."""
+        """fp16 tensor-core operand copies of the atlas hidden weights (+ packed hidden biases).  Must follow every
+        write to the parameters: optimizer_step() does it, and _sync_operands() does it for writes that went through
+        torch (load_state_dict / utils.load_model / manual edits), which bump the flat buffer's version counter."""
         ops.pack_hidden_weights(self.aw[1].data, self.aw[2].data, self.aw[3].data, self.w16, self.wT16)
         ops.pack_head_weights(self.aw[4].data, self.w4T16)
         for i in range(3):
             self.b_hid[i].copy_(self.ab[i + 1].data)
+        self._packed_version = self.params.flat._version
+
+    def _sync_operands(self):
+        # the fused Adam writes through raw pointers (no version bump) and repacks itself; any OTHER writer is a torch
+        # op on the flat buffer or one of its views, which shares this counter
+        if self.params.flat._version != self._packed_version:
+            self.repack()
+
+    def _step_args(self, use_mask):
+        """The argument block of neucam_step_fwd_bwd for this step's (static) buffers, built once per variant."""
+        key = bool(use_mask)
+        if key in self._args:
+            return self._args[key]
+        o, P, dp = self.opt, self.params, ops._dp
+        N, H, W = self.shape
+        a = ops.StepArgs()
+        a.struct_bytes = ctypes.sizeof(ops.StepArgs)
+        a.B, a.K, a.N, a.H, a.W = self.B, self.K, N, H, W
+        a.out_dim, a.tm_width = self.out_dim, ops.TM_WIDTH
+        a.offset_size, a.fixed_value, a.ue_weight = float(o.offset_size), float(o.fixed_value), 1.0 / self.world
+        a.global_count = 3 * self.global_pixels
+        a.coords, a.coord_idx, a.img = dp(self.coords), dp(self.coord_idx), dp(self.img)
+        a.gamma_w = dp(self.gamma_w) if o.use_random_gamma else None
+        a.gamma_dev = dp(self.gamma) if o.use_random_gamma else None
+        a.mask_w = dp(self.mask_w) if use_mask else None
+        if self.has_blur:
+            a.focus, a.g_focus = dp(self.focus.data), dp(self.focus.grad)
+            for i in range(8):
+                a.blur_params[i] = dp(self.blur_p[i].data)
+                a.g_blur[i] = dp(self.blur_g[i])
+            a.kout, a.hid, a.dkw = dp(self.kout), dp(self.hid), dp(self.dkw)
+        a.w0, a.b0, a.b_hid, a.w4, a.b4 = dp(self.aw[0].data), dp(self.ab[0].data), dp(self.b_hid), dp(self.aw[4].data), dp(self.ab[4].data)
+        a.w_hid16, a.wT_hid16, a.w4T16 = dp(self.w16), dp(self.wT16), dp(self.w4T16)
+        a.exps, a.g_exps = dp(self.exps.data), dp(self.exps.grad)
+        for i in range(12):
+            a.tm_params[i] = dp(self.tm_p[i].data)
+            a.g_tm[i] = dp(self.tm_g[i])
+        a.g_w0, a.g_b0, a.g_w4, a.g_b4 = dp(self.aw[0].grad), dp(self.ab[0].grad), dp(self.aw[4].grad), dp(self.ab[4].grad)
+        for i in range(3):
+            a.g_w[i] = dp(self.aw[i + 1].grad)
+            a.g_b[i] = dp(self.ab[i + 1].grad)
+        a.zero_ptr, a.zero_bytes = dp(P.grad), P.grad.numel() * 4
+        a.uv, a.y, a.dy, a.duv = dp(self.uv), dp(self.y), dp(self.dy), dp(self.duv)
+        a.act16, a.phase16, a.dz16 = dp(self.act16), dp(self.phase16), dp(self.dz16)
+        a.sums, a.absmax_bits, a.scale = dp(self.sums), dp(self.absmax_bits), dp(self.scale)
+        a.ws, a.ws_bytes = dp(self.ws_main), self.ws_main.numel()
+        a.ws_side, a.ws_side_bytes = dp(self.ws_side), self.ws_side.numel()
+        self._args[key] = a
+        return a
 
     # -- data ----------------------------------------------------------------------------------------------
     def load_batch(self, model_input, gt, gamma=None, non_blocking=True):
@@ -287,7 +371,14 @@ class FusedTrainStep:
         events: optional list; the three tensor-core kernels are then bracketed by CUDA events on the launch stream
         and (name, start, end) tuples appended (bench.py: per-kernel durations inside real steps)."""
         o = self.opt
+        self._sync_operands()
+        if events is None:
+            # the product path: the whole forward + backward from ONE C call (neucam_step_fwd_bwd)
+            ops.step_fwd_bwd(self._step_args(use_mask), self._side if self.has_blur else None)
+            return
 
+        # per-kernel path (bench.py's in-step kernel timing; tests pin it to the one-call path): the same entry points
+        # in the same order, launched one by one
         def timed(name, fn):
             if events is None:
                 return fn()
@@ -305,9 +396,9 @@ class FusedTrainStep:
         if self.has_blur:
             ops.blur_fwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.shape, K,
                          float(o.offset_size), self.uv, self.kout, self.hid)
-            uv = self.uv.view(-1, 2)
         else:
-            uv = self.coords[:, 1:3].contiguous()
+            self.uv.view(-1, 2).copy_(self.coords[:, 1:3])
+        uv = self.uv.view(-1, 2)
         timed("sine_chain_fwd", lambda: ops.sine_mlp_fwd(
             uv, self.aw[0].data, self.ab[0].data, self.w16, self.b_hid, self.aw[4].data, self.ab[4].data,
             y=self.y.view(-1, self.out_dim), act16=self.act16, phase16=self.phase16))
@@ -316,14 +407,14 @@ class FusedTrainStep:
                          [p.data for p in self.tm_p], self.tm_g, self.shape, K, self.has_blur,
                          self.gamma if o.use_random_gamma else None, float(o.fixed_value), 1.0 / self.world,
                          3 * self.global_pixels, self.dy, self.dkw if self.has_blur else None, self.exps.grad,
-                         self.ab[4].grad, self.sums, self.absmax_bits.view(torch.int32), self.scale)
+                         self.ab[4].grad, self.sums, self.absmax_bits.view(torch.int32), self.scale, ws=self.ws_main)
         dyf = self.dy.view(-1, self.out_dim)
         timed("sine_chain_bwd", lambda: ops.sine_mlp_bwd(
             uv, self.aw[0].data, self.ab[0].data, self.wT16, self.w4T16, dyf, self.phase16, self.scale,
-            self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2)))
+            self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2), ws=self.ws_main))
         timed("hidden_wgrad", lambda: ops.sine_mlp_wgrad(
             self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
-            [self.ab[i].grad for i in (1, 2, 3)]))
+            [self.ab[i].grad for i in (1, 2, 3)], ws=self.ws_main))
         # the HBM-bound head wgrad and the FMA-bound blur backward are independent: run them side by side
         main = torch.cuda.current_stream(self.device)
         if self.has_blur:
@@ -331,8 +422,8 @@ class FusedTrainStep:
             with torch.cuda.stream(self._side):
                 ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
                              self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw,
-                             self.duv)
-        ops.sine_mlp_head_wgrad(self.act16, dyf, self.aw[4].grad)
+                             self.duv, ws=self.ws_side)
+        ops.sine_mlp_head_wgrad(self.act16, dyf, self.aw[4].grad, ws=self.ws_main)
         if self.has_blur:
             main.wait_stream(self._side)
 
@@ -341,6 +432,32 @@ class FusedTrainStep:
         if self.world > 1:
             from .dist import allreduce_flat_gradients
             allreduce_flat_gradients(self.params.grad, self.pg)
+
+    def _bucket_split(self):
+        """Offset in the flat buffer where the atlas head weights start: everything before it (atlas layers 0..3 =
+        98 % of the parameters) is final once the hidden weight gradients are reduced, i.e. BEFORE the step's tails."""
+        for slot, name, p, off, n in self.params.entries:
+            if slot == "atlas_b" and name == "net.net.4.0.weight":
+                return off
+        raise RuntimeError("atlas_b.net.net.4.0.weight not found in the flat parameter buffer")
+
+    def forward_backward_reduced(self, use_mask=False):
+        """forward + backward + gradient reduction.  Distributed: the all-reduce of the atlas bucket (layers 0..3)
+        is enqueued on NCCL's stream as soon as the hidden weight gradients exist and runs UNDER the step's tails
+        (head weight gradient || blur backward); the small rest follows.  Both are graph-capturable."""
+        if self.world == 1:
+            return self.forward_backward(use_mask=use_mask)
+        import torch.distributed as dist
+        self._sync_operands()
+        a = self._step_args(use_mask)
+        g = self.params.grad
+        cut = self._bucket_split()
+        ops.step_fwd_bwd(a, None, phases=ops.STEP_TO_HIDDEN_WGRAD)
+        w1 = dist.all_reduce(g[:cut], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        ops.step_fwd_bwd(a, self._side if self.has_blur else None, phases=ops.STEP_TAILS)
+        w2 = dist.all_reduce(g[cut:], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        w1.wait()
+        w2.wait()
 
     def optimizer_step(self, lr=None, reduce=True, lr_groups=None):
         """Gradient all-reduce (when distributed) + fused Adam + operand re-pack.
@@ -364,54 +481,67 @@ class FusedTrainStep:
         return torch.relu(-slope) * 1e6
 
     def losses(self):
-        """Device scalars: img_loss (this rank's share of the global mean), ue_loss, total."""
+        """Device scalars: img_loss (this rank's share of the global mean), ue_loss (weighted 1 / world like its
+        gradient), total -- the SUM over ranks of each equals the single-process loss on the union batch."""
         img = self.sums[0] / float(3 * self.global_pixels)
-        ue = self.sums[1]
+        ue = self.sums[1] * (1.0 / self.world)
         return OrderedDict(img_loss=img, ue_loss=ue, total=img + ue)
 
     # -- CUDA graph ---------------------------------------------------------------------------------------
-    def capture(self, use_mask=False, lr=None):
-        """Captures forward_backward + optimizer_step into one CUDA graph (all kernel arguments are pointers
-        to fixed buffers; the step's inputs are read from the static device buffers filled by load_batch, the
-        step counter and loss scale live on the device).  `step()` replays it afterwards.  Re-capture after
-        changing the learning rate or use_mask."""
-        # one eager step first: sets kernel attributes and warms NCCL outside of capture
-        saved = [t.clone() for t in (self.params.flat, self.params.exp_avg, self.params.exp_avg_sq,
-                                     self.params.adam_state)]
-        self.forward_backward(use_mask=use_mask)
-        self.optimizer_step(lr)
-        torch.cuda.synchronize(self.device)
-        for dst, src in zip((self.params.flat, self.params.exp_avg, self.params.exp_avg_sq, self.params.adam_state),
-                            saved):
-            dst.copy_(src)
-        self.repack()
-        # the NCCL all-reduce stays outside the graphs (eager, same stream): graph 1 = forward + backward,
-        # graph 2 = Adam + re-pack.  Single GPU: one graph.
-        g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            self.forward_backward(use_mask=use_mask)
-            if self.world == 1:
-                self.optimizer_step(lr, reduce=False)
-        g2 = None
-        if self.world > 1:
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                self.optimizer_step(lr, reduce=False)
-        self._graph = (g1, g2)
-        self._graph_key = (bool(use_mask), lr)
-        return self._graph
+    @staticmethod
+    def _graph_key_of(use_mask, lr, lr_groups):
+        groups = None if lr_groups is None else tuple(sorted(lr_groups.items(), key=lambda kv: kv[0]))
+        return (bool(use_mask), None if lr is None else float(lr), groups)
 
-    def run_resident(self, use_mask=False):
-        """One step on the batch already in the device buffers (graph replay when captured)."""
-        g = getattr(self, "_graph", None)
-        if g is not None and self._graph_key == (bool(use_mask), None):
-            g[0].replay()
-            if g[1] is not None:
-                self.reduce_gradients()
-                g[1].replay()
+    def capture(self, use_mask=False, lr=None, lr_groups=None):
+        """Captures forward + backward + gradient all-reduce + Adam + operand re-pack into ONE CUDA graph (every
+        kernel argument is a pointer to a fixed buffer; the step's inputs are read from the static device buffers
+        filled by load_batch; step counter and loss scale live on the device; NCCL collectives are captured like any
+        other stream work).  Graphs are kept per (use_mask, lr, lr_groups); run_resident() replays the matching one."""
+        P = self.params
+        state = (P.flat, P.exp_avg, P.exp_avg_sq, P.adam_state)
+        saved = [t.clone() for t in state]
+        # warm-up off the capture stream: kernel attributes, tensor-map cache, NCCL communicators
+        warm = torch.cuda.Stream(self.device)
+        warm.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(warm):
+            for _ in range(2):
+                self.forward_backward_reduced(use_mask=use_mask)
+                self.optimizer_step(lr, reduce=False, lr_groups=lr_groups)
+        torch.cuda.current_stream(self.device).wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        with torch.no_grad():
+            for dst, src in zip(state, saved):
+                dst.copy_(src)
+        self.repack()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward_backward_reduced(use_mask=use_mask)
+            self.optimizer_step(lr, reduce=False, lr_groups=lr_groups)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        self._graphs[self._graph_key_of(use_mask, lr, lr_groups)] = g
+        return g
+
+    def run_resident(self, use_mask=False, lr=None, lr_groups=None):
+        """One step on the batch already in the device buffers: replays the graph captured for exactly this
+        (use_mask, lr, lr_groups), else launches eagerly."""
+        g = getattr(self, "_graphs", {}).get(self._graph_key_of(use_mask, lr, lr_groups))
+        if g is not None:
+            self._sync_operands()
+            g.replay()
         else:
-            self.forward_backward(use_mask=use_mask)
-            self.optimizer_step()
+            self.forward_backward_reduced(use_mask=use_mask)
+            self.optimizer_step(lr, reduce=False, lr_groups=lr_groups)
+
+    def graph_step(self, model_input, gt, gamma=None, use_mask=False, lr=None, lr_groups=None):
+        """step() through a CUDA graph, capturing on first use of a (use_mask, lr, lr_groups) combination -- what
+        neucam_b200.training.train runs."""
+        self.load_batch(model_input, gt, gamma)
+        if self._graph_key_of(use_mask, lr, lr_groups) not in getattr(self, "_graphs", {}):
+            self.capture(use_mask, lr, lr_groups)
+        self.run_resident(use_mask, lr, lr_groups)
+        return self.losses()
 
     def step(self, model_input, gt, gamma=None, use_mask=False):
         self.load_batch(model_input, gt, gamma)

@@ -59,13 +59,26 @@ def test_step_matches_golden_reference_run():
                 tol = 1e-2 if i == 0 else 2e-2
                 assert e <= tol and e2 <= tol, (i, slot, k, e, e2)
         print(f"step {i}: img_loss {losses['img_loss']:.6f} (ref {ref['loss/img_loss']:.6f}); worst grad err {worst:.2e}")
+        before = {(slot, k): dict(models[slot].named_parameters())[k].detach().float().cpu().reshape(-1).clone()
+                  for slot, d in fx["params_digest"][i].items() for k in d}
         step.optimizer_step()
         torch.cuda.synchronize()
         for slot, d in fx["params_digest"][i].items():
             for k, dg in d.items():
                 mine = dict(models[slot].named_parameters())[k].detach().float().cpu().reshape(-1)
-                # Adam's first steps move every weight by ~lr regardless of gradient scale
-                assert (mine[dg["idx"]] - dg["val"]).abs().max() <= 2.5e-5, (i, slot, k)
+                idx = dg["idx"]
+                # (a) the UPDATE Adam applied (~lr = 1e-4 per weight in the first steps) against the reference's own
+                # update of the same entries: relative, so an error of the size of the step cannot hide.  Step 0
+                # starts from identical parameters and moments; later steps are free-running on both sides.
+                ref_prev = (fx["init_state"][slot][k].reshape(-1)[idx] if i == 0
+                            else fx["params_digest"][i - 1][slot][k]["val"])
+                d_ref = (dg["val"] - ref_prev).double()
+                d_mine = (mine[idx] - before[(slot, k)][idx]).double()
+                if d_ref.norm() > 0:
+                    e_upd = ((d_mine - d_ref).norm() / d_ref.norm()).item()
+                    assert e_upd <= (2e-2 if i == 0 else 1e-1), (i, slot, k, e_upd)
+                # (b) the parameters themselves: a fraction of one Adam step
+                assert (mine[idx] - dg["val"]).abs().max() <= (5e-6 if i == 0 else 2.5e-5), (i, slot, k)
 
 
 @pytest.mark.parametrize("name,gamma", [("mf", False), ("mfme_gamma", True)])
@@ -135,11 +148,10 @@ def test_cuda_graph_replay_equals_eager_steps():
         finals.append((losses, step.params.flat.clone(), step.params.adam_state.clone()))
     (l0, p0, s0), (l1, p1, s1) = finals
     assert s0[0].item() == 3.0 and s1[0].item() == 3.0
-    for a, b in zip(l0, l1):
-        assert a == pytest.approx(b, rel=1e-4)
-    # atomics make gradient summation order non-deterministic; Adam's early steps are sign-like, so compare loosely
-    assert (p0 - p1).abs().max().item() <= 2.5e-4
-    assert rel(p1, p0) <= 1e-4
+    # no float atomics anywhere (fixed-order reductions): a graph replay launches the same kernels on the same
+    # data as the eager path, so losses and parameters are BIT-identical
+    assert l0 == l1
+    assert torch.equal(p0, p1)
 
 
 def test_mask_weights_and_value_only_grad_loss():

@@ -4,7 +4,9 @@ import sys
 import os
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from neucam_b200 import ops
+from neucam_b200 import _lib, ops
+if os.environ.get("NEUCAM_CHAIN_DBG", "0") != "0":
+    _lib.use_debug_library()   # the experiment switches live in the debug build only
 
 def main():
     Q = int(sys.argv[1]) if len(sys.argv) > 1 else 382725
@@ -32,18 +34,18 @@ def main():
     dbs = [torch.zeros(512, device=dev) for _ in range(3)]
     dw4 = torch.zeros(3, 512, device=dev)
 
+    ws = ops.new_ws(ops.WS_WGRAD, device=dev)     # >= every other reduction workspace used below
     fns = {
         "fwd(train)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y, act16=act, phase16=cos),
         "fwd(infer)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y),
-        "bwd": lambda: ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, cos, scale, dz, dw0, db0, duv=duv),
-        "wgrad": lambda: ops.sine_mlp_wgrad(dz, act, scale, dws, dbs),
-        "head_wgrad": lambda: ops.sine_mlp_head_wgrad(act, dy, dw4),
+        "bwd": lambda: ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, cos, scale, dz, dw0, db0, duv=duv, ws=ws),
+        "wgrad": lambda: ops.sine_mlp_wgrad(dz, act, scale, dws, dbs, ws=ws),
+        "head_wgrad": lambda: ops.sine_mlp_head_wgrad(act, dy, dw4, ws=ws),
     }
     flops = {"fwd(train)": 2 * 788992, "fwd(infer)": 2 * 788992, "bwd": 2 * 788992, "wgrad": 2 * 3 * 512 * 512, "head_wgrad": 2 * 3 * 512}
     total = 0.0
     dbg = int(os.environ.get("NEUCAM_CHAIN_DBG", "0"))
     if dbg:
-        from neucam_b200 import _lib
         _lib.lib().neucam_debug_set_chain_flags(dbg)
         print("debug flags", dbg)
     for name, fn in fns.items():

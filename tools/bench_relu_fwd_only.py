@@ -3,6 +3,7 @@ import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from neucam_b200 import modules, _lib
+_lib.use_debug_library()   # diagnostics live in the debug build only
 Q = 165888
 net = modules.SimpleMLP(hidden_dim=256, num_layer=4, in_dim=3, out_dim=2, use_encoding=True, num_frequencies=3,
                         skip_layer=[4], nonlinear="tanh").cuda()

@@ -3,6 +3,7 @@ import ctypes, math, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neucam_b200 import ops, _lib
+_lib.use_debug_library()   # diagnostics live in the debug build only
 
 def run(bwd, Q=148 * 128 * 4):
     dev = "cuda"

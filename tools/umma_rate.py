@@ -2,6 +2,7 @@ import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neucam_b200 import _lib
+_lib.use_debug_library()   # diagnostics live in the debug build only
 lib = _lib.lib()
 for grid, ovh in ((148, 0), (148, 1), (148, 2), (148, 3)):
     for two, N in ((0, 256), (1, 256)):

@@ -2,6 +2,7 @@ import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neucam_b200 import _lib
+_lib.use_debug_library()   # diagnostics live in the debug build only
 lib = _lib.lib()
 grid = 148
 for name, extra in (("A in smem", 0), ("A in tmem", 1 << 10)):
