@@ -44,7 +44,7 @@ int neucam_check_device(void);
 
 /* Bytes of reduction workspace an entry point needs on the current device.  kind = NEUCAM_WS_*;
  * n / aux: SINE_BWD, WGRAD (both wgrad entry points), HEAD_WGRAD (both): unused; PSF_CRF and BLUR_BWD: n = B pixels,
- * aux = N frames; RIGIDITY: n = B; BLEND: n = K * B. */
+ * aux = N frames; RIGIDITY: n = B; BLEND: n = K * B; TM: n = M samples. */
 #define NEUCAM_WS_SINE_BWD 0
 #define NEUCAM_WS_WGRAD 1
 #define NEUCAM_WS_HEAD_WGRAD 2
@@ -221,6 +221,18 @@ int neucam_layer_blend_fwd(const float* back, const float* front, const float* a
 int neucam_layer_blend_bwd(const float* dout, const float* back, const float* front, const float* alpha,
                            const float* e2, const float* g_reg, int K, int B, float c1, float c2, float c3,
                            float* d_back, float* d_front, float* d_alpha, void* stream);
+
+/* neucam_tm_fwd / neucam_tm_bwd: TonemapNet.forward (modules.py:219-247, noise=None) on its own, for the callers around
+ *   the step that evaluate the CRF alone -- utils.warm_tm (utils.py:265-282) and full-frame rendering
+ *   (utils.write_video_summary, render_video.py).  x [M,3] log radiance, expo [M] exposure in stops; ldr [M,3] =
+ *   tanh(CRF(x + ln2 * expo)).  The backward takes dldr [M,3], writes dx [M,3] and (optionally) dexpo [M], and
+ *   ACCUMULATES the 12 parameter gradients (workspace: M/128 records of 1156 floats = NEUCAM_WS_TM with n = M). */
+#define NEUCAM_WS_TM 7
+int neucam_tm_fwd(const float* const* tm_params, int tm_width, const float* x, const float* expo, int64_t M,
+                  float* ldr, void* stream);
+int neucam_tm_bwd(const float* const* tm_params, int tm_width, const float* x, const float* expo, const float* dldr,
+                  int64_t M, float* dx, float* dexpo, float* const* tm_grads, void* ws, int64_t ws_bytes,
+                  void* stream);
 
 /* neucam_tm_min_slope: the VALUE-ONLY CRF gradient regulariser of training.py:248-252 (TonemapNet.forward with
  *   output_grads=True, modules.py:249-251): min over M points of d mean(ldr)/d lnx for rad [M,3], expo [M,1].

@@ -47,7 +47,6 @@ namespace {
 
 constexpr int HID = 512;
 constexpr int TILE_M = 128;
-constexpr int NSTAGE = 4;
 constexpr uint32_t STAGE_BYTES = 128 * 64 * 2;     // weight chunk: 128 output rows x 64 k
 constexpr uint32_t A_BLOCK_BYTES = TILE_M * 128;   // one 64-column k-block of the operand tile
 constexpr uint32_t A_BYTES = 8 * A_BLOCK_BYTES;    // 128 x 512 fp16
@@ -57,33 +56,36 @@ constexpr int FIRST_EPI_WARP = 0;
 // producer / MMA-issuer / relay / store threads must never queue behind the 16 busy epilogue warps (measured:
 // with control warps at ids 0..3 every mbarrier poll of the MMA thread took 100-900 ns).
 constexpr int WARP_PRODUCER = 16, WARP_MMA = 17, WARP_ALLOC = 18, WARP_STORE = 19;
-#ifndef CHAIN_SETMAXNREG
-#define CHAIN_SETMAXNREG 0
-#endif
-#define CHAIN_REGS_CONTROL 40
-#define CHAIN_REGS_EPILOGUE 112
 constexpr int PAIR = 2;                            // CTAs per cluster (tcgen05 cta_group::2)
 constexpr uint16_t PAIR_MASK = 0x3;
 
-constexpr uint32_t OFF_A = 0;
-constexpr uint32_t OFF_W = OFF_A + A_BYTES;
-constexpr uint32_t OFF_P0 = OFF_W + NSTAGE * STAGE_BYTES;   // float4[512]: 30*W0[j,0], 30*W0[j,1], 30*b0[j], 0
-constexpr uint32_t OFF_W4 = OFF_P0 + 512 * 16;              // float4[512]: W4[0..3][j] (missing rows = 0)
-constexpr uint32_t OFF_B30 = OFF_W4 + 512 * 16;             // float[3][512]: 30*b_l                    (forward)
-constexpr uint32_t OFF_XCH = OFF_B30 + 3 * 512 * 4;         // float4[4][128]: per-column-quarter partial sums
-constexpr uint32_t OFF_UV = OFF_XCH + 4 * 128 * 16;         // float2[128]: the tile's input coordinates
-constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;              // 52 mbarriers
-constexpr uint32_t OFF_TMEM = OFF_BAR + 448;
-constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
-constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;           // + alignment slack
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+// Shared-memory layout.  The weight ring is what bounds the tensor pipe inside a layer: with a stage round trip
+// (commit -> empty -> producer -> TMA -> full -> issuer) of ~1.3 us and 260 ns of MMAs per stage, bytes in flight =
+// ring bytes decide the MMA rate (in-kernel timeline, profiles/r2_findings.md).  The backward needs neither the head
+// weights nor the hidden biases in shared memory, so it affords a fifth stage.
+template <bool BWD>
+struct Lay {
+  static constexpr int NSTAGE = BWD ? 5 : 4;
+  static constexpr uint32_t OFF_A = 0;
+  static constexpr uint32_t OFF_W = OFF_A + A_BYTES;
+  static constexpr uint32_t OFF_P0 = OFF_W + NSTAGE * STAGE_BYTES;    // float4[512]: 30*W0[j,0], 30*W0[j,1], 30*b0[j], 0
+  static constexpr uint32_t OFF_W4 = OFF_P0 + 512 * 16;               // float4[512]: W4[0..3][j] (missing rows = 0)  (forward)
+  static constexpr uint32_t OFF_B30 = OFF_W4 + (BWD ? 0 : 512 * 16);  // float[3][512]: 30*b_l                       (forward)
+  static constexpr uint32_t OFF_XCH = OFF_B30 + (BWD ? 0 : 3 * 512 * 4);   // float4[4][128]: per-column-quarter partial sums
+  static constexpr uint32_t OFF_UV = OFF_XCH + 4 * 128 * 16;          // float2[128]: the tile's input coordinates
+  static constexpr uint32_t OFF_BAR = OFF_UV + 128 * 8;               // 62 mbarriers
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + 512;
+  static constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
+  static constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;            // + alignment slack
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+};
 
-// mbarrier slots
-constexpr uint32_t BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_KFREE = 12, BAR_AREADY = 20, BAR_STORED = 28,
-                   BAR_PEER = 36,   // leader only: the peer CTA's operand k-block kb is ready
-                   BAR_AOUT = 44,   // k-block kb of the tile's LAST output (a4 / dz0) is written (store warp only)
-                   BAR_DYR = 52,    // backward: the tile's scaled output-gradient operand (dy, K = 16) is written
-                   BAR_PEERDY = 53; // leader only: same, for the peer CTA
+// mbarrier slots (8 reserved per ring barrier kind)
+constexpr uint32_t BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_ACC = 16, BAR_KFREE = 20, BAR_AREADY = 28, BAR_STORED = 36,
+                   BAR_PEER = 44,   // leader only: the peer CTA's operand k-block kb is ready
+                   BAR_AOUT = 52,   // k-block kb of the tile's LAST output (a4 / dz0) is written (store warp only)
+                   BAR_DYR = 60,    // backward: the tile's scaled output-gradient operand (dy, K = 16) is written
+                   BAR_PEERDY = 61; // leader only: same, for the peer CTA
 // a_ready / peer count the MMA-visible operand events only (prologue + first two layers = 3 per tile): every
 // such event needs MMA progress on the previous one, so no waiter can be lapped by a full barrier phase.
 
@@ -179,9 +181,83 @@ __device__ __forceinline__ void write_a_half_row(uint32_t a_base, uint32_t kb, u
     st_shared_v4(blk + sw128_offset(row, qb + q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
-template <bool BWD>
+// ---- per-chunk epilogue math ----------------------------------------------------------------------------------
+// One thread turns its 32 accumulator columns of one row into 16 packed fp16 pairs of the next operand.  The layer-
+// dependent variants are TEMPLATES selected by a warp-uniform branch around the whole chunk: written as conditions
+// inside one unrolled loop, the compiler if-converts them and every element pays for both sides (measured in SASS:
+// 2 MUFU + 5 FFMA + 4 FMUL per element in the backward instead of 1 + 1 + 2).
+
+// forward: a = sin(30 z + 30 b); STORE: also the 16-bit phase of the angle (for the backward's cos); HEAD: accumulate
+// this thread's share of the 512 -> out_dim output layer.
+template <bool STORE, bool HEAD>
+__device__ __forceinline__ void fwd_chunk_math(const uint32_t (&r)[32], uint32_t (&w)[16], const float* __restrict__ b30c,
+                                               const float4* __restrict__ w4c, uint16_t* __restrict__ ph_dst,
+                                               bool ph_ok, float (&acc)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t pw[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int i = q * 8 + jj * 2;
+      const float t0 = fmaf(__uint_as_float(r[i]), 30.f, b30c[i]), t1 = fmaf(__uint_as_float(r[i + 1]), 30.f, b30c[i + 1]);
+      const float h0 = __sinf(t0), h1 = __sinf(t1);
+      w[q * 4 + jj] = pack_h2(h0, h1);
+      if (STORE) {
+        // phase in revolutions * 65536, rounded on the FMA pipe (1.5 * 2^23 magic number): one FFMA from the angle
+        // the sine already needed
+        const uint32_t p0 = __float_as_uint(fmaf(t0, PH_PER_RAD, MAGIC));
+        const uint32_t p1 = __float_as_uint(fmaf(t1, PH_PER_RAD, MAGIC));
+        pw[jj] = __byte_perm(p0, p1, 0x5410);
+      }
+      if (HEAD) {
+        const float4 wa = w4c[i], wb = w4c[i + 1];
+        acc[0] = fmaf(h0, wa.x, fmaf(h1, wb.x, acc[0]));
+        acc[1] = fmaf(h0, wa.y, fmaf(h1, wb.y, acc[1]));
+        acc[2] = fmaf(h0, wa.z, fmaf(h1, wb.z, acc[2]));
+        acc[3] = fmaf(h0, wa.w, fmaf(h1, wb.w, acc[3]));
+      }
+    }
+    if (STORE && ph_ok)
+      *reinterpret_cast<uint4*>(ph_dst + (size_t)q * (TILE_M * 8)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+  }
+}
+
+// backward: dz = (dh W^T-accumulator) * cos(angle) (the operand W^T carries the factor 30).  !LAST: the angle comes from
+// the stored 16-bit phase; LAST (layer 0): it is recomputed from the input coordinates, and the thread accumulates its
+// share of the coordinate gradient duv = dz0 W0.
+template <bool LAST>
+__device__ __forceinline__ void bwd_chunk_math(const uint32_t (&r)[32], uint32_t (&w)[16], const uint4 (&pv)[4],
+                                               const float4* __restrict__ p0c, float u, float v, float (&acc)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int i = q * 8 + jj * 2;
+      float z0, z1;
+      if (!LAST) {
+        z0 = __uint_as_float(r[i]) * cos_of_phase(pw[jj] & 0xFFFFu);
+        z1 = __uint_as_float(r[i + 1]) * cos_of_phase(pw[jj] >> 16);
+      } else {
+        const float4 q0 = p0c[i], q1 = p0c[i + 1];
+        z0 = __uint_as_float(r[i]) * __cosf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
+        z1 = __uint_as_float(r[i + 1]) * __cosf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
+        acc[0] = fmaf(z0, q0.x, fmaf(z1, q1.x, acc[0]));
+        acc[1] = fmaf(z0, q0.y, fmaf(z1, q1.y, acc[1]));
+      }
+      w[q * 4 + jj] = pack_h2_sat(z0, z1);
+    }
+  }
+}
+
+// BWD: backward chain; STORE (forward only): write a1..a4 and the phases for a later backward (training) or not (inference)
+template <bool BWD, bool STORE>
 __global__ void __cluster_dims__(PAIR, 1, 1) __launch_bounds__(NTHREADS, 1)
 sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+  using L = Lay<BWD>;
+  constexpr int NSTAGE = L::NSTAGE;
+  constexpr uint32_t OFF_A = L::OFF_A, OFF_W = L::OFF_W, OFF_P0 = L::OFF_P0, OFF_W4 = L::OFF_W4, OFF_B30 = L::OFF_B30,
+                     OFF_XCH = L::OFF_XCH, OFF_UV = L::OFF_UV, OFF_BAR = L::OFF_BAR, OFF_TMEM = L::OFF_TMEM;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -215,8 +291,8 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     for (uint32_t s = 0; s < NSTAGE; ++s) {
       mbar_init(bar(BAR_WFULL + s), 1);
       mbar_init(bar(BAR_WEMPTY + s), 1);
-      mbar_init(bar(BAR_ACC + s), 1);
     }
+    for (uint32_t c = 0; c < 4; ++c) mbar_init(bar(BAR_ACC + c), 1);
     for (uint32_t k = 0; k < 8; ++k) {
       mbar_init(bar(BAR_KFREE + k), 1);
       mbar_init(bar(BAR_AREADY + k), 256);
@@ -238,24 +314,13 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / commit / TMA signal
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const bool do_store_any = BWD || p.store_act;
+  const bool do_store_any = BWD || STORE;
   const uint32_t crank = cluster_ctarank();
   const bool leader = (crank == 0);
   // a pair walks tiles (2j, 2j+1) + it * gridDim.x together; it runs while its leader's tile exists.  When
   // only the peer's tile is past the end it runs a phantom tile (all rows invalid, no global traffic).
   const int lead0 = (int)(blockIdx.x & ~1u);
 
-  // Register re-partitioning: 640 threads cap the launch allocation at 96 registers per thread, which the epilogue
-  // warps overflow (spills into a tiny L1 next to 227 KB of shared memory) while the four single-lane control warps
-  // need a fraction of it.  The control warpgroup (warps 16..19) hands registers back, the four epilogue warpgroups
-  // take them: 4 x 128 x (96 - 40) freed + 4096 unallocated >= 16 x 32 x (112 - 96).
-#if CHAIN_SETMAXNREG
-  if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS_CONTROL));
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CHAIN_REGS_EPILOGUE));
-  }
-#endif
   if (warp == WARP_PRODUCER) {
     // ===================== TMA weight producer =====================
     // (the whole warp runs the loop and the waits; only the issue instructions are predicated to lane 0, so the
@@ -420,7 +485,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int tile = lt + (int)crank;
         const bool tile_ok = tile < p.ntiles;
         for (int e4 = 0; e4 < 4; ++e4) {
-          const bool do_store = tile_ok && (BWD ? (e4 < 3) : (p.store_act != 0));
+          const bool do_store = tile_ok && (BWD ? (e4 < 3) : STORE);
           for (int kb = 0; kb < 8; ++kb) {
             if (e4 < 3) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
             else        mbar_wait(bar(BAR_AOUT + kb), tcount & 1);
@@ -480,7 +545,6 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         v = t.y;
       }
       const size_t ph_row_off = ((size_t)tile * 64 * TILE_M + row) * 8;   // + chunk8 * 128 * 8
-      const bool store_ph = tile_ok && p.store_act != 0;
 
       // ---------------- prologue ----------------
       // forward: first operand tile a1 = sin(30 (uv W0^T + b0)) (SIMT, K = 2)
@@ -527,7 +591,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       // ---------------- tensor-core layers (backward: g = -1 is the head dgrad) ----------------
 #pragma unroll 1
       for (int g = BWD ? -1 : 0; g < 3; ++g) {
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // head (fwd) / duv (bwd) partials
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};   // head (fwd) / duv (bwd) partials
         const float* b30 = s_b30 + (g < 0 ? 0 : g) * HID;
         uint16_t* ph_out = p.phase + (size_t)(g < 0 ? 0 : g) * ph_layer_stride + ph_row_off;
         const uint16_t* ph_in = p.phase + (size_t)(g < 2 ? 1 - g : 0) * ph_layer_stride + ph_row_off;
@@ -565,60 +629,12 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) w[i] = r[2 * i];
             } else if (!BWD) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint32_t pw[4];
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  const int i = q * 8 + jj * 2;
-                  const int j = col + i;
-                  const float z0 = __uint_as_float(r[i]), z1 = __uint_as_float(r[i + 1]);
-                  const float t0 = fmaf(z0, 30.f, b30[j]), t1 = fmaf(z1, 30.f, b30[j + 1]);
-                  const float h0 = __sinf(t0), h1 = __sinf(t1);
-                  w[q * 4 + jj] = pack_h2(h0, h1);
-                  if (store_ph) {
-                    // phase in revolutions * 65536, rounded on the FMA pipe (1.5 * 2^23 magic number): one FFMA from
-                    // the angle the sine already needed
-                    const uint32_t p0 = __float_as_uint(fmaf(t0, PH_PER_RAD, MAGIC));
-                    const uint32_t p1 = __float_as_uint(fmaf(t1, PH_PER_RAD, MAGIC));
-                    pw[jj] = __byte_perm(p0, p1, 0x5410);
-                  }
-                  if (g == 2) {
-                    const float4 wa = s_w4[j], wb = s_w4[j + 1];
-                    acc0 = fmaf(h0, wa.x, fmaf(h1, wb.x, acc0));
-                    acc1 = fmaf(h0, wa.y, fmaf(h1, wb.y, acc1));
-                    acc2 = fmaf(h0, wa.z, fmaf(h1, wb.z, acc2));
-                    acc3 = fmaf(h0, wa.w, fmaf(h1, wb.w, acc3));
-                  }
-                }
-                if (store_ph)
-                  *reinterpret_cast<uint4*>(ph_out + (size_t)((col >> 3) + q) * (TILE_M * 8)) =
-                      make_uint4(pw[0], pw[1], pw[2], pw[3]);
-              }
+              uint16_t* ph_dst = ph_out + (size_t)(col >> 3) * (TILE_M * 8);
+              if (g == 2) fwd_chunk_math<STORE, true>(r, w, b30 + col, s_w4 + col, ph_dst, tile_ok, acc);
+              else        fwd_chunk_math<STORE, false>(r, w, b30 + col, s_w4 + col, ph_dst, tile_ok, acc);
             } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  const int i = q * 8 + jj * 2;
-                  const int j = col + i;
-                  float c0v, c1v;
-                  if (g < 2) {
-                    c0v = cos_of_phase(pw[jj] & 0xFFFFu);
-                    c1v = cos_of_phase(pw[jj] >> 16);
-                  } else {
-                    const float4 q0 = s_p0[j], q1 = s_p0[j + 1];
-                    c0v = __cosf(fmaf(u, q0.x, fmaf(v, q0.y, q0.z)));
-                    c1v = __cosf(fmaf(u, q1.x, fmaf(v, q1.y, q1.z)));
-                    const float z0 = __uint_as_float(r[i]) * c0v;   // the operand W^T carries the factor 30
-                    const float z1 = __uint_as_float(r[i + 1]) * c1v;
-                    acc0 = fmaf(z0, q0.x, fmaf(z1, q1.x, acc0));
-                    acc1 = fmaf(z0, q0.y, fmaf(z1, q1.y, acc1));
-                  }
-                  w[q * 4 + jj] = pack_h2_sat(__uint_as_float(r[i]) * c0v, __uint_as_float(r[i + 1]) * c1v);
-                }
-              }
+              if (g < 2) bwd_chunk_math<false>(r, w, pv, s_p0 + col, u, v, acc);
+              else       bwd_chunk_math<true>(r, w, pv, s_p0 + col, u, v, acc);
             }
             trace_stamp(tr, role, tile_i, g, step, 2);
             if (park) {
@@ -648,7 +664,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 
         if (g == 2) {
           // combine the 4 column quarters of every row: head output (forward) / coordinate gradient (backward)
-          s_xch[sub * TILE_M + row] = make_float4(acc0, acc1, acc2, acc3);
+          s_xch[sub * TILE_M + row] = make_float4(acc[0], acc[1], acc[2], acc[3]);
           epi_bar_sync();
           if (sub == 0) {
             float4 o = s_xch[row];
@@ -739,11 +755,12 @@ int chain_grid(int ntiles) {
   return (grid + PAIR - 1) / PAIR * PAIR;   // whole pairs; an odd tile count gives one pair a phantom tile
 }
 
-template <bool BWD>
+template <bool BWD, bool STORE>
 int launch(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
-  int rc = nchost::ensure_dyn_smem((const void*)sine_chain_kernel<BWD>, (int)SMEM_BYTES);
+  constexpr uint32_t SMEM_BYTES = Lay<BWD>::SMEM_BYTES;
+  int rc = nchost::ensure_dyn_smem((const void*)sine_chain_kernel<BWD, STORE>, (int)SMEM_BYTES);
   if (rc) return rc;
-  sine_chain_kernel<BWD><<<chain_grid(p.ntiles), NTHREADS, SMEM_BYTES, stream>>>(maps, p);
+  sine_chain_kernel<BWD, STORE><<<chain_grid(p.ntiles), NTHREADS, SMEM_BYTES, stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
   return 0;
@@ -790,7 +807,8 @@ extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, 
   for (int i = 0; i < 4; ++i) act[i] = act16 ? (void*)((__half*)act16 + (size_t)i * Q * HID) : nullptr;
   int rc = build_maps(&maps, w_hid16, act, Q, p.store_act);
   if (rc) return rc;
-  return launch<false>(maps, p, (cudaStream_t)stream);
+  return p.store_act ? launch<false, true>(maps, p, (cudaStream_t)stream)
+                     : launch<false, false>(maps, p, (cudaStream_t)stream);
 }
 
 extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float* b0,
@@ -821,7 +839,7 @@ extern "C" int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, 
   act[3] = act[2];
   int rc = build_maps(&maps, wT_hid16, act, Q, true, w4T16);
   if (rc) return rc;
-  rc = launch<true>(maps, p, (cudaStream_t)stream);
+  rc = launch<true, true>(maps, p, (cudaStream_t)stream);
   if (rc) return rc;
   // dW0 += sum over CTAs (in CTA order) of their records / loss scale; same for db0
   nchost::ReduceSegs segs{};
