@@ -485,7 +485,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int tile = lt + (int)crank;
         const bool tile_ok = tile < p.ntiles;
         for (int e4 = 0; e4 < 4; ++e4) {
-          const bool do_store = tile_ok && (BWD ? (e4 < 3) : STORE);
+          const bool do_store = tile_ok && (BWD ? (e4 < 3) : STORE) && !CHAIN_DBG(16);
           for (int kb = 0; kb < 8; ++kb) {
             if (e4 < 3) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
             else        mbar_wait(bar(BAR_AOUT + kb), tcount & 1);
@@ -616,7 +616,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               const uint16_t* src = ph_in + (size_t)(col >> 3) * (TILE_M * 8);
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                pv[q] = tile_ok ? *reinterpret_cast<const uint4*>(src + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
+                pv[q] = (tile_ok && !CHAIN_DBG(8)) ? *reinterpret_cast<const uint4*>(src + (size_t)q * (TILE_M * 8)) : make_uint4(0, 0, 0, 0);
             }
             mbar_wait(bar(BAR_ACC + c), lp);
             tc_fence_after_sync();
