@@ -226,6 +226,33 @@ class FCBlock(MetaModule):
         return y.reshape(*lead, y.shape[-1])
 
 
+def _fcblock_forward_with_activations(self, coords, params=None, retain_grad=False):
+    """FCBlock.forward_with_activations (modules.py:97-117): the model output AND every sublayer's output, as an
+    OrderedDict keyed '<sublayer class>_<layer index>' after 'input'.  A DIAGNOSTIC entry point (its one caller in the
+    reference is the activation-histogram summary, utils.py:46): it evaluates layer by layer with plain torch ops in
+    fp32 on whatever device the input lives on, i.e. it shows what the reference would show -- not the fused kernels'
+    fp16 operand tiles -- and is not part of the training path."""
+    if params is None:
+        params = OrderedDict(self.named_parameters())
+    activations = OrderedDict()
+    x = coords.clone().detach().requires_grad_(True)
+    activations["input"] = x
+    for i, layer in enumerate(self.net):
+        subdict = get_subdict(params, "net.%d" % i)
+        for j, sublayer in enumerate(layer):
+            if isinstance(sublayer, BatchLinear):
+                x = sublayer(x, params=get_subdict(subdict, "%d" % j))
+            else:
+                x = sublayer(x)
+            if retain_grad:
+                x.retain_grad()
+            activations["_".join((str(sublayer.__class__), "%d" % i))] = x
+    return activations
+
+
+FCBlock.forward_with_activations = _fcblock_forward_with_activations
+
+
 class SingleBVPNet(MetaModule):
     """The scene ("atlas") network: coords -> log radiance."""
 
@@ -248,6 +275,12 @@ class SingleBVPNet(MetaModule):
             coords_org = coords_org.clone().detach().requires_grad_(True)
         output = self.net(coords_org, get_subdict(params, "net"))
         return {"model_in": coords_org, "model_out": output}
+
+    def forward_with_activations(self, model_input):
+        """modules.py:477-481: {'model_in', 'model_out': (key, tensor) of the last sublayer, 'activations'}."""
+        coords = model_input["coords"].clone().detach().requires_grad_(True)
+        activations = self.net.forward_with_activations(coords)
+        return {"model_in": coords, "model_out": activations.popitem(), "activations": activations}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,6 +380,25 @@ class SimpleMLP(nn.Module):
         raise Exception("Unknown activation functions.", kind)
 
 
+class _TonemapFunction(torch.autograd.Function):
+    """TonemapNet.forward through the standalone CRF kernels (csrc/tonemap.cu): warm-up and rendering callers."""
+
+    @staticmethod
+    def forward(ctx, x, expo, *params):
+        ps = [p.contiguous() for p in params]
+        xc, ec = x.contiguous().float(), expo.reshape(-1).contiguous().float()
+        ctx.save_for_backward(xc, ec, *ps)
+        ctx.expo_shape = expo.shape
+        return ops.tm_fwd(ps, xc, ec)
+
+    @staticmethod
+    def backward(ctx, dldr):
+        xc, ec, *ps = ctx.saved_tensors
+        grads = [torch.zeros_like(p) for p in ps]
+        dx, dexpo = ops.tm_bwd(ps, xc, ec, dldr.contiguous().float(), grads, want_dexpo=ctx.needs_input_grad[1])
+        return (dx, dexpo.view(ctx.expo_shape) if dexpo is not None else None, *grads)
+
+
 class TonemapNet(nn.Module):
     """Per-channel 1 -> W -> 1 ReLU MLP camera response function on log exposure."""
 
@@ -359,6 +411,10 @@ class TonemapNet(nn.Module):
     def forward(self, x, input_exps, noise=None, output_grads=False):
         if noise is not None:
             raise NotImplementedError("the noise branch (opt.denoise) is not used by any shipped config")
+        if x.is_cuda and not output_grads and self.layers_r[0].out_features == ops.TM_WIDTH and x.dim() == 2:
+            # CUDA: the CRF kernels (csrc/tonemap.cu); exposure [M,1] or [M]
+            return _TonemapFunction.apply(x, input_exps.expand(x.shape[0], 1) if input_exps.dim() == 2 else input_exps,
+                                          *self.parameters())
         lnx = x + math.log(2.0) * input_exps
         ldr = torch.cat([self.layers_r(lnx[:, 0:1]), self.layers_g(lnx[:, 1:2]), self.layers_b(lnx[:, 2:3])], -1)
         ldr = torch.tanh(ldr)

@@ -22,7 +22,7 @@ def num_tiles(Q):
 
 # reduction workspaces (include/neucam_b200.h: NEUCAM_WS_*): every cross-block reduction writes per-block partial
 # records there and sums them in block order -- no float atomics, bit-reproducible results
-WS_SINE_BWD, WS_WGRAD, WS_HEAD_WGRAD, WS_PSF_CRF, WS_BLUR_BWD, WS_RIGIDITY, WS_BLEND = range(7)
+WS_SINE_BWD, WS_WGRAD, WS_HEAD_WGRAD, WS_PSF_CRF, WS_BLUR_BWD, WS_RIGIDITY, WS_BLEND, WS_TM = range(8)
 
 
 def reduce_ws_bytes(kind, n=0, aux=0):
@@ -206,6 +206,30 @@ def psf_crf_loss(y, kout, coord_idx, exps, fixed_exps, gt, gamma_w, mask_w, tm_p
         _lib.ptr(db4), _lib.ptr(sums), _lib.ptr(absmax_bits), ctypes.c_float(SCALE_TARGET), _lib.ptr(scale_out), _lib.ptr(ldr_out),
         tm_width, *_ws_args(ws), _lib.cur_stream())
     _lib.check(rc, "neucam_psf_crf_loss")
+
+
+def tm_fwd(tm_params, x, expo):
+    """TonemapNet.forward (modules.py:219-247, noise=None): x [M,3] log radiance, expo [M] stops -> ldr [M,3]."""
+    _chk_cuda(x, expo, *tm_params)
+    ldr = torch.empty_like(x)
+    rc = _lib.lib().neucam_tm_fwd(_ptr_array(tm_params), check_tm_shapes(tm_params), _lib.ptr(x), _lib.ptr(expo),
+                                  ctypes.c_int64(x.shape[0]), _lib.ptr(ldr), _lib.cur_stream())
+    _lib.check(rc, "neucam_tm_fwd")
+    return ldr
+
+
+def tm_bwd(tm_params, x, expo, dldr, tm_grads, want_dexpo=True):
+    """Backward of tm_fwd: returns (dx [M,3], dexpo [M] or None) and ACCUMULATES the 12 parameter gradients."""
+    _chk_cuda(x, expo, dldr, *tm_params, *tm_grads)
+    M = x.shape[0]
+    dx = torch.empty_like(x)
+    dexpo = torch.empty_like(expo) if want_dexpo else None
+    ws = new_ws(WS_TM, M, device=x.device)
+    rc = _lib.lib().neucam_tm_bwd(_ptr_array(tm_params), check_tm_shapes(tm_params), _lib.ptr(x), _lib.ptr(expo),
+                                  _lib.ptr(dldr), ctypes.c_int64(M), _lib.ptr(dx), _lib.ptr(dexpo),
+                                  _ptr_array(tm_grads), *_ws_args(ws), _lib.cur_stream())
+    _lib.check(rc, "neucam_tm_bwd")
+    return dx, dexpo
 
 
 def adam_tick(state, beta1=0.9, beta2=0.999):

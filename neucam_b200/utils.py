@@ -7,7 +7,14 @@
                             render_video.py:172-261 with the blur model disabled: LDR = tm(atlas_b(y,x), exp[f]),
                             all-in-focus HDR = exp(atlas_b(y,x)) at the un-shifted centre sample (utils.py:164).
   psnr                    : 10 log10(1 / mse) on [0,1] images (utils.py:198).
+  warm_tm / warm_mapping  : the pre-training loops train_video.py:126-142 runs before the main loop (utils.py:265-334):
+  / warm_alpha              CRF towards a fixed gamma curve, uv-mapping networks towards the (scaled) identity, alpha
+                            network towards a given mask.  Same objectives, sample counts, learning rates and CPU RNG
+                            consumption as the reference, so a seeded run reproduces the reference's warm start; the
+                            network forward / backward runs on this package's kernels (tonemap.cu, relu_chain.cu) and
+                            the optimizer is the fused flat Adam (adam.cu).
 """
+import numpy as np
 import torch
 
 from . import harness
@@ -39,7 +46,11 @@ def save_model(models, path):
 
 
 def load_model(models, path, map_location="cpu"):
-    """Loads a checkpoint written by save_model (or by the reference's utils.save_model) into `models`."""
+    """Loads a checkpoint written by save_model (or by the reference's utils.save_model) into `models`.
+
+    Parameters are written IN PLACE (they may be views of a training step's flat buffer).  A step that already exists
+    keeps fp16 tensor-core operand copies of the atlas weights; FusedTrainStep notices the write through the flat
+    buffer's version counter and re-packs before its next launch (step.repack() does it explicitly)."""
     ckpt = torch.load(path, map_location=map_location)
     for slot, key in CHECKPOINT_KEYS.items():
         m = models.get(slot)
@@ -52,6 +63,116 @@ def load_model(models, path, map_location="cpu"):
 
 
 psnr = harness.psnr
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# warm-ups (reference utils.py:262-334, called from experiment_scripts/train_video.py:126-142)
+# ------------------------------------------------------------------------------------------------------------------
+def tonemapSimple(x):
+    """The fixed target curve of warm_tm (utils.py:262-263)."""
+    return (torch.exp(x) / (torch.exp(x) + 1)) ** (1 / 2.2)
+
+
+class _WarmupAdam:
+    """torch.optim.Adam(model.parameters(), lr) as the reference constructs it for the warm-ups, executed by the fused
+    flat Adam kernel: the model's parameters are re-homed into one flat buffer (the training step re-homes them again
+    later, copying the warmed values)."""
+
+    def __init__(self, model, lr, device):
+        from .step import FlatParameters
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("neucam_b200 warm-ups run on the CUDA kernels only (there is no CPU path)")
+        model.to(dev)
+        self.P = FlatParameters({"atlas_b": model}, dev)    # slot name is irrelevant here: one model, one flat buffer
+        self.lr = lr
+
+    def zero_grad(self):
+        self.P.zero_grad()
+
+    def step(self):
+        from . import ops
+        ops.adam_tick(self.P.adam_state)
+        ops.adam_step(self.P.flat, self.P.grad, self.P.exp_avg, self.P.exp_avg_sq, self.P.adam_state, self.lr)
+
+
+def warm_tm(model, pretrain_iters=1000, device="cuda", verbose=False):
+    """utils.warm_tm (utils.py:265-282): fit the CRF to tonemapSimple on random radiance in [0,3] and exposure in
+    [-3,3] stops, 1024 samples per iteration, Adam lr 5e-4.  Random draws come from the CPU generator in the reference's
+    order (radiance, then exposure).  Returns the model; `history` of losses is attached as model.warm_history."""
+    opt = _WarmupAdam(model, 5e-4, device)
+    hist = []
+    for i in range(pretrain_iters):
+        opt.zero_grad()
+        rand_radiance = torch.rand(1024, 3).to(device) * 3
+        rand_exposure = torch.rand(1024, 1).to(device) * 6 - 3.0
+        gt_rgb = tonemapSimple(rand_radiance + rand_exposure)
+        rgb_l = model(rand_radiance, rand_exposure) / 2 + 0.5
+        loss = (rgb_l - gt_rgb).norm(dim=1).mean()
+        loss.backward()
+        opt.step()
+        hist.append(loss.detach())
+        if verbose:
+            print(f"step {i} pre-train loss: {loss.item()}")
+    model.warm_history = torch.stack(hist) if hist else torch.zeros(0)
+    return model
+
+
+def warm_mapping(model_mapping, shape, uv_mapping_scale=0.8, pretrain_iters=100, device="cuda", verbose=False):
+    """utils.warm_mapping (utils.py:284-305): pull the uv-mapping network towards uv = scale * (y, x) on 10000 random
+    pixels of every frame per iteration, Adam lr 1e-4 (one optimizer step per frame)."""
+    frames_num, img_h, img_w = shape
+    opt = _WarmupAdam(model_mapping, 1e-4, device)
+    hist = []
+    for i in range(pretrain_iters):
+        for f in range(frames_num):
+            i_s_int = torch.randint(img_h, (np.int64(10000), 1))
+            j_s_int = torch.randint(img_w, (np.int64(10000), 1))
+            i_s = i_s_int / (img_h - 1) * 2 - 1
+            j_s = j_s_int / (img_w - 1) * 2 - 1
+            t_s = (f / (frames_num - 1 + 1e-16) * 2 - 1) * torch.ones_like(i_s)
+            coords = torch.cat((t_s, i_s, j_s), dim=1).to(device)
+            uv_temp = model_mapping(coords)
+            opt.zero_grad()
+            loss = (coords[:, 1:] * uv_mapping_scale - uv_temp).norm(dim=1).mean()
+            loss.backward()
+            opt.step()
+            hist.append(loss.detach())
+            if verbose:
+                print(f"pre-train loss: {loss.item()}")
+    model_mapping.warm_history = torch.stack(hist) if hist else torch.zeros(0)
+    return model_mapping
+
+
+def warm_alpha(model_alpha, dataset, pretrain_iters=1000, device="cuda", verbose=False):
+    """utils.warm_alpha (utils.py:307-334): pull the alpha network towards the dataset's mask channel
+    (dataset.vid[..., 3:4], [N,H,W,1]) on 10000 random pixels of every frame per iteration, Adam lr 1e-4."""
+    frames_num, img_h, img_w = dataset.shape
+    opt = _WarmupAdam(model_alpha, 1e-4, device)
+    vid = dataset.vid
+    mask_gt = (torch.from_numpy(vid[..., 3:4]) if isinstance(vid, np.ndarray) else vid[..., 3:4]).to(device)
+    y = torch.linspace(-1, 1, img_h)
+    x = torch.linspace(-1, 1, img_w)
+    y, x = torch.meshgrid(y, x, indexing="ij")
+    xy_grid = torch.stack([y, x], -1).reshape(-1, 2).to(device)
+    hist = []
+    for i in range(pretrain_iters):
+        for f in range(frames_num):
+            idx = torch.randint(xy_grid.shape[0], (10000,))
+            i_s = xy_grid[idx, 0:1]
+            j_s = xy_grid[idx, 1:2]
+            t_s = (f / (frames_num - 1) * 2 - 1) * torch.ones_like(i_s)
+            coords = torch.cat((t_s, i_s, j_s), dim=1).to(device)
+            alpha_temp = model_alpha(coords)
+            opt.zero_grad()
+            loss = (mask_gt[f].reshape(-1, 1)[idx] - alpha_temp).norm(dim=1).mean()
+            loss.backward()
+            opt.step()
+            hist.append(loss.detach())
+            if verbose:
+                print(f"pre-train loss: {loss.item()}, max alpha: {torch.max(alpha_temp).item()}")
+    model_alpha.warm_history = torch.stack(hist) if hist else torch.zeros(0)
+    return model_alpha
 
 
 @torch.no_grad()

@@ -124,3 +124,49 @@ def test_mgrid_matches_reference_formula():
     if ref_shim.available():
         dataio = ref_shim.load("dataio")
         assert torch.equal(g, dataio.get_mgrid((2, 5, 7), dim=3).view(-1, 3))
+
+
+def test_forward_with_activations_matches_reference():
+    """FCBlock / SingleBVPNet.forward_with_activations (modules.py:97-117, 477-481): same entries, same values as the
+    reference's (its keys carry the class path, which differs by package name only)."""
+    torch.manual_seed(4)
+    net = modules.SingleBVPNet(type="sine", mode="mlp", hidden_features=32, num_hidden_layers=2, in_features=2,
+                               out_features=3, sidelength=(30, 45))
+    x = torch.rand(1, 17, 2) * 2 - 1
+    out = net.forward_with_activations({"coords": x})
+    acts = out["activations"]
+    assert list(acts)[0] == "input" and len(acts) == 1 + 2 * 3 + 1 - 1     # input + (linear, sine) x 3; last popped
+    key, y = out["model_out"]
+    assert "BatchLinear" in key and key.endswith("_3") and y.shape == (1, 17, 3)
+    # values: the explicit chain of modules.py:17-35
+    h = x
+    sd = net.state_dict()
+    for i in range(3):
+        z = h @ sd[f"net.net.{i}.0.weight"].t() + sd[f"net.net.{i}.0.bias"]
+        h = torch.sin(30 * z)
+        assert torch.allclose(acts[[k for k in acts if k.endswith(f"Sine'>_{i}")][0]], h, atol=1e-6)
+    assert torch.allclose(y, h @ sd["net.net.3.0.weight"].t() + sd["net.net.3.0.bias"], atol=1e-6)
+    # retain_grad keeps gradients of the intermediates
+    a = net.net.forward_with_activations(x, retain_grad=True)
+    list(a.values())[-1].sum().backward()
+    assert all(v.grad is not None for k, v in a.items() if k != "input")
+    if ref_shim.available():
+        ref_modules = ref_shim.load("modules")
+        torch.manual_seed(4)
+        ref = ref_modules.SingleBVPNet(type="sine", mode="mlp", hidden_features=32, num_hidden_layers=2, in_features=2,
+                                       out_features=3, sidelength=(30, 45))
+        ro = ref.forward_with_activations({"coords": x})
+        assert len(ro["activations"]) == len(acts)
+        for (ka, va), (kb, vb) in zip(acts.items(), ro["activations"].items()):
+            assert ka.split(".")[-1] == kb.split(".")[-1] and torch.allclose(va, vb, atol=1e-6), (ka, kb)
+        assert torch.allclose(ro["model_out"][1], y, atol=1e-6)
+
+
+def test_from_opt_refuses_options_outside_the_path():
+    import argparse
+    from neucam_b200.step import StepOptions
+    base = dict(patch_size=9, offset_size=5, lr=1e-4)
+    StepOptions.from_opt(argparse.Namespace(**base))
+    for flag in ("flow_loss", "mask_loss", "use_depth", "patch_sample", "denoise"):
+        with pytest.raises(NotImplementedError):
+            StepOptions.from_opt(argparse.Namespace(**base, **{flag: True}))
