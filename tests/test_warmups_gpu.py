@@ -21,16 +21,22 @@ def _digest_ok(model, dg):
         assert float(v.double().abs().sum()) == pytest.approx(dg[k][1], rel=1e-12), k
 
 
-def _compare(model, fx, loss_rel, p_max, p_mean):
+def _compare(model, fx, loss_rel, travel, p_mean):
+    """Losses per iteration, and the warmed parameters.  Adam's first steps move every weight by ~lr whatever the
+    gradient's size, so a weight whose gradient is ~0 can legitimately go the other way: the bound on single entries is
+    the distance Adam can travel (`travel` = 2 x steps x lr), while the bulk must agree to a fraction of one step:
+    mean <= p_mean, and all but 3e-3 of the entries within 2e-5 -- the share of weights whose gradient is smaller than
+    the kernels' ~1e-3 relative gradient error, i.e. whose Adam direction g / |g| is not determined at that accuracy
+    (measured: 8e-4 of layers.1.weight of the alpha network, whose sigmoid output starts flat)."""
     got = model.warm_history.cpu()
     assert got.shape == fx["losses"].shape
     assert torch.allclose(got, fx["losses"], rtol=loss_rel, atol=1e-7), (got[:3], fx["losses"][:3])
     for k, want in fx["final"].items():
         mine = model.state_dict()[k].detach().cpu()
         d = (mine - want).abs()
-        moved = (want - 0).abs().max().item()
-        assert d.max().item() <= p_max, (k, d.max().item(), moved)
+        assert d.max().item() <= travel, (k, d.max().item())
         assert d.mean().item() <= p_mean, (k, d.mean().item())
+        assert (d > 2e-5).float().mean().item() <= 3e-3, (k, (d > 2e-5).float().mean().item())
 
 
 def test_warm_tm_matches_reference_run():
@@ -41,7 +47,7 @@ def test_warm_tm_matches_reference_run():
     torch.manual_seed(fx["rng_seed"])
     nutils.warm_tm(tm, pretrain_iters=fx["iters"], device="cuda")
     # 25 Adam steps of 5e-4: the CRF kernel is fp32, differences are summation order only
-    _compare(tm, fx, loss_rel=1e-4, p_max=2e-5, p_mean=2e-6)
+    _compare(tm, fx, loss_rel=1e-4, travel=2e-5, p_mean=2e-6)
 
 
 def test_warm_mapping_matches_reference_run():
@@ -51,8 +57,7 @@ def test_warm_mapping_matches_reference_run():
     _digest_ok(net, fx["init_digest"])
     torch.manual_seed(fx["rng_seed"])
     nutils.warm_mapping(net, fx["shape"], uv_mapping_scale=fx["scale"], pretrain_iters=fx["iters"], device="cuda")
-    # 6 Adam steps of 1e-4 (sign-like in the first steps): a weight whose gradient is ~0 may move the other way
-    _compare(net, fx, loss_rel=1e-4, p_max=2.5e-4, p_mean=2e-6)
+    _compare(net, fx, loss_rel=1e-4, travel=2 * 6 * 1e-4, p_mean=2e-6)      # 2 iterations x 3 frames of lr 1e-4
 
 
 def test_warm_alpha_matches_reference_run():
@@ -63,7 +68,7 @@ def test_warm_alpha_matches_reference_run():
     ds = types.SimpleNamespace(shape=fx["shape"], vid=fx["vid"].numpy())
     torch.manual_seed(fx["rng_seed"])
     nutils.warm_alpha(net, ds, pretrain_iters=fx["iters"], device="cuda")
-    _compare(net, fx, loss_rel=1e-4, p_max=2.5e-4, p_mean=2e-6)
+    _compare(net, fx, loss_rel=1e-4, travel=2 * 6 * 1e-4, p_mean=2e-6)
 
 
 def test_tonemap_kernels_match_the_torch_module():
