@@ -67,17 +67,25 @@ def _record_call_scales(monkeypatch, models):
     return scales
 
 
+def _to_double(tree):
+    return {s: {k: v.double() if v.is_floating_point() else v for k, v in d.items()} for s, d in tree.items()}
+
+
 @pytest.mark.parametrize("kind", ["me_dynamic", "video_deblur", "video_hdr"])
 def test_losses_and_gradients_match_oracle(kind, monkeypatch):
     """Every loss and every parameter gradient of one step against the oracle.
 
-    Bound: 1e-2 relative (BASELINE.json north_star) -- for the uv / alpha networks relative to the summed size of
-    their per-call contributions, at 1e-3.  Reason (tools/relu_diag.py, profiles/r1_findings.md): a ReLU network's
-    gradient is discontinuous in its pre-activations; the split-fp16 forward reproduces them to ~1e-6, and in the
-    video_hdr case exactly ONE gate out of 537 600 (|z| = 1.5e-6 of the mean) lands on the other side than in the
-    fp32 reference.  That is 4e-4 of the call's gradient, and 2.6e-2 of the step's, because the rigidity loss
-    cancels the calls against each other 140-fold.  Any implementation that is not bit-identical in the forward
-    has this sensitivity; per call the parity is 1e-6 .. 6e-4 (tests/test_relu_mlp.py asserts <= 1e-2)."""
+    Bound: 1e-2 relative (BASELINE.json north_star), or twice the REFERENCE'S OWN arithmetic noise on that tensor where
+    that is larger: the oracle is evaluated in fp32 (the reference's arithmetic) and in fp64 on the same state and batch,
+    and e_self = |g32 - g64| / |g64| is what the reference itself is uncertain by.
+
+    One documented exception, with an explicit ceiling (tools/relu_diag.py, profiles/r1_findings.md): the uv networks
+    under the rigidity loss.  The loss differences the network between neighbouring pixels, so a weight gradient is the
+    residue of per-call contributions that cancel 25- to 140-fold, and a ReLU network's gradient is discontinuous in its
+    pre-activations: ONE gate of 537 600 (|z| = 1.5e-6 of the mean) landing on the other side than in fp32 is 4e-4 of
+    that call's gradient and 2.6e-2 of the cancelled sum.  Where the step gradient is less than a tenth of what was
+    summed (cancellation >= 10x), the error is bounded against the summed contributions (1e-3) and by a hard 5e-2
+    against the gradient itself; per call the parity is 1e-6 .. 6e-4 (tests/test_relu_mlp.py asserts <= 1e-2)."""
     B = 700   # ragged against the 128-row tiles of the chain, also after the x9 taps
     models, state, opts, batch, cfg = _setup(kind, B)
     step = LayeredTrainStep(models, SHAPES[kind], opts, device="cuda")
@@ -88,10 +96,13 @@ def test_losses_and_gradients_match_oracle(kind, monkeypatch):
     dev_state = {s: {k: v.cuda() for k, v in d.items()} for s, d in state.items()}
     dev_batch = {k: v.cuda() for k, v in batch.items()}
     ref_l, ref_g = orc.step_grads(dev_state, dev_batch, cfg, gamma.cuda() if gamma is not None else None)
+    # the reference's arithmetic noise: the same oracle in double precision
+    batch64 = {k: (v.double() if v.is_floating_point() else v) for k, v in dev_batch.items()}
+    _, g64 = orc.step_grads(_to_double(dev_state), batch64, cfg, gamma.cuda().double() if gamma is not None else None)
     for k, v in losses.items():
         assert v.item() == pytest.approx(ref_l[k].item(), rel=1e-3, abs=1e-7), k
     assert set(losses) == set(ref_l)
-    worst = ("", 0.0)
+    worst, worst_self, exceptions = ("", 0.0), ("", 0.0), []
     for slot, d in ref_g.items():
         for k, g_ref in d.items():
             g = dict(models[slot].named_parameters())[k].grad
@@ -99,16 +110,22 @@ def test_losses_and_gradients_match_oracle(kind, monkeypatch):
                 assert g.abs().max() == 0, (slot, k)
                 continue
             e = rel(g, g_ref)
-            if (slot, k) in scales:
-                e_call = (g.double() - g_ref.double()).norm().item() / scales[(slot, k)]
-                assert e_call < 1e-3, (slot, k, e_call, e)
-                assert e < 1e-2 or g_ref.double().norm().item() < 0.1 * scales[(slot, k)], (slot, k, e, e_call)
-                if e < 1e-2:
-                    worst = max(worst, (f"{slot}.{k}", e), key=lambda t: t[1])
+            e_self = rel(g_ref, g64[slot][k])
+            worst_self = max(worst_self, (f"{slot}.{k}", e_self), key=lambda t: t[1])
+            bound = max(1e-2, 2 * e_self)
+            if e <= bound:
+                worst = max(worst, (f"{slot}.{k}", e), key=lambda t: t[1])
                 continue
-            worst = max(worst, (f"{slot}.{k}", e), key=lambda t: t[1])
-            assert e < 1e-2, (slot, k, e)
-    print(kind, "worst gradient error", worst)
+            # the cancellation exception: uv / alpha networks only, and only where >= 10x of the summed per-call
+            # contributions cancelled
+            assert (slot, k) in scales, (slot, k, e, e_self)
+            cancelled = scales[(slot, k)] / g_ref.double().norm().item()
+            e_call = (g.double() - g_ref.double()).norm().item() / scales[(slot, k)]
+            assert cancelled >= 10 and e_call < 1e-3 and e <= 5e-2, (slot, k, e, e_self, e_call, cancelled)
+            exceptions.append((f"{slot}.{k}", round(e, 4), f"cancel x{cancelled:.0f}", f"e_call {e_call:.1e}",
+                               f"e_self {e_self:.1e}"))
+    print(kind, "worst gradient error", worst, "| reference fp32-vs-fp64 noise, worst", worst_self,
+          "| cancellation exceptions", exceptions)
 
 
 def test_adam_update_applies_the_step_gradients():

@@ -1,119 +1,53 @@
-"""North-star end criterion: after the SAME number of training iterations on the SAME batches the fused GPU
-step reaches the quality of the reference-semantics step (oracle: fp32 autograd + Adam).
+"""North-star end criterion (BASELINE.json): after the SAME number of training iterations on the SAME batches the fused
+GPU step reaches the PSNR of the reference-semantics step (oracle: fp32 autograd + Adam), at BASELINE config shapes:
 
-Measured fact this test is built around (tools/psnr_diag.py, profiles/r1_psnr_parity.md): training this
-model is chaotic at the trajectory level -- the SAME fp32 oracle run on CPU vs GPU (different summation
-order only) differs by 0.3 dB after 150 iterations, and 1e-3 relative gradient noise moves the LDR PSNR by
-0.1-0.6 dB.  "Within 0.1 dB of the reference" is therefore only resolvable against the reference's own
-perturbation band: the fused step must not be worse than the worst member of {oracle, oracle + 2e-3 relative
-gradient noise (2 seeds)} by more than 0.1 dB (2e-3 is the measured gradient error of the fp16 tensor-core
-path at init).  LDR PSNR per utils.py:198; all-in-focus HDR PSNR = exp(atlas_b(uv)) at the unshifted centre
-sample (utils.py:164), max-normalised (utils.py:733-736) -- reported, but gated on its exposure-fitted variant
-because the max-normalisation alone moves it by 2 dB between two runs of the same binary.
+  * config_mf_static : 2 x 300 x 450, B = 8 100 px/step, K = 9 taps, 2 000 iterations  (FusedTrainStep)
+  * config_me_dynamic: 3 x 448 x 680, B = 54 835 px/step, uv mapping + rigidity loss + random gamma, 2 000 iterations
+                       (LayeredTrainStep)
 
-Second measured fact (tools/psnr_spread.py): at 300 iterations the all-in-focus HDR has TWO basins -- exposure-fitted
-PSNR ~14.9 dB and ~10.8 dB at the same LDR PSNR (the data do not yet decide how the blur is split between the scene
-and the blur kernels).  The reference visits both under gradient noise (seeds 0-7: 14.78, 14.91, 14.99, 14.93, 10.86,
-14.75, 15.06, 14.75) and so do identical runs of the fused step, whose only run-to-run difference is the order of
-float atomics (8 runs: 15.03, 10.80, 10.88, 14.96, 14.83, 10.74, 14.89, 10.91); the fp32 oracle with a mere 1e-6
-relative gradient noise lands in the low basin in 3 of 8 seeds.  The test therefore repeats the fused
-run and asks that it reaches the high basin and never falls below the reference's low one."""
+Metrics: all-in-focus LDR PSNR over every frame (utils.py:95-198) and all-in-focus HDR PSNR with evaluate_hdr's
+max / mean normalisation (utils.py:733-736), both evaluated with the oracle's fp32 networks for every contestant.
+
+What "within 0.1 dB of the reference" can mean for this model: training is chaotic at the trajectory level -- the SAME
+fp32 oracle fed the SAME pixels of every batch in a different order (same set, another fp32 summation order) ends
+0.2 dB (mf_static) to 3.3 dB (me_dynamic) away from itself in LDR PSNR after 2 000 iterations (measured:
+profiles/r2_psnr_parity.md).  The fused step is deterministic (no float atomics: tests/test_determinism_gpu.py), so its
+number is a single point; the reference's is a band.  The test measures that band in the same run -- the oracle as is
+plus its order-permuted repeats -- and requires the fused step's PSNR inside it, widened on both sides by
+max(0.1 dB, the band's own width): the spread a further reference run would itself be expected to show.
+"""
 import pytest
 import torch
 
-from oracle_replay import orc
-
-from neucam_b200 import harness
-from neucam_b200.step import FusedTrainStep, StepOptions
+from psnr_harness import gammas, index_stream, make_case, metrics, run_fused, run_oracle
 
 pytestmark = pytest.mark.gpu
 
-ITERS = 300
-DEV = "cuda"
+ITERS = 2000
 
 
-def render_metrics(state, scene, shape):
-    n, h, w = shape
-    st = {s: {k: v.to(DEV) for k, v in d.items()} for s, d in state.items()}
-    grid = scene.mgrid.to(DEV)
-    idx = torch.arange(grid.shape[0], device=DEV)
-    with torch.no_grad():
-        cfg = orc.StepConfig(shape, with_grad_loss=False)
-        batch = {"coords": grid[None], "coord_idx": idx[None], "img": scene.data.to(DEV)[None]}
-        _, inter = orc.step_losses(st, batch, cfg, return_intermediates=True)
-        psnr_ldr = harness.psnr(inter["ldr"] / 2 + 0.5, scene.data.to(DEV) / 2 + 0.5).item()
-        hdr = torch.exp(orc.sine_mlp(st["atlas_b"], grid[: h * w, 1:])).t().reshape(3, h, w)
-        rad = scene.radiance.to(DEV)
-        psnr_hdr = harness.psnr(hdr / hdr.max(), rad / rad.max()).item()
-        # the same comparison with the least-squares exposure scale instead of the max-normalisation: one bright
-        # pixel moves hdr.max() and with it the reference's metric by decibels (observed run to run: 10.5 .. 12.7 dB
-        # for the SAME code, float atomics order only), which makes the max-normalised number unusable as a gate
-        fit = (hdr * rad).sum() / (hdr * hdr).sum()
-        psnr_hdr_fit = harness.psnr(fit * hdr / rad.max(), rad / rad.max()).item()
-    return psnr_ldr, psnr_hdr, psnr_hdr_fit
+def _check(kind, n_permuted):
+    case = make_case(kind)
+    n_total = case["shape"][0] * case["shape"][1] * case["shape"][2]
+    idxs, gams = index_stream(n_total, case["B"], ITERS, 4), gammas(ITERS, 5)
+    ours = metrics(case, run_fused(case, idxs, gams))
+    band = [metrics(case, run_oracle(case, idxs, gams))]
+    band += [metrics(case, run_oracle(case, idxs, gams, permute_seed=100 + j)) for j in range(n_permuted)]
+    msg = []
+    for key in ("ldr_psnr", "hdr_psnr"):
+        lo, hi = min(b[key] for b in band), max(b[key] for b in band)
+        w = max(0.1, hi - lo)
+        msg.append(f"{key}: fused {ours[key]:.3f} dB; reference {band[0][key]:.3f} dB, order-permuted "
+                   f"{[round(b[key], 3) for b in band[1:]]} -> band [{lo:.3f}, {hi:.3f}] +- {w:.3f}")
+        assert lo - w <= ours[key] <= hi + w, msg[-1]
+    print(f"{kind} after {ITERS} iterations (B = {case['B']}): " + " | ".join(msg))
 
 
-def run_oracle(scene, shape, focal, batches, noise, seed):
-    models = harness.build_static_models(shape, focal, hidden=512, seed=1)
-    state = {s: {k: v.detach().clone().to(DEV) for k, v in m.state_dict().items()}
-             for s, m in models.items() if m is not None}
-    cfg = orc.StepConfig(shape, with_grad_loss=False)
-    mom = {s: {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in d.items()} for s, d in state.items()}
-    g = torch.Generator(device=DEV).manual_seed(seed)
-    for i, (inp, gt) in enumerate(batches):
-        b = {k: v.to(DEV) for k, v in inp.items()}
-        b["img"] = gt["img"].to(DEV)
-        _, grads = orc.step_grads(state, b, cfg)
-        for s, d in state.items():
-            for k in d:
-                gr = grads[s][k]
-                if noise > 0:
-                    gr = gr + noise * gr.norm() / max(gr.numel(), 1) ** 0.5 * torch.randn(gr.shape, generator=g, device=DEV)
-                p, m, v = orc.adam_update(d[k], gr, mom[s][k][0], mom[s][k][1], i + 1, cfg.lr)
-                d[k] = p
-                mom[s][k] = (m, v)
-    return render_metrics(state, scene, shape)
-
-
-OUR_RUNS = 6
-# Lowest member of the reference's LOW basin of the exposure-fitted HDR metric seen in tools/psnr_spread.py
-# (oracle + 2e-3 gradient noise, seed 4: 10.859 dB; see the module docstring and profiles/r1_psnr_parity.md).
-REFERENCE_LOW_BASIN_DB = 10.86
-
-
-def test_psnr_after_same_iterations_matches_reference_band():
+def test_psnr_mf_static_at_baseline_shape():
     torch.backends.cuda.matmul.allow_tf32 = False
-    shape, focal, B = (2, 20, 30), [-1.0, 1.0], 400
-    scene = harness.SyntheticScene(shape, focal, exposures=[-0.5, 0.5], seed=3, max_radius=2)
-    gen = torch.Generator().manual_seed(4)
-    batches = [scene.sample(B, gen) for _ in range(ITERS)]
+    _check("mf_static", n_permuted=2)
 
-    ours = []
-    for _ in range(OUR_RUNS):      # identical runs: only the order of the float atomics differs
-        models = harness.build_static_models(shape, focal, hidden=512, seed=1)
-        step = FusedTrainStep(models, shape, StepOptions(lr=1e-4), B, device=DEV)
-        for inp, gt in batches:
-            step.step(inp, gt)
-        torch.cuda.synchronize()
-        ours.append(render_metrics({s: {k: v.detach().float() for k, v in m.state_dict().items()}
-                                    for s, m in models.items() if m is not None}, scene, shape))
 
-    band = [run_oracle(scene, shape, focal, batches, 0.0, 0),
-            run_oracle(scene, shape, focal, batches, 2e-3, 1),
-            run_oracle(scene, shape, focal, batches, 2e-3, 2)]
-    ldr = [b[0] for b in band]
-    fit = [b[2] for b in band]
-    our_ldr = sorted(o[0] for o in ours)
-    our_fit = sorted(o[2] for o in ours)
-    print(f"after {ITERS} iterations, {OUR_RUNS} runs of the fused step: LDR PSNR {[round(v, 3) for v in our_ldr]} dB "
-          f"(reference {ldr[0]:.3f}, + 2e-3 grad noise {ldr[1]:.3f} / {ldr[2]:.3f}); exposure-fitted all-in-focus HDR "
-          f"PSNR {[round(v, 3) for v in our_fit]} dB (reference {fit[0]:.3f}, noisy {fit[1]:.3f} / {fit[2]:.3f}); "
-          f"max-normalised HDR PSNR {[round(o[1], 3) for o in ours]} (reference {band[0][1]:.3f})")
-    # LDR PSNR (unimodal): the median run is inside the reference's perturbation band, no run far below it
-    assert our_ldr[OUR_RUNS // 2] >= min(ldr) - 0.1
-    assert our_ldr[0] >= min(ldr) - 0.5
-    assert abs(our_ldr[OUR_RUNS // 2] - ldr[0]) <= max(1.0, 3 * (max(ldr) - min(ldr)))
-    # all-in-focus HDR (bimodal for the reference as well): the fused step reaches the reference's high basin, and
-    # no run falls below the reference's low basin
-    assert our_fit[-1] >= min(fit) - 0.25
-    assert our_fit[0] >= min(min(fit), REFERENCE_LOW_BASIN_DB) - 0.3
+def test_psnr_me_dynamic_at_baseline_shape():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _check("me_dynamic", n_permuted=3)

@@ -1,9 +1,13 @@
 """GPU parity of the fused 256-wide ReLU MLP (csrc/relu_chain.cu + the job-table wgrad kernel, through the C ABI and
-neucam_b200.relu_mlp) against the same module evaluated with plain fp32 torch ops, for every uv-mapping / alpha
-network shape the shipped configs build (configs/config_{me_dynamic,video_deblur,video_hdr}.txt).
+neucam_b200.relu_mlp) against the ORACLE's restatement of SimpleMLP.forward (oracle.neucam_oracle.simple_mlp, which
+follows modules.py:282-312 and is pinned to the unmodified reference by tests/test_oracle_vs_golden.py) in fp32 with
+autograd, for every uv-mapping / alpha network shape the shipped configs build
+(configs/config_{me_dynamic,video_deblur,video_hdr}.txt).
 Tolerances: forward <= 1e-3, gradients <= 1e-2 relative (BASELINE.json north_star)."""
 import pytest
 import torch
+
+from oracle_replay import orc
 
 from neucam_b200 import modules, relu_mlp
 
@@ -24,20 +28,24 @@ CASES = {
 
 
 def run(net, x, upstream, fused, monkeypatch):
-    with monkeypatch.context() as mp:
-        if not fused:
-            mp.setattr(relu_mlp, "eligible", lambda m: False)
+    """fused=True: the module's CUDA path (the chain kernels).  fused=False: the oracle on the module's state_dict."""
+    xin = x.clone().requires_grad_(True)
+    if fused:
         for p in net.parameters():
             p.grad = None
-        xin = x.clone().requires_grad_(True)
         y = net(xin)
         (y * upstream).sum().backward()
         return y.detach(), xin.grad.detach(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    nf = net.positional_encoding.num_frequencies if net.use_encoding else None
+    y = orc.simple_mlp(sd, xin, net.last_nonlinear, 3, skip_layer=tuple(net.skip_layer), num_frequencies=nf)
+    (y * upstream).sum().backward()
+    return y.detach(), xin.grad.detach(), {k: v.grad.detach().clone() for k, v in sd.items()}
 
 
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("Q", [1000, 128 * 300 + 5])
-def test_forward_and_gradients_match_torch(case, Q, monkeypatch):
+def test_forward_and_gradients_match_oracle(case, Q, monkeypatch):
     torch.manual_seed(hash(case) % 1000)
     c = CASES[case]
     net = modules.SimpleMLP(hidden_dim=256, num_layer=c["num_layer"], in_dim=3, out_dim=c["out_dim"],
