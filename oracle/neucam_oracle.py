@@ -7,8 +7,8 @@ cpu_baseline / `--impl reference` legs may import it; the product (neucam_b200/)
 
 Parity pinning: the reference ships NO tests or golden vectors for this path, so the
 oracle is pinned against outputs of the reference itself run in the build container
-(oracle/make_golden.py -> tests/golden/*.pt, checked by tests/test_oracle_vs_golden.py, and live by
-tests/test_oracle_vs_reference.py whenever /root/reference is present).
+(oracle/make_golden.py -> tests/golden/*.pt, checked by tests/test_oracle_vs_golden.py, and live, function by
+function, by tests/test_oracle_vs_reference.py whenever /root/reference is present).
 
 State layout: `state` maps the reference's model slot names to the reference's own state_dict keys
 (utils.py:645-673), e.g. state['atlas_b']['net.net.0.0.weight'], state['blur']['layers.0.weight'],
@@ -297,7 +297,8 @@ def step_losses(state, batch, cfg, gamma=None, grad_loss_points=None, return_int
             losses["sparsity_loss2"] = torch.mean(-1 / (torch.log(alpha + 1e-24) + torch.log(1 - alpha + 1e-24)))
         if cfg.alpha_loss_w is not None:
             losses["alpha_loss"] = torch.mean(alpha) * cfg.alpha_loss_w
-    z3, z1 = torch.zeros(1, 3, device=coords.device), torch.zeros(1, 1, device=coords.device)
+    z3 = torch.zeros(1, 3, device=coords.device, dtype=coords.dtype)     # dtype follows the inputs: the oracle also runs
+    z1 = torch.zeros(1, 1, device=coords.device, dtype=coords.dtype)     # in fp64 (its own arithmetic-noise reference)
     ue, _ = tonemap(state["tm"], z3, z1)
     losses["ue_loss"] = torch.mean(torch.abs(ue - cfg.fixed_value))                 # 244-245
     if cfg.with_grad_loss and grad_loss_points is not None:

@@ -36,7 +36,8 @@ def _compare(model, fx, loss_rel, travel, p_mean):
         d = (mine - want).abs()
         assert d.max().item() <= travel, (k, d.max().item())
         assert d.mean().item() <= p_mean, (k, d.mean().item())
-        assert (d > 2e-5).float().mean().item() <= 3e-3, (k, (d > 2e-5).float().mean().item())
+        n_off = int((d > 2e-5).sum().item())
+        assert n_off <= max(1, int(3e-3 * d.numel())), (k, n_off, d.numel())
 
 
 def test_warm_tm_matches_reference_run():
