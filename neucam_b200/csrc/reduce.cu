@@ -9,13 +9,34 @@
 
 namespace {
 
-// thread = one element of the record; sums the nparts records with four interleaved accumulators combined in a fixed
-// order (deterministic, and 4 loads in flight per thread).
-__global__ void __launch_bounds__(256)
+// A block owns 32 consecutive elements of the record.  Its 8 warps split the nparts records between them (warp g sums
+// records g, g + 8, g + 16, ... in that order, four loads in flight) and the eight partial sums are then added in warp
+// order by warp 0: a FIXED summation tree, so the result is bit-reproducible, with 8 x 32 threads of parallelism per
+// 32 outputs instead of one long serial loop per output (the first version of this kernel took 24 us per call).
+constexpr int RG = 8;   // record groups = warps per block
+__global__ void __launch_bounds__(32 * RG)
 reduce_partials_kernel(const float* __restrict__ ws, int nparts, long long stride, nchost::ReduceSegs segs, int total,
                        const float* __restrict__ inv_scale_of) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  __shared__ float s_part[RG][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (i < total) {
+    const float* p = ws + i;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int q = g;
+    for (; q + 3 * RG < nparts; q += 4 * RG) {
+      a0 += p[(long long)q * stride];
+      a1 += p[(long long)(q + RG) * stride];
+      a2 += p[(long long)(q + 2 * RG) * stride];
+      a3 += p[(long long)(q + 3 * RG) * stride];
+    }
+    for (; q < nparts; q += RG) a0 += p[(long long)q * stride];
+    acc = (a0 + a1) + (a2 + a3);
+  }
+  s_part[g][lane] = acc;
+  __syncthreads();
+  if (g != 0 || i >= total) return;
   float* dst = nullptr;
 #pragma unroll 1
   for (int s = 0; s < segs.nseg; ++s) {
@@ -23,17 +44,9 @@ reduce_partials_kernel(const float* __restrict__ ws, int nparts, long long strid
     if (r >= 0 && r < segs.seg[s].n) dst = segs.seg[s].dst + r;
   }
   if (dst == nullptr) return;   // padding between segments
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  const float* p = ws + i;
-  int q = 0;
-  for (; q + 4 <= nparts; q += 4) {
-    a0 += p[(long long)(q + 0) * stride];
-    a1 += p[(long long)(q + 1) * stride];
-    a2 += p[(long long)(q + 2) * stride];
-    a3 += p[(long long)(q + 3) * stride];
-  }
-  for (; q < nparts; ++q) a0 += p[(long long)q * stride];
-  float t = (a0 + a1) + (a2 + a3);
+  float t = s_part[0][lane];
+#pragma unroll
+  for (int k = 1; k < RG; ++k) t += s_part[k][lane];
   if (inv_scale_of != nullptr) t *= 1.f / *inv_scale_of;
   *dst += t;
 }
@@ -48,8 +61,8 @@ int launch_reduce_partials(const float* ws, int nparts, int64_t stride, const Re
   for (int s = 0; s < segs.nseg; ++s)
     if (segs.seg[s].off + segs.seg[s].n > total) total = segs.seg[s].off + segs.seg[s].n;
   if (total == 0 || nparts <= 0) return 0;
-  reduce_partials_kernel<<<(total + 255) / 256, 256, 0, stream>>>(ws, nparts, (long long)stride, segs, total,
-                                                                  inv_scale_of);
+  reduce_partials_kernel<<<(total + 31) / 32, 32 * RG, 0, stream>>>(ws, nparts, (long long)stride, segs, total,
+                                                                    inv_scale_of);
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
   return 0;

@@ -188,29 +188,29 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
   if (warp == 4) tmem_dealloc_2cta(tmem_base, 512);
 }
 
-// Second pass of the split-K weight gradients: element (i, j) of the 256 x 256 tile space (and the 256 bias sums) is
-// owned by one thread, which walks the jobs IN ORDER and, per job, its Q-slices in order:
-//   dw[m0 + i, n0 + j] += (sum_s part[job][s][i][j]) / scale.
-// Jobs that target the same tile of the same tensor (the optional hi / lo operand splits of the ReLU MLPs) are thus
-// serialised inside one thread: no atomics, no races, a fixed summation order.
+// Second pass of the split-K weight gradients: thread = (element (i, j) of the 256 x 256 tile space or one of the 256
+// bias sums, job): dw[m0 + i, n0 + j] += (sum over the job's Q-slices, in slice order) / scale.  Jobs that target the
+// SAME tile of the same tensor (the optional hi / lo operand splits of the ReLU MLPs) are chained on the host and
+// walked in job order by the thread of the chain's first job: no atomics, no races, a fixed summation order.
 struct ReduceJob {
   float* dw;
   float* db;
   int m0, n0, ldw, n_valid;
+  int next;      // next job of the same destination tile, or -1
+  int is_head;   // first job of its chain
 };
 struct ReduceJobs {
   ReduceJob job[MAX_JOBS];
 };
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int n_jobs, int splits,
-                    const float* __restrict__ scale) {
+wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int splits, const float* __restrict__ scale) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. REC-1
-  if (e >= REC) return;
+  if (e >= REC || !jobs.job[blockIdx.y].is_head) return;
   const float inv = 1.f / *scale;
   const bool bias = e >= 256 * 256;
   const int i = bias ? (e - 256 * 256) : (e >> 8), j = e & 255;
 #pragma unroll 1
-  for (int jb = 0; jb < n_jobs; ++jb) {
+  for (int jb = blockIdx.y; jb >= 0; jb = jobs.job[jb].next) {
     const ReduceJob& J = jobs.job[jb];
     if (bias ? (J.db == nullptr) : (j >= J.n_valid)) continue;
     const float* src = part + (size_t)jb * splits * REC + e;
@@ -315,9 +315,16 @@ static int launch_wgrad_jobs(WgradJobs& jobs, int n_jobs, int64_t Q, const float
   ReduceJobs rj;
   for (int i = 0; i < n_jobs; ++i) {
     const WgradJob& j = jobs.job[i];
-    rj.job[i] = ReduceJob{j.dw, j.db, j.m0, j.n0, j.ldw, j.n_valid};
+    rj.job[i] = ReduceJob{j.dw, j.db, j.m0, j.n0, j.ldw, j.n_valid, -1, 1};
   }
-  wgrad_reduce_kernel<<<(REC + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p.part, rj, n_jobs, splits, scale_dev);
+  for (int i = 0; i < n_jobs; ++i)        // chain the jobs that write the same destination tile, in job order
+    for (int k = i + 1; k < n_jobs; ++k)
+      if (rj.job[k].dw == rj.job[i].dw && rj.job[k].m0 == rj.job[i].m0 && rj.job[k].n0 == rj.job[i].n0) {
+        rj.job[i].next = k;
+        rj.job[k].is_head = 0;
+        break;
+      }
+  wgrad_reduce_kernel<<<dim3((REC + 255) / 256, n_jobs), 256, 0, (cudaStream_t)stream>>>(p.part, rj, splits, scale_dev);
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(2);
   return 0;
