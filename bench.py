@@ -68,29 +68,29 @@ def pick_peak(peaks, src, clocks):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons DURING a timed region, polled through NVML every 2 ms (nvidia-smi's process
+    start-up is slower than a whole 50 ms timed region; NVML is what it reads anyway).  The power sensor is a ~100 ms
+    moving average: on a region shorter than that, `power_w_max` lags the real draw."""
 
     def __init__(self, index):
-        self.index = index
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
         self.rows = []
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        nv = self.nv
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         self._t.start()
@@ -98,16 +98,27 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        self._t.join(timeout=2)
 
     def summary(self):
+        nv = self.nv
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0}
         sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+        bits = 0
+        for r in self.rows:
+            bits |= int(r[2])
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+        reasons = [n for n, attr in names if bits & int(getattr(nv, attr, 0))]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(r[1] for r in self.rows)}
 
 
 class Dist:
@@ -345,14 +356,20 @@ def measure_static(D, cfg, B, global_pixels, steps, warmup, with_kernels=True, k
     # ---- per-kernel timing (rank 0): whole eager steps, the tensor kernels bracketed by CUDA events on the launch
     #      stream -- durations in the context they run in (caches, clocks, neighbours), not back-to-back reruns ----
     kern = {}
+    kern_clocks = None
     if with_kernels and D.rank == 0:
         evs = []
         n_eager = 16
-        for i in range(n_eager):
-            load_resident(i)
-            step.forward_backward(events=evs)
-            step.optimizer_step(reduce=False)
         torch.cuda.synchronize()
+        time.sleep(0.5)      # let the power-management state of the previous (longer) regions decay: the kernels are
+                             # timed in a burst of the same length as the driver's 20-step timed region
+        with ClockSampler(D.local_rank) as kclk:
+            for i in range(n_eager):
+                load_resident(i)
+                step.forward_backward(events=evs)
+                step.optimizer_step(reduce=False)
+            torch.cuda.synchronize()
+        kern_clocks = kclk.summary()
         acc = {}
         for name, a, b in evs[3 * 4:]:            # first 4 steps = warm-up of the eager path
             acc.setdefault(name, []).append(a.elapsed_time(b))
@@ -377,6 +394,7 @@ def measure_static(D, cfg, B, global_pixels, steps, warmup, with_kernels=True, k
         import torch.distributed as dist
         dist.barrier()
     out["kernels"] = kern
+    out["kernel_clocks"] = kern_clocks
     del step
     torch.cuda.empty_cache()
     return out
@@ -393,7 +411,9 @@ def static_line(D, args, name, cfg, peaks, peak_src, B, global_pixels, scaling, 
     kern = m["kernels"]
     tensor_k = {k: v for k, v in kern.items() if "tflops" in v}
     dom = max(tensor_k, key=lambda k: tensor_k[k]["ms"])
-    peak, peak_source = pick_peak(peaks, peak_src, m["clocks"])
+    # the roofline kernel is timed in its own region: the peak it is compared with follows THAT region's clocks
+    peak, peak_source = pick_peak(peaks, peak_src, m["kernel_clocks"] or m["clocks"])
+    step_peak, _ = pick_peak(peaks, peak_src, m["clocks"])
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp) and name == "mfme_blender":
@@ -414,7 +434,7 @@ def static_line(D, args, name, cfg, peaks, peak_src, B, global_pixels, scaling, 
                    "cuda_graph": True},
         "px_per_s": value / K,
         "tflops_algorithmic": value * FLOP_PER_SAMPLE_FWD_BWD / 1e12,
-        "frac_of_tensor_peak_whole_step": value / world * FLOP_PER_SAMPLE_FWD_BWD / 1e12 / peak,
+        "frac_of_tensor_peak_whole_step": value / world * FLOP_PER_SAMPLE_FWD_BWD / 1e12 / step_peak,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": m["e2e_ms"],
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4},
         "gpu_launches": m["launches_per_step"] * args.steps,
@@ -422,6 +442,7 @@ def static_line(D, args, name, cfg, peaks, peak_src, B, global_pixels, scaling, 
         "gpu_launches_how": "neucam_launch_count() (the library counts its own kernel launches) over the graph's "
                             "warm-up + capture, per step, x steps replayed",
         "clocks": m["clocks"],
+        "kernel_timing_clocks": m["kernel_clocks"],
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": tensor_k[dom]["tflops"], "peak": peak,
                      "unit": "TFLOP/s", "frac": tensor_k[dom]["tflops"] / peak, "traffic": traffic,
                      "peak_source": peak_source, "flops_per_launch": Q * FLOP_PER_SAMPLE_ONE_PASS,
