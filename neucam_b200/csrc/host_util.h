@@ -191,12 +191,13 @@ int launch_reduce_partials(const float* ws, int nparts, int64_t stride, const Re
 // Workspace layouts (floats per partial record x records), shared by the kernels and neucam_reduce_ws_bytes.
 constexpr int WS_SINE_BWD_REC = 3 * 512;                       // dW0 [512,2] | db0 [512] per CTA
 constexpr int WS_WGRAD_REC = 256 * 256 + 256;                  // one 256 x 256 dW tile + 256 bias sums per (job, Q-slice)
+constexpr int WS_WGRAD_WIDE_REC = 256 * 512 + 256;             // scene network: 256 x 512 per (job, Q-slice)
 constexpr int WS_SKINNY_REC = 4 * 512;                         // <= 4 output rows x <= 512 columns per block
 constexpr int WS_TM_GRADS = 3 * 3 * 128;                       // CRF: (u, a, v) x (r, g, b) x 128 hidden units
 constexpr int WS_BLUR_PARAMS = 64 * 3 + 64 + 2 * (64 * 64 + 64) + 27 * 64 + 27;   // 10 331
 inline int pad4(int n) { return (n + 3) & ~3; }
 inline int64_t ws_bytes_sine_bwd() { return (int64_t)(sm_count() + 1) * WS_SINE_BWD_REC * 4; }
-inline int64_t ws_bytes_wgrad() { return (int64_t)(sm_count() / 2 > 24 ? sm_count() / 2 : 24) * WS_WGRAD_REC * 4; }
+inline int64_t ws_bytes_wgrad() { return (int64_t)(sm_count() / 2 > 24 ? sm_count() / 2 : 24) * WS_WGRAD_WIDE_REC * 4; }
 inline int64_t ws_bytes_skinny() { return (int64_t)(2 * sm_count()) * WS_SKINNY_REC * 4; }
 inline int ws_rec_psf_crf(int N) { return WS_TM_GRADS + 8 + pad4(N); }   // + gd[3], sum sq, db4[3], pad | dexps[N]
 inline int64_t ws_bytes_psf_crf(int64_t B, int N) { return ((B + 1 + 127) / 128) * (int64_t)ws_rec_psf_crf(N) * 4; }

@@ -188,6 +188,177 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
   if (warp == 4) tmem_dealloc_2cta(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// wide_wgrad_kernel: the 512 x 512 weight gradients of the scene network, 256 (rows) x 512 (columns) per CTA pair.
+//
+// hidden_wgrad_kernel covers a 512 x 512 gradient with four 256 x 256 tile jobs; each operand half is then read by two
+// jobs and shared only through L2: ncu measured 3.25 GB of DRAM reads against 2.36 GB of operands (profiles/
+// r2_ncu_static_summary.md) on a kernel that runs at 76 % of HBM peak -- the excess bytes are time.  Here a pair keeps
+// ALL 512 columns of its 256 rows in tensor memory (2 x 256 accumulator columns per CTA = the whole TMEM), so a dz half is
+// read exactly once and only the activations are shared between the two row-tile jobs of a layer.  With no accumulator
+// column left for the bias MMA, db = column sums of dz is taken from the A tiles in shared memory by the four otherwise
+// idle epilogue warps (thread = column, k-rows in order: fixed summation order).
+//   stage (per CTA) = 64 k-rows x [128 dz columns | 256 activation columns] = 48 KB, 4 stages.
+//   barriers: full[s] (leader: both CTAs' TMA bytes), mma_done[s] (tcgen05.commit, both CTAs), empty[s] (the CTA's four
+//   bias warps have read the A tile): the producer refills a stage only after the MMAs AND the bias pass are done with it.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WNSTAGE = 4;
+constexpr uint32_t WA_STAGE = 2 * ATOM_BYTES;             // 64 k x 128 dz columns
+constexpr uint32_t WB_STAGE = 4 * ATOM_BYTES;             // 64 k x 256 activation columns (this CTA's halves of both N = 256 MMAs)
+constexpr uint32_t WSTAGE_BYTES = WA_STAGE + WB_STAGE;
+constexpr uint32_t WOFF_BAR = WNSTAGE * WSTAGE_BYTES;
+constexpr uint32_t WOFF_TMEM = WOFF_BAR + 128;
+constexpr uint32_t WSMEM_BYTES = WOFF_TMEM + 16 + 1024;
+constexpr int WREC = 256 * 512 + 256;
+
+struct WideJob {
+  CUtensorMap dz;       // [Q, 512] fp16 row-major, box 64 x 64
+  CUtensorMap act;      // [Q, 512] fp16 row-major, box 64 x 64
+  int m0;               // first of this job's 256 dW rows (= dz columns)
+};
+struct WideJobs {
+  WideJob job[6];
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+wide_wgrad_kernel(const __grid_constant__ WideJobs jobs, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+  const uint32_t bar_full = base + WOFF_BAR, bar_done = bar_full + 8 * WNSTAGE, bar_empty = bar_done + 8 * WNSTAGE,
+                 bar_acc = bar_empty + 8 * WNSTAGE;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + WOFF_TMEM);
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int split = blockIdx.x >> 1;
+  const WideJob& job = jobs.job[blockIdx.y];
+  const int kb0 = split * p.kb_per_split;
+  int kb1 = kb0 + p.kb_per_split;
+  if (kb1 > p.nkb) kb1 = p.nkb;
+  const int nk = kb1 - kb0;
+  const int m0 = job.m0 + (int)crank * 128;   // this CTA's dz columns = the dW rows it owns
+
+  if (tid == 0) {
+    for (int s = 0; s < WNSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_done + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 4);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  float* rec = p.part + ((size_t)blockIdx.y * p.splits + split) * WREC;
+
+  if (nk > 0) {
+    if (warp == 4) {
+      // ---- TMA producer ----
+      uint32_t s = 0, ph = 0;
+      const uint32_t full_leader0 = mapa_shared(bar_full, 0);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * WSTAGE_BYTES);
+          const uint32_t a_st = base + s * WSTAGE_BYTES, b_st = a_st + WA_STAGE;
+          const uint32_t fb = full_leader0 + 8 * s;
+          for (int a = 0; a < 2; ++a) tma_load_2d_2cta(a_st + a * ATOM_BYTES, &job.dz, fb, m0 + a * 64, kb * 64);
+          // MMA h covers activation columns [256 h, 256 h + 256): this CTA stages its half [256 h + 128 crank, +128)
+          for (int h = 0; h < 2; ++h)
+            for (int a = 0; a < 2; ++a)
+              tma_load_2d_2cta(b_st + (2 * h + a) * ATOM_BYTES, &job.act, fb, 256 * h + 128 * (int)crank + a * 64,
+                               kb * 64);
+        }
+        __syncwarp();
+        if (++s == WNSTAGE) { s = 0; ph ^= 1; }
+      }
+    } else if (warp == 5) {
+      // ---- MMA issuer (leader) ----
+      if (leader) {
+        const uint32_t idesc = make_idesc_f16(256, 256, FMT_F16, FMT_F16, MAJOR_MN, MAJOR_MN);
+        uint32_t s = 0, ph = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a_st = base + s * WSTAGE_BYTES, b_st = a_st + WA_STAGE;
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const uint64_t ad = make_sdesc_sw128(a_st + k16 * 2048, ATOM_BYTES, 1024);
+              const uint32_t accum = (kb > kb0 || k16 > 0) ? 1u : 0u;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                umma_f16_ss_2cta(tmem_base + 256 * h, ad,
+                                 make_sdesc_sw128(b_st + 2 * h * ATOM_BYTES + k16 * 2048, ATOM_BYTES, 1024), idesc, accum);
+            }
+            umma_commit_2cta(bar_done + 8 * s, PAIR_MASK);
+          }
+          __syncwarp();
+          if (++s == WNSTAGE) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) umma_commit_2cta(bar_acc, PAIR_MASK);
+        __syncwarp();
+      }
+    } else {
+      // ---- warps 0..3: bias column sums during the main loop, then the accumulator drain ----
+      // thread t owns dz column m0 + t: element (k, t) of the A stage sits in atom t / 64 at k * 128 + ((t % 64) / 8 ^ k % 8) * 16
+      const uint32_t col_off = (tid >> 6) * ATOM_BYTES + (tid & 7) * 2;
+      const uint32_t chunk = (tid & 63) >> 3;
+      float bsum = 0.f;
+      uint32_t s = 0, ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_backoff(bar_done + 8 * s, ph, 64);     // the MMAs have consumed the stage: its data is (still) valid
+        const uint32_t a_st = base + s * WSTAGE_BYTES + col_off;
+#pragma unroll 8
+        for (uint32_t k = 0; k < 64; ++k) {
+          unsigned short hv;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(a_st + k * 128u + ((chunk ^ (k & 7u)) << 4)));
+          bsum += __half2float(__ushort_as_half(hv));
+        }
+        __syncwarp();
+        if (elect_one()) mbar_arrive(bar_empty + 8 * s);
+        if (++s == WNSTAGE) { s = 0; ph ^= 1; }
+      }
+      const uint32_t quad = warp & 3;
+      const uint32_t row = quad * 32 + lane;
+      mbar_wait(bar_acc, 0);
+      tc_fence_after_sync();
+      float* out = rec + (size_t)(crank * 128 + row) * 512;
+      const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
+      for (int i = 0; i < 16; ++i) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + i * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(out + i * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+      rec[256 * 512 + crank * 128 + tid] = bsum;
+    }
+  } else if (warp < 4) {
+    // an empty trailing Q-slice still owns a record: zero it so that the reduction reads defined values
+    float* out = rec + (size_t)(crank * 128 + tid) * 512;
+    for (int j = 0; j < 512; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec[256 * 512 + crank * 128 + tid] = 0.f;
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 4) tmem_dealloc_2cta(tmem_base, 512);
+}
+
 // Second pass of the split-K weight gradients: thread = (element (i, j) of the 256 x 256 tile space or one of the 256
 // bias sums, job): dw[m0 + i, n0 + j] += (sum over the job's Q-slices, in slice order) / scale.  Jobs that target the
 // SAME tile of the same tensor (the optional hi / lo operand splits of the ReLU MLPs) are chained on the host and
@@ -202,13 +373,16 @@ struct ReduceJob {
 struct ReduceJobs {
   ReduceJob job[MAX_JOBS];
 };
+// tile_w = columns of a record's tile (256: hidden_wgrad_kernel, 512: wide_wgrad_kernel); record = 256 x tile_w + 256 bias sums
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int splits, const float* __restrict__ scale) {
+wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int splits, int tile_w,
+                    const float* __restrict__ scale) {
+  const int REC = 256 * tile_w + 256;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. REC-1
   if (e >= REC || !jobs.job[blockIdx.y].is_head) return;
   const float inv = 1.f / *scale;
-  const bool bias = e >= 256 * 256;
-  const int i = bias ? (e - 256 * 256) : (e >> 8), j = e & 255;
+  const bool bias = e >= 256 * tile_w;
+  const int i = bias ? (e - 256 * tile_w) : (e / tile_w), j = e % tile_w;
 #pragma unroll 1
   for (int jb = blockIdx.y; jb >= 0; jb = jobs.job[jb].next) {
     const ReduceJob& J = jobs.job[jb];
@@ -324,7 +498,8 @@ static int launch_wgrad_jobs(WgradJobs& jobs, int n_jobs, int64_t Q, const float
         rj.job[k].is_head = 0;
         break;
       }
-  wgrad_reduce_kernel<<<dim3((REC + 255) / 256, n_jobs), 256, 0, (cudaStream_t)stream>>>(p.part, rj, splits, scale_dev);
+  wgrad_reduce_kernel<<<dim3((REC + 255) / 256, n_jobs), 256, 0, (cudaStream_t)stream>>>(p.part, rj, splits, 256,
+                                                                                         scale_dev);
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(2);
   return 0;
@@ -347,20 +522,42 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
   NC_CHECK_ARG(Q > 0 && Q < (1ll << 31) - 128);
   float* dw[3] = {dw1, dw2, dw3};
   float* db[3] = {db1, db2, db3};
-  WgradJobs jobs;
+  WideJobs jobs;
+  ReduceJobs rj;
   int n = 0;
   for (int l = 0; l < 3; ++l) {
     // dz16 = [3,Q,512] holding dz_1..dz_3 ; act16 = [4,Q,512] holding a_1..a_4
     const __half* dz = (const __half*)dz16 + (size_t)l * Q * HID;
     const __half* a = (const __half*)act16 + (size_t)l * Q * HID;
-    for (int mt = 0; mt < 2; ++mt)
-      for (int nt = 0; nt < 2; ++nt) {
-        int rc = fill_job(jobs.job[n++], dz, HID, a, HID, Q, dw[l], nt == 0 ? db[l] : nullptr, mt * 256, nt * 256,
-                          HID, 256);
-        if (rc) return rc;
-      }
+    for (int mt = 0; mt < 2; ++mt) {
+      int rc = nchost::make_tmap_16b(&jobs.job[n].dz, dz, (uint64_t)Q, HID, HID, 64, 64);
+      if (rc) return rc;
+      rc = nchost::make_tmap_16b(&jobs.job[n].act, a, (uint64_t)Q, HID, HID, 64, 64);
+      if (rc) return rc;
+      jobs.job[n].m0 = mt * 256;
+      rj.job[n] = ReduceJob{dw[l], db[l], mt * 256, 0, HID, 512, -1, 1};
+      ++n;
+    }
   }
-  return launch_wgrad_jobs(jobs, n, Q, scale_dev, ws, ws_bytes, stream);
+  WgradParams p{};
+  p.Q = (int)Q;
+  p.nkb = (int)((Q + 63) / 64);
+  int splits = (nchost::sm_count() / 2) / n;
+  if (splits < 1) splits = 1;
+  if (splits > p.nkb) splits = p.nkb;
+  p.kb_per_split = (p.nkb + splits - 1) / splits;
+  p.splits = splits;
+  p.scale = scale_dev;
+  p.part = reinterpret_cast<float*>(ws);
+  NC_CHECK_WS(ws, ws_bytes, (int64_t)n * splits * WREC * 4);
+  int rc = nchost::ensure_dyn_smem((const void*)wide_wgrad_kernel, (int)WSMEM_BYTES);
+  if (rc) return rc;
+  wide_wgrad_kernel<<<dim3(2 * splits, n, 1), NTHREADS, WSMEM_BYTES, (cudaStream_t)stream>>>(jobs, p);
+  NC_CHECK_CUDA(cudaGetLastError());
+  wgrad_reduce_kernel<<<dim3((WREC + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(p.part, rj, splits, 512, scale_dev);
+  NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(2);
+  return 0;
 }
 
 // Weight gradients of one 256-wide ReLU MLP (reference modules.py:255-306) from the buffers the chain kernels stored.
