@@ -182,7 +182,8 @@ __device__ __forceinline__ void write_a_half_row(uint32_t a_base, uint32_t kb, u
 }
 
 // ---- per-chunk epilogue math ----------------------------------------------------------------------------------
-// One thread turns its 32 accumulator columns of one row into 16 packed fp16 pairs of the next operand.  The layer-
+// One thread turns its 32 accumulator columns of one row into 16 packed fp16 pairs of the next operand, 16 columns
+// (one tcgen05.ld) at a time so that the second load is in flight under the first half's math.  The layer-
 // dependent variants are TEMPLATES selected by a warp-uniform branch around the whole chunk: written as conditions
 // inside one unrolled loop, the compiler if-converts them and every element pays for both sides (measured in SASS:
 // 2 MUFU + 5 FFMA + 4 FMUL per element in the backward instead of 1 + 1 + 2).
@@ -190,11 +191,11 @@ __device__ __forceinline__ void write_a_half_row(uint32_t a_base, uint32_t kb, u
 // forward: a = sin(30 z + 30 b); STORE: also the 16-bit phase of the angle (for the backward's cos); HEAD: accumulate
 // this thread's share of the 512 -> out_dim output layer.
 template <bool STORE, bool HEAD>
-__device__ __forceinline__ void fwd_chunk_math(const uint32_t (&r)[32], uint32_t (&w)[16], const float* __restrict__ b30c,
-                                               const float4* __restrict__ w4c, uint16_t* __restrict__ ph_dst,
-                                               bool ph_ok, float (&acc)[4]) {
+__device__ __forceinline__ void fwd_half_math(const uint32_t (&r)[16], uint32_t* __restrict__ w, const float* __restrict__ b30c,
+                                              const float4* __restrict__ w4c, uint16_t* __restrict__ ph_dst, bool ph_ok,
+                                              float (&acc)[4]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
     uint32_t pw[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -226,10 +227,10 @@ __device__ __forceinline__ void fwd_chunk_math(const uint32_t (&r)[32], uint32_t
 // the stored 16-bit phase; LAST (layer 0): it is recomputed from the input coordinates, and the thread accumulates its
 // share of the coordinate gradient duv = dz0 W0.
 template <bool LAST>
-__device__ __forceinline__ void bwd_chunk_math(const uint32_t (&r)[32], uint32_t (&w)[16], const uint4 (&pv)[4],
-                                               const float4* __restrict__ p0c, float u, float v, float (&acc)[4]) {
+__device__ __forceinline__ void bwd_half_math(const uint32_t (&r)[16], uint32_t* __restrict__ w, const uint4* __restrict__ pv,
+                                              const float4* __restrict__ p0c, float u, float v, float (&acc)[4]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
     const uint32_t pw[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -621,20 +622,40 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             mbar_wait(bar(BAR_ACC + c), lp);
             tc_fence_after_sync();
             trace_stamp(tr, role, tile_i, g, step, 1);
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_row + col, r);
+            // the 32 columns are drained as two 16-column loads: the second is in flight while the first is worked on
+            uint32_t ra[16], rb[16];
+            tmem_ld_32x32b_x16(t_row + col, ra);
             tmem_ld_wait();
+            tmem_ld_32x32b_x16(t_row + col + 16, rb);
             if (CHAIN_DBG(4)) {
               // debug: no epilogue math (isolates tensor-pipe rate from SIMT/LDS contention)
+              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) w[i] = r[2 * i];
+              for (int i = 0; i < 8; ++i) {
+                w[i] = ra[2 * i];
+                w[8 + i] = rb[2 * i];
+              }
             } else if (!BWD) {
               uint16_t* ph_dst = ph_out + (size_t)(col >> 3) * (TILE_M * 8);
-              if (g == 2) fwd_chunk_math<STORE, true>(r, w, b30 + col, s_w4 + col, ph_dst, tile_ok, acc);
-              else        fwd_chunk_math<STORE, false>(r, w, b30 + col, s_w4 + col, ph_dst, tile_ok, acc);
+              if (g == 2) {
+                fwd_half_math<STORE, true>(ra, w, b30 + col, s_w4 + col, ph_dst, tile_ok, acc);
+                tmem_ld_wait();
+                fwd_half_math<STORE, true>(rb, w + 8, b30 + col + 16, s_w4 + col + 16, ph_dst + 2 * (TILE_M * 8), tile_ok, acc);
+              } else {
+                fwd_half_math<STORE, false>(ra, w, b30 + col, s_w4 + col, ph_dst, tile_ok, acc);
+                tmem_ld_wait();
+                fwd_half_math<STORE, false>(rb, w + 8, b30 + col + 16, s_w4 + col + 16, ph_dst + 2 * (TILE_M * 8), tile_ok, acc);
+              }
             } else {
-              if (g < 2) bwd_chunk_math<false>(r, w, pv, s_p0 + col, u, v, acc);
-              else       bwd_chunk_math<true>(r, w, pv, s_p0 + col, u, v, acc);
+              if (g < 2) {
+                bwd_half_math<false>(ra, w, pv, s_p0 + col, u, v, acc);
+                tmem_ld_wait();
+                bwd_half_math<false>(rb, w + 8, pv + 2, s_p0 + col + 16, u, v, acc);
+              } else {
+                bwd_half_math<true>(ra, w, pv, s_p0 + col, u, v, acc);
+                tmem_ld_wait();
+                bwd_half_math<true>(rb, w + 8, pv + 2, s_p0 + col + 16, u, v, acc);
+              }
             }
             trace_stamp(tr, role, tile_i, g, step, 2);
             if (park) {
