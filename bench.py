@@ -288,7 +288,9 @@ def measure_static(D, cfg, B, global_pixels, steps, warmup, with_kernels=True, k
     dev = D.dev
     models = harness.build_static_models(cfg["shape"], cfg["focal_list"], hidden=512, seed=0)
     opts = StepOptions(patch_size=9, offset_size=5, use_random_gamma=cfg["use_random_gamma"], fixed_value=0.0, lr=1e-4)
-    step = FusedTrainStep(models, cfg["shape"], opts, B, device=dev, process_group=D.pg, global_pixels=global_pixels)
+    step = FusedTrainStep(models, cfg["shape"], opts, B, device=dev,
+                          process_group=None if os.environ.get("NEUCAM_BENCH_NO_COMM") else D.pg,   # diagnostics only
+                          global_pixels=global_pixels, overlap_allreduce=not os.environ.get("NEUCAM_BENCH_NO_OVERLAP"))
     n_batches = min(steps + warmup, 8)
     host = make_host_batches(cfg, B, n_batches, seed=100 + D.rank, pin=True)
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]

@@ -159,7 +159,7 @@ class FusedTrainStep:
     """
 
     def __init__(self, models, video_shape, options, pixels_per_step, device=None, process_group=None,
-                 global_pixels=None):
+                 global_pixels=None, overlap_allreduce=True):
         _lib.check(_lib.lib().neucam_check_device(), "neucam_check_device (need an sm_100 GPU)")
         self.models = models
         self.shape = tuple(int(s) for s in video_shape)
@@ -168,6 +168,8 @@ class FusedTrainStep:
         self.device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         self.pg = process_group
         self.world = 1
+        # data parallel: reduce the atlas bucket under the step's tails (two collectives) or everything at the end (one)
+        self.overlap_allreduce = bool(overlap_allreduce)
         if process_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
@@ -447,6 +449,9 @@ class FusedTrainStep:
         (head weight gradient || blur backward); the small rest follows.  Both are graph-capturable."""
         if self.world == 1:
             return self.forward_backward(use_mask=use_mask)
+        if not self.overlap_allreduce:
+            self.forward_backward(use_mask=use_mask)
+            return self.reduce_gradients()
         import torch.distributed as dist
         self._sync_operands()
         a = self._step_args(use_mask)
