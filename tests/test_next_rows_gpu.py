@@ -134,3 +134,35 @@ def test_frozen_groups_do_not_move():
     moved_atlas = (models["atlas_b"].state_dict()["net.net.2.0.weight"] - before["atlas_b"]["net.net.2.0.weight"]).abs().max()
     moved_blur = (models["blur"].state_dict()["layers.1.weight"] - before["blur"]["layers.1.weight"]).abs().max()
     assert 0.5e-5 < moved_atlas.item() <= 1.01e-5 and 0.5e-6 < moved_blur.item() <= 1.01e-6
+
+
+def test_parameter_writes_after_the_step_exists_are_picked_up(tmp_path):
+    """FusedTrainStep keeps fp16 tensor-core operand copies of the atlas weights.  A checkpoint loaded (utils.load_model)
+    or any torch write to the parameters AFTER the step was built must reach those copies before the next launch: the
+    step watches the flat buffer's version counter and re-packs (load_model left them stale)."""
+    from neucam_b200 import utils as nutils
+    shape, focal, B = (2, 24, 36), [-1.0, 1.0], 300
+    scene = harness.SyntheticScene(shape, focal, seed=1)
+    inp, gt = scene.sample(B, torch.Generator().manual_seed(2))
+    donor = harness.build_static_models(shape, focal, hidden=512, seed=11)
+    path = str(tmp_path / "ckpt.pth")
+    nutils.save_model(donor, path)
+
+    models = harness.build_static_models(shape, focal, hidden=512, seed=3)
+    step = FusedTrainStep(models, shape, StepOptions(), B, device="cuda")
+    step.load_batch(inp, gt)
+    step.forward_backward()
+    loss_before = step.losses()["total"].item()
+    nutils.load_model(models, path)                    # writes into the flat buffer's views, after the step exists
+    step.forward_backward()
+    torch.cuda.synchronize()
+    got = (step.losses()["total"].item(), step.params.grad.clone())
+
+    fresh_models = harness.build_static_models(shape, focal, hidden=512, seed=11)
+    fresh = FusedTrainStep(fresh_models, shape, StepOptions(), B, device="cuda")
+    fresh.load_batch(inp, gt)
+    fresh.forward_backward()
+    torch.cuda.synchronize()
+    assert got[0] != loss_before
+    assert got[0] == fresh.losses()["total"].item()
+    assert torch.equal(got[1], fresh.params.grad)
