@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NEUCAM_ABI_VERSION 6
+#define NEUCAM_ABI_VERSION 7
 
 #define NEUCAM_ERR_BAD_ARG (-1)
 #define NEUCAM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point unavailable */
@@ -65,7 +65,8 @@ int neucam_launch_count(int64_t* count_out);
  *   w0 [512,2], b0 [512], b_hid [3,512], w4 [out_dim,512], b4 [out_dim] : fp32 master parameters.
  *   w_hid16 : fp16 [3*512,512], the three hidden weight matrices stacked, each row-major [out,in]
  *             (kept in sync with the fp32 masters by neucam_pack_hidden_weights).
- *   act16   : fp16 [4,Q,512] out, a1..a4 (inputs of layers 1..4), or NULL for inference.
+ *   act16   : fp16 [3,Q,512] out, a1..a3 (inputs of layers 1..3, the weight-gradient operands), or NULL for inference.
+ *             a4 is not stored: neucam_sine_mlp_head_wgrad regenerates it from the phase of z3.
  *   phase16 : 16-bit [3, ceil(Q/128)*128*512] out, the phase of 30 z_l (l=1..3) in revolutions * 65536,
  *             in the library's tile-blocked layout (opaque; only neucam_sine_mlp_bwd reads it, to
  *             regenerate cos(30 z_l)); NULL iff act16 is NULL.
@@ -90,13 +91,14 @@ int neucam_sine_mlp_bwd(const float* uv, int64_t Q, const float* w0, const float
 
 /* neucam_sine_mlp_wgrad: ACCUMULATES dW_l [512,512] += dz_l^T a_l / scale and db_l [512] += colsum(dz_l) / scale
  *   for the hidden layers l = 1..3 (autograd MmBackward/sum of BatchLinear.forward, modules.py:24-25).
- *   dz16 = [3,Q,512] from neucam_sine_mlp_bwd, act16 = [4,Q,512] from neucam_sine_mlp_fwd. */
+ *   dz16 = [3,Q,512] from neucam_sine_mlp_bwd, act16 = [3,Q,512] from neucam_sine_mlp_fwd. */
 int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const float* scale_dev, float* dw1,
                           float* db1, float* dw2, float* db2, float* dw3, float* db3, void* ws, int64_t ws_bytes,
                           void* stream);
 
-/* neucam_sine_mlp_head_wgrad: ACCUMULATES dW4 [out_dim,512] += dy^T a4 (a4 = act16 slot 3). */
-int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q, float* dw4, void* ws,
+/* neucam_sine_mlp_head_wgrad: ACCUMULATES dW4 [out_dim,512] += dy^T a4 with a4 = sin(30 z3) regenerated from
+ *   phase3_16 = the third layer's slice of phase16 (phase16 + 2 * ceil(Q/128)*128*512 elements). */
+int neucam_sine_mlp_head_wgrad(const void* phase3_16, const float* dy, int out_dim, int64_t Q, float* dw4, void* ws,
                                int64_t ws_bytes, void* stream);
 
 /* ---- 256-wide ReLU MLPs: the uv-mapping and alpha networks of the layered configs --------------------------

@@ -14,9 +14,10 @@
 //       a1 = sin(30 (uv W0^T + b0))            SIMT prologue (K = 2)
 //       a_{l+1} = sin(30 (a_l W_l^T + b_l))    l = 1..3, tcgen05 + epilogue
 //       y  = a4 W4^T + b4                      SIMT, fused in the last epilogue (N = 3)
-//     side outputs for the backward: a1..a4 (TMA-stored straight from the operand tile) and the PHASE
+//     side outputs for the backward: a1..a3 (TMA-stored straight from the operand tile) and the PHASE
 //     of 30 z_l (l = 1..3) as 16-bit fixed point in revolutions, from which the backward regenerates
-//     cos(30 z_l) with one MUFU (tile-blocked layout so the per-row threads store/load coalesced).
+//     cos(30 z_l) with one MUFU (tile-blocked layout so the per-row threads store/load coalesced).  a4 is
+//     not stored: the head weight gradient regenerates it as sin of the stored phase of z3 (wgrad.cu).
 //   backward (autograd of the same, training.py:270):
 //       dz3 = (dy W4) * 30 cos(30 z3)          tcgen05 (one K = 16 step on a zero-padded fp16 dy / W4^T pair) + epilogue
 //       dz_{l-1} = (dz_l 30 W_l) * cos(30 z_{l-1})   l = 3..1, tcgen05 + epilogue (30 folded into the fp16 W^T)
@@ -136,7 +137,7 @@ __device__ __forceinline__ void trace_stamp(long long* tr, int role, int tile_i,
 
 struct ChainMaps {
   CUtensorMap w;         // stacked hidden weights [3*512, 512] fp16 (forward: W_l; backward: W_l^T), box 64 x 128
-  CUtensorMap act[4];    // forward: a1..a4 ; backward: dz3, dz2, dz1, (unused)   ([Q,512] fp16, box 64x128)
+  CUtensorMap act[4];    // forward: a1..a3, (unused) ; backward: dz3, dz2, dz1, (unused)   ([Q,512] fp16, box 64x128)
   CUtensorMap w4t;       // backward: head weights transposed + zero-padded, fp16 [512, 64], box 64 x 128
 };
 
@@ -485,7 +486,10 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       for (int lt = lead0; lt < p.ntiles; lt += gridDim.x, ++tcount) {
         const int tile = lt + (int)crank;
         const bool tile_ok = tile < p.ntiles;
-        for (int e4 = 0; e4 < 4; ++e4) {
+        // forward: a1 (prologue), a2, a3 -- the last activation a4 is never materialised: its only reader, the head
+        // weight gradient, regenerates it from the stored phase of z3.  backward: dz3, dz2, dz1, and the dz0 event that
+        // only hands the k-blocks back.
+        for (int e4 = 0; e4 < (BWD ? 4 : 3); ++e4) {
           const bool do_store = tile_ok && (BWD ? (e4 < 3) : STORE) && !CHAIN_DBG(16);
           for (int kb = 0; kb < 8; ++kb) {
             if (e4 < 3) mbar_wait(bar(BAR_AREADY + kb), ev & 1);
@@ -602,8 +606,12 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         // k-blocks 0..3 free up early in half 1 (kfree), so B(0), B(1) also run under it and the next layer's
         // first half can start the moment half 1 retires.  Chunks 2,3 then write their k-blocks directly.
 #pragma unroll 1
+        // forward, last layer: nothing consumes a4 on the chip (no next GEMM) or off it (see the store warp): the four A
+        // steps only feed the head accumulators (and the phase stream) -- no parking, no B steps, no operand writes
+        const bool last_fwd = !BWD && g == 2;
         for (int step = 0; step < 6; ++step) {
           const bool is_b = (step == 2 || step == 3);
+          if (last_fwd && is_b) continue;
           const uint32_t c = is_b ? (step - 2) : (step < 2 ? step : step - 2);
           const bool park = (step < 2);
           const uint32_t col = c * 128 + sub * 32;
@@ -658,6 +666,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               }
             }
             trace_stamp(tr, role, tile_i, g, step, 2);
+            if (last_fwd) continue;
             if (park) {
               // park the packed result in the accumulator columns this thread has just drained
               tmem_st_32x32b_x16(t_row + col, w);
@@ -681,7 +690,7 @@ sine_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           trace_stamp(tr, role, tile_i, g, step, 3);
         }
         lp ^= 1;
-        ++ev;
+        if (!last_fwd) ++ev;
 
         if (g == 2) {
           // combine the 4 column quarters of every row: head output (forward) / coordinate gradient (backward)
@@ -825,7 +834,7 @@ extern "C" int neucam_sine_mlp_fwd(const float* uv, int64_t Q, const float* w0, 
 #endif
   ChainMaps maps;
   void* act[4];
-  for (int i = 0; i < 4; ++i) act[i] = act16 ? (void*)((__half*)act16 + (size_t)i * Q * HID) : nullptr;
+  for (int i = 0; i < 4; ++i) act[i] = act16 ? (void*)((__half*)act16 + (size_t)(i < 3 ? i : 2) * Q * HID) : nullptr;
   int rc = build_maps(&maps, w_hid16, act, Q, p.store_act);
   if (rc) return rc;
   return p.store_act ? launch<false, true>(maps, p, (cudaStream_t)stream)

@@ -99,8 +99,10 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
     NC_TRY(neucam_blur_bwd(a->coords, a->coord_idx, a->focus, a->blur_params, a->g_blur, a->g_focus, a->B, a->K, a->N,
                            a->H, a->W, a->offset_size, a->kout, a->hid, a->dkw, a->duv, a->ws_side, a->ws_side_bytes,
                            blur_stream));
-  const __half* a4 = (const __half*)a->act16 + (size_t)3 * Q * 512;
-  NC_TRY(neucam_sine_mlp_head_wgrad(a4, a->dy, a->out_dim, Q, a->g_w4, a->ws, a->ws_bytes, stream));
+  // a4 = sin(30 z_3) is regenerated from the stored phase of z_3 (third slice of phase16)
+  const int64_t ph_stride = ((Q + 127) / 128) * 128 * 512;
+  const uint16_t* phase3 = (const uint16_t*)a->phase16 + (size_t)2 * ph_stride;
+  NC_TRY(neucam_sine_mlp_head_wgrad(phase3, a->dy, a->out_dim, Q, a->g_w4, a->ws, a->ws_bytes, stream));
   if (fj != nullptr) {
     NC_CHECK_CUDA(cudaEventRecord(fj->join, (cudaStream_t)side_stream));
     NC_CHECK_CUDA(cudaStreamWaitEvent(st, fj->join, 0));

@@ -7,7 +7,8 @@
 //     pair owns one 256 x 256 output tile of one layer for one slice of the Q axis and writes it as a partial record
 //     into the reduction workspace; wgrad_reduce_kernel then adds the slices up in slice order (no float atomics:
 //     bit-reproducible).  The bias gradient rides along as a 16-column MMA against an all-ones tile.
-//   head:  dW4[c,k] = sum_r dy[r,c] * a4[r,k]  (c < 4) -- an HBM-bound SIMT column reduction, per-block partials.
+//   head:  dW4[c,k] = sum_r dy[r,c] * a4[r,k]  (c < 4) -- an HBM-bound SIMT column reduction, per-block partials; a4 is
+//     regenerated from the stored phase of z3 (the forward chain never writes it).
 //
 // dz carries the power-of-two loss scale of the backward chain; it is divided out here.
 #include "host_util.h"
@@ -401,12 +402,18 @@ wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int splits,
   }
 }
 
-// part[block][c][k] = sum over the block's rows of s[r][c] * x[r][k]   x: fp16 [Q,512]; s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
-// 512 threads = 8 row lanes x 64 column groups of 8 (one 16-byte load each), 4 rows in flight per thread.
-template <int WIDTH>
-__global__ void __launch_bounds__(512)
+// part[block][c][k] = sum over the block's rows of s[r][c] * x[r][k]   s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
+// 512 threads = row lanes x column groups of 8 (one 16-byte load each), 4 rows in flight per thread.
+//   PHASE = false: x = fp16 [Q,WIDTH] row-major activations (the ReLU MLPs' last hidden layer).
+//   PHASE = true (WIDTH 512): x is the scene network's stored 16-bit PHASE of 30 z_3 in the chain's tile-blocked layout
+//   [tile][column group of 8][row][8]; the activation a4 = sin(30 z_3) is regenerated here (one FFMA + one MUFU per
+//   element, on a kernel that is HBM-bound) instead of being written by the forward chain and read back: 0.39 GB less
+//   HBM write traffic per step at Q = 382 725, and a4 from a 16-bit phase is more accurate than its fp16 rounding.
+template <int WIDTH, bool PHASE>
+__global__ void __launch_bounds__(512, PHASE ? 2 : 1)
 skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int nc, int Q,
                     int rows_per_block, float* __restrict__ part) {
+  constexpr int UNR = PHASE ? 2 : 4;          // rows in flight per thread (the phase variant trades them for occupancy)
   constexpr int HID = WIDTH;                 // row length of x
   constexpr int CG = WIDTH / 8;              // column groups of 8 (one 16-byte load each)
   constexpr int RL = 512 / CG;               // row lanes
@@ -415,20 +422,24 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
   const int r0 = blockIdx.x * rows_per_block;
   int r1 = r0 + rows_per_block;
   if (r1 > Q) r1 = Q;
-  const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+  // row-major x: consecutive threads = consecutive column groups of one row; blocked phases: consecutive threads =
+  // consecutive rows of one column group (128 contiguous bytes per 8 threads)
+  const int cg = PHASE ? threadIdx.x / RL : threadIdx.x % CG;
+  const int rl = PHASE ? threadIdx.x % RL : threadIdx.x / CG;
   float acc[4][8];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
-  for (int rb = r0 + rl; rb < r1; rb += 4 * RL) {
-    uint4 v[4];
-    float sv[4][4];
+  for (int rb = r0 + rl; rb < r1; rb += UNR * RL) {
+    uint4 v[UNR];
+    float sv[UNR][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const int r = rb + RL * u;
       if (r < r1) {
-        v[u] = *reinterpret_cast<const uint4*>(x + (size_t)r * HID + cg * 8);
+        const size_t off = PHASE ? ((((size_t)(r >> 7) * CG + cg) * 128 + (r & 127)) * 8) : ((size_t)r * HID + cg * 8);
+        v[u] = *reinterpret_cast<const uint4*>(x + off);
 #pragma unroll
         for (int c = 0; c < 4; ++c) sv[u][c] = (c < nc) ? __ldg(s + (size_t)r * nc + c) : 0.f;
       } else {
@@ -438,11 +449,19 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[jj]));
+        float2 f;
+        if (PHASE) {
+          // sin of a 16-bit phase (revolutions * 65536): exact int -> float through the mantissa, one FFMA, one MUFU
+          constexpr float K = 6.283185307179586f / 65536.0f;
+          f.x = __sinf(fmaf(__uint_as_float(0x4B000000u | (w[jj] & 0xFFFFu)), K, -8388608.0f * K));
+          f.y = __sinf(fmaf(__uint_as_float(0x4B000000u | (w[jj] >> 16)), K, -8388608.0f * K));
+        } else {
+          f = __half22float2(*reinterpret_cast<const __half2*>(&w[jj]));
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           acc[c][2 * jj] = fmaf(sv[u][c], f.x, acc[c][2 * jj]);
@@ -526,7 +545,7 @@ extern "C" int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_
   ReduceJobs rj;
   int n = 0;
   for (int l = 0; l < 3; ++l) {
-    // dz16 = [3,Q,512] holding dz_1..dz_3 ; act16 = [4,Q,512] holding a_1..a_4
+    // dz16 = [3,Q,512] holding dz_1..dz_3 ; act16 = [3,Q,512] holding a_1..a_3
     const __half* dz = (const __half*)dz16 + (size_t)l * Q * HID;
     const __half* a = (const __half*)act16 + (size_t)l * Q * HID;
     for (int mt = 0; mt < 2; ++mt) {
@@ -604,7 +623,7 @@ extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, cons
   return launch_wgrad_jobs(jobs, n, Q, scale_dev, ws, ws_bytes, stream);
 }
 
-template <int WIDTH>
+template <int WIDTH, bool PHASE>
 static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, float* out, void* ws, int64_t ws_bytes,
                          void* stream) {
   const int blocks = nchost::sm_count() * 2;
@@ -612,9 +631,9 @@ static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, flo
   if (rows < 32) rows = 32;
   const int grid = (int)((Q + rows - 1) / rows);
   NC_CHECK_WS(ws, ws_bytes, (int64_t)grid * nchost::WS_SKINNY_REC * 4);
-  int rc = nchost::ensure_dyn_smem((const void*)skinny_wgrad_kernel<WIDTH>, 65536);
+  int rc = nchost::ensure_dyn_smem((const void*)skinny_wgrad_kernel<WIDTH, PHASE>, 65536);
   if (rc) return rc;
-  skinny_wgrad_kernel<WIDTH><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows,
+  skinny_wgrad_kernel<WIDTH, PHASE><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows,
                                                                          reinterpret_cast<float*>(ws));
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
@@ -625,11 +644,11 @@ static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, flo
                                         (cudaStream_t)stream);
 }
 
-extern "C" int neucam_sine_mlp_head_wgrad(const void* a4_16, const float* dy, int out_dim, int64_t Q,
+extern "C" int neucam_sine_mlp_head_wgrad(const void* phase3_16, const float* dy, int out_dim, int64_t Q,
                                           float* dw4, void* ws, int64_t ws_bytes, void* stream) {
-  NC_CHECK_ARG(a4_16 && dy && dw4);
+  NC_CHECK_ARG(phase3_16 && dy && dw4);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  return launch_skinny<512>(a4_16, dy, out_dim, Q, dw4, ws, ws_bytes, stream);
+  return launch_skinny<512, true>(phase3_16, dy, out_dim, Q, dw4, ws, ws_bytes, stream);
 }
 
 // dw_last[c,k] += sum_r dpre[r,c] * (h[r,k] + h_lo[r,k]) for the last layer of a 256-wide ReLU MLP
@@ -638,7 +657,7 @@ extern "C" int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, c
                                           int64_t Q, float* dw_last, void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(h16 && dpre && dw_last);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  int rc = launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);
+  int rc = launch_skinny<256, false>(h16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);
   if (rc || h_lo16 == nullptr) return rc;
-  return launch_skinny<256>(h_lo16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);   // stream order: ws is free again
+  return launch_skinny<256, false>(h_lo16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);   // stream order: ws is free again
 }

@@ -164,7 +164,7 @@ class _SineMLPFunction(torch.autograd.Function):
             dw4 = torch.zeros_like(w4)
         duv = ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, cos, scale, dz, dw0, db0)
         ops.sine_mlp_wgrad(dz, act, scale, dws, dbs)
-        ops.sine_mlp_head_wgrad(act, dy, dw4)
+        ops.sine_mlp_head_wgrad(cos, dy, dw4)
         if tg is not None:
             tg[9].add_(dy.sum(0))
             return (None, duv) + (None,) * 10

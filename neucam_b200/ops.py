@@ -50,12 +50,21 @@ def launch_count():
 
 
 def alloc_chain_workspace(Q, device):
-    """(act16 [4,Q,512], phase16 [3, ntiles*128*512], dz16 [3,Q,512]) fp16 scratch for one atlas network."""
+    """(act16 [3,Q,512] = a1..a3, phase16 [3, ntiles*128*512], dz16 [3,Q,512]) fp16 scratch for one atlas network."""
     nt = num_tiles(Q)
-    act = torch.empty((4, Q, HID), dtype=torch.float16, device=device)
+    act = torch.empty((3, Q, HID), dtype=torch.float16, device=device)
     cos = torch.empty((3, nt * TILE_M * HID), dtype=torch.float16, device=device)
     dz = torch.empty((3, Q, HID), dtype=torch.float16, device=device)
     return act, cos, dz
+
+
+def activation_from_phase(phase16, layer, Q):
+    """a_{layer+2} = sin(30 z_{layer+1}) as fp32 [Q,512] from the stored 16-bit phases (tile-blocked layout
+    [tile][column group of 8][row][8]) -- what the head weight gradient regenerates in-kernel; used by tests."""
+    nt = num_tiles(Q)
+    p = phase16[layer].view(torch.int16).to(torch.int32) & 0xFFFF
+    p = p.view(nt, HID // 8, TILE_M, 8).permute(0, 2, 1, 3).reshape(nt * TILE_M, HID)[:Q]
+    return torch.sin(p.float() * (2.0 * 3.141592653589793 / 65536.0))
 
 
 def sine_mlp_fwd(uv, w0, b0, w_hid16, b_hid, w4, b4, y=None, act16=None, phase16=None):
@@ -108,13 +117,14 @@ def sine_mlp_wgrad(dz16, act16, scale, dws, dbs, ws=None):
     _lib.check(rc, "neucam_sine_mlp_wgrad")
 
 
-def sine_mlp_head_wgrad(act16, dy, dw4, ws=None):
-    """Accumulates dW4 [out_dim,512] += dy^T a4."""
-    _chk_cuda(act16, dy, dw4, ws)
-    Q = act16.shape[1]
+def sine_mlp_head_wgrad(phase16, dy, dw4, ws=None):
+    """Accumulates dW4 [out_dim,512] += dy^T a4, a4 = sin(30 z3) regenerated from phase16[2] (the forward does not store
+    a4)."""
+    _chk_cuda(phase16, dy, dw4, ws)
+    Q = dy.shape[0]
     if ws is None:
         ws = new_ws(WS_HEAD_WGRAD, device=dy.device)
-    rc = _lib.lib().neucam_sine_mlp_head_wgrad(_lib.ptr(act16[3]), _lib.ptr(dy), dy.shape[1], ctypes.c_int64(Q),
+    rc = _lib.lib().neucam_sine_mlp_head_wgrad(_lib.ptr(phase16[2]), _lib.ptr(dy), dy.shape[1], ctypes.c_int64(Q),
                                                _lib.ptr(dw4), *_ws_args(ws), _lib.cur_stream())
     _lib.check(rc, "neucam_sine_mlp_head_wgrad")
 

@@ -277,12 +277,17 @@ class FusedTrainStep:
         ops.pack_head_weights(self.aw[4].data, self.w4T16)
         for i in range(3):
             self.b_hid[i].copy_(self.ab[i + 1].data)
-        self._packed_version = self.params.flat._version
+        self._packed_version = self._operand_version()
+
+    def _operand_version(self):
+        # version counters of the parameters the operand copies derive from.  state_dict() / load_state_dict() /
+        # utils.load_model write through `param.detach()`, which shares the parameter's counter (the flat buffer's own
+        # counter does NOT see writes through `.data` views); the fused Adam writes through raw pointers (no bump) and
+        # re-packs itself.
+        return sum(p._version for p in self.aw[1:] + self.ab[1:4]) + self.params.flat._version
 
     def _sync_operands(self):
-        # the fused Adam writes through raw pointers (no version bump) and repacks itself; any OTHER writer is a torch
-        # op on the flat buffer or one of its views, which shares this counter
-        if self.params.flat._version != self._packed_version:
+        if self._operand_version() != self._packed_version:
             self.repack()
 
     def _step_args(self, use_mask):
@@ -425,7 +430,7 @@ class FusedTrainStep:
                 ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
                              self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw,
                              self.duv, ws=self.ws_side)
-        ops.sine_mlp_head_wgrad(self.act16, dyf, self.aw[4].grad, ws=self.ws_main)
+        ops.sine_mlp_head_wgrad(self.phase16, dyf, self.aw[4].grad, ws=self.ws_main)
         if self.has_blur:
             main.wait_stream(self._side)
 

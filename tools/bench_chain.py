@@ -40,7 +40,7 @@ def main():
         "fwd(infer)": lambda: ops.sine_mlp_fwd(uv, w0, b0, w16, bh, w4, b4, y=y),
         "bwd": lambda: ops.sine_mlp_bwd(uv, w0, b0, wT16, w4T16, dy, cos, scale, dz, dw0, db0, duv=duv, ws=ws),
         "wgrad": lambda: ops.sine_mlp_wgrad(dz, act, scale, dws, dbs, ws=ws),
-        "head_wgrad": lambda: ops.sine_mlp_head_wgrad(act, dy, dw4, ws=ws),
+        "head_wgrad": lambda: ops.sine_mlp_head_wgrad(cos, dy, dw4, ws=ws),
     }
     flops = {"fwd(train)": 2 * 788992, "fwd(infer)": 2 * 788992, "bwd": 2 * 788992, "wgrad": 2 * 3 * 512 * 512, "head_wgrad": 2 * 3 * 512}
     total = 0.0
