@@ -448,22 +448,25 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
                 int N, float sy, float sx, float offset_size, const float* __restrict__ kout,
                 const float* __restrict__ hid, const float* __restrict__ dkw, const float* __restrict__ duv) {
   extern __shared__ __align__(16) float sm[];
-  float* s_w2 = sm;                    // [64][64] (out, in) as stored
-  float* s_w3 = s_w2 + BH * BH;        // [64][64]
-  float* s_w4 = s_w3 + BH * BH;        // [28][64] (rows 27.. zero)
-  float* s_dz = s_w4 + 28 * BH;        // [PB][TP]  current layer's d(pre-activation)
+  // The weight matrices are read straight from global memory: every thread of a warp reads the same row element at
+  // the same time (one broadcast load through L1), and keeping the 39 KB out of shared memory brings a block down to
+  // 71 KB, so that a block fits next to a CTA of the weight-gradient GEMM this kernel runs concurrently with.
+  const float* __restrict__ s_w2 = bp.w2;    // [64][64] (out, in) as stored
+  const float* __restrict__ s_w3 = bp.w3;    // [64][64]
+  const float* __restrict__ s_w4 = bp.w4;    // [27][64]
+  float* s_dz = sm;                    // [PB][TP]  current layer's d(pre-activation)
   float* s_h = s_dz + PB * TP;         // [PB][TP]  that layer's input activation
   float* s_red = s_h + PB * TP;        // [PB]
   int* s_fr = reinterpret_cast<int*>(s_red + PB);   // [PB]
   const int tid = threadIdx.x;
-  float* rec = part + (size_t)blockIdx.x * rec_floats;
-  for (int i = tid; i < BH * BH; i += PB) {
-    s_w2[i] = bp.w2[i];
-    s_w3[i] = bp.w3[i];
-  }
-  for (int i = tid; i < 28 * BH; i += PB) s_w4[i] = (i < BO * BH) ? bp.w4[i] : 0.f;
+  // Persistent: ONE block per SM walks the 128-pixel groups (each with its own partial record), so that this kernel
+  // occupies 71 KB and 4 warps of every SM and the weight-gradient GEMM's CTA (145 KB) fits beside it.
+  const int ngroups = (B + PB - 1) / PB;
+#pragma unroll 1
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  float* rec = part + (size_t)grp * rec_floats;
 
-  const int p0 = blockIdx.x * PB;
+  const int p0 = grp * PB;
   const int p = p0 + tid;
   const bool valid = p < B;
   int np = B - p0;
@@ -583,6 +586,8 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
         if (s_fr[q] == f) t += s_red[q];
       rec[BR_FOCUS + f] = t;
     }
+  }
+  __syncthreads();   // the next group rewrites the shared tiles
   }
 }
 
@@ -752,12 +757,15 @@ extern "C" int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, co
   NC_CHECK_WS(ws, ws_bytes, nchost::ws_bytes_blur_bwd(B, N));
   BlurParams bp{blur_params[0], blur_params[1], blur_params[2], blur_params[3],
                 blur_params[4], blur_params[5], blur_params[6], blur_params[7]};
-  const size_t smem = sizeof(float) * (2 * BH * BH + 28 * BH + 2 * PB * TP + 2 * PB);
+  const size_t smem = sizeof(float) * (2 * PB * TP + 2 * PB);
   int rc = nchost::ensure_dyn_smem((const void*)blur_bwd_kernel, (int)smem);
   if (rc) return rc;
-  const int grid = (B + PB - 1) / PB;
+  rc = nchost::prefer_max_smem_carveout((const void*)blur_bwd_kernel);   // shares SMs with the weight-gradient GEMM
+  if (rc) return rc;
+  const int grid = (B + PB - 1) / PB;      // pixel groups = partial records
   const int rec = nchost::ws_rec_blur_bwd(N);
-  blur_bwd_kernel<<<grid, PB, smem, (cudaStream_t)stream>>>(
+  const int launch_blocks = grid < nchost::sm_count() ? grid : nchost::sm_count();
+  blur_bwd_kernel<<<launch_blocks, PB, smem, (cudaStream_t)stream>>>(
       coords, (const long long*)coord_idx, focus, bp, reinterpret_cast<float*>(ws), rec, B, H * W, N, 2.f / (H - 1),
       2.f / (W - 1), offset_size, kout, hid, dkw, duv);
   NC_CHECK_CUDA(cudaGetLastError());

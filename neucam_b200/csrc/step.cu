@@ -56,6 +56,7 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
   const int phases = a->phases == 0 ? 3 : a->phases;
   NC_CHECK_ARG((phases & ~3) == 0);
 
+  ForkJoin* fj = nullptr;
   if (phases & NEUCAM_STEP_TO_HIDDEN_WGRAD) {
   if (a->zero_ptr != nullptr && a->zero_bytes > 0) NC_CHECK_CUDA(cudaMemsetAsync(a->zero_ptr, 0, a->zero_bytes, st));
   NC_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, 4 * sizeof(float), st));
@@ -79,31 +80,34 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
                              a->gamma_dev, a->fixed_value, a->ue_weight, a->global_count, a->dy,
                              has_blur ? a->dkw : nullptr, a->g_exps, a->g_b4, a->sums, a->absmax_bits, 16.0f, a->scale,
                              nullptr, a->tm_width, a->ws, a->ws_bytes, stream));
-  // S14: scene MLP backward, hidden weight gradients (training.py:270)
+  // S14: scene MLP backward (training.py:270)
   NC_TRY(neucam_sine_mlp_bwd(a->uv, Q, a->w0, a->b0, a->wT_hid16, a->w4T16, a->out_dim, a->dy, a->phase16, a->scale,
                              a->dz16, a->duv, a->g_w0, a->g_b0, a->ws, a->ws_bytes, stream));
+  // The blur-MLP backward (FMA-pipe / latency bound, 71 KB of shared memory per block) forks to the side stream here and
+  // runs UNDER the hidden weight gradients (tensor-pipe bound, 145 KB per CTA): both fit on an SM at the same time.
+  if (has_blur) {
+    void* blur_stream = stream;
+    if (side_stream != nullptr && side_stream != stream) {
+      NC_TRY(fork_join_events(&fj));
+      NC_CHECK_CUDA(cudaEventRecord(fj->fork, st));
+      NC_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, fj->fork, 0));
+      blur_stream = side_stream;
+    }
+    NC_TRY(neucam_blur_bwd(a->coords, a->coord_idx, a->focus, a->blur_params, a->g_blur, a->g_focus, a->B, a->K, a->N,
+                           a->H, a->W, a->offset_size, a->kout, a->hid, a->dkw, a->duv, a->ws_side, a->ws_side_bytes,
+                           blur_stream));
+  }
   NC_TRY(neucam_sine_mlp_wgrad(a->dz16, a->act16, Q, a->scale, a->g_w[0], a->g_b[0], a->g_w[1], a->g_b[1], a->g_w[2],
                                a->g_b[2], a->ws, a->ws_bytes, stream));
   }
   if (!(phases & NEUCAM_STEP_TAILS)) return 0;
-  // the HBM-bound head weight gradient and the FMA-bound blur backward are independent: side by side
-  ForkJoin* fj = nullptr;
-  void* blur_stream = stream;
-  if (has_blur && side_stream != nullptr && side_stream != stream) {
-    NC_TRY(fork_join_events(&fj));
-    NC_CHECK_CUDA(cudaEventRecord(fj->fork, st));
-    NC_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, fj->fork, 0));
-    blur_stream = side_stream;
-  }
-  if (has_blur)
-    NC_TRY(neucam_blur_bwd(a->coords, a->coord_idx, a->focus, a->blur_params, a->g_blur, a->g_focus, a->B, a->K, a->N,
-                           a->H, a->W, a->offset_size, a->kout, a->hid, a->dkw, a->duv, a->ws_side, a->ws_side_bytes,
-                           blur_stream));
   // a4 = sin(30 z_3) is regenerated from the stored phase of z_3 (third slice of phase16)
   const int64_t ph_stride = ((Q + 127) / 128) * 128 * 512;
   const uint16_t* phase3 = (const uint16_t*)a->phase16 + (size_t)2 * ph_stride;
   NC_TRY(neucam_sine_mlp_head_wgrad(phase3, a->dy, a->out_dim, Q, a->g_w4, a->ws, a->ws_bytes, stream));
-  if (fj != nullptr) {
+  if (has_blur && side_stream != nullptr && side_stream != stream) {
+    // join the side stream (forked in the first phase, possibly by an earlier call with the same streams)
+    NC_TRY(fork_join_events(&fj));
     NC_CHECK_CUDA(cudaEventRecord(fj->join, (cudaStream_t)side_stream));
     NC_CHECK_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   }

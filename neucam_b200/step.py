@@ -5,8 +5,8 @@
     S7      neucam_sine_mlp_fwd    scene sine-MLP on all K*B taps (tcgen05)
     S9-S12  neucam_psf_crf_loss    PSF sum, exposure, CRF, image_mse (+gamma/mask), ue_loss; and their backward
     S14     neucam_sine_mlp_bwd    dgrad chain + layer-0 wgrad (tcgen05)
-            neucam_sine_mlp_wgrad  hidden-layer weight gradients (tcgen05 split-K), head wgrad
-            neucam_blur_bwd        blur MLP / focus backward
+            neucam_sine_mlp_wgrad  hidden-layer weight gradients (tcgen05 split-K)  ||  neucam_blur_bwd (side stream)
+            neucam_sine_mlp_head_wgrad
             [all-reduce]           one NCCL sum over the flat gradient buffer when world_size > 1
             neucam_adam_*          fused Adam over the flat buffers + fp16 operand re-pack
 
@@ -419,10 +419,8 @@ class FusedTrainStep:
         timed("sine_chain_bwd", lambda: ops.sine_mlp_bwd(
             uv, self.aw[0].data, self.ab[0].data, self.wT16, self.w4T16, dyf, self.phase16, self.scale,
             self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2), ws=self.ws_main))
-        timed("hidden_wgrad", lambda: ops.sine_mlp_wgrad(
-            self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
-            [self.ab[i].grad for i in (1, 2, 3)], ws=self.ws_main))
-        # the HBM-bound head wgrad and the FMA-bound blur backward are independent: run them side by side
+        # the FMA-pipe-bound blur backward forks to the side stream and runs UNDER the tensor-bound weight-gradient GEMM
+        # (71 KB + 145 KB of shared memory: both fit on an SM); the head wgrad follows on the main stream; then join
         main = torch.cuda.current_stream(self.device)
         if self.has_blur:
             self._side.wait_stream(main)
@@ -430,6 +428,9 @@ class FusedTrainStep:
                 ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
                              self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw,
                              self.duv, ws=self.ws_side)
+        timed("hidden_wgrad", lambda: ops.sine_mlp_wgrad(
+            self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
+            [self.ab[i].grad for i in (1, 2, 3)], ws=self.ws_main))
         ops.sine_mlp_head_wgrad(self.phase16, dyf, self.aw[4].grad, ws=self.ws_main)
         if self.has_blur:
             main.wait_stream(self._side)
@@ -462,9 +463,10 @@ class FusedTrainStep:
         a = self._step_args(use_mask)
         g = self.params.grad
         cut = self._bucket_split()
-        ops.step_fwd_bwd(a, None, phases=ops.STEP_TO_HIDDEN_WGRAD)
+        side = self._side if self.has_blur else None     # the blur backward forks in phase 1, joins in phase 2
+        ops.step_fwd_bwd(a, side, phases=ops.STEP_TO_HIDDEN_WGRAD)
         w1 = dist.all_reduce(g[:cut], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        ops.step_fwd_bwd(a, self._side if self.has_blur else None, phases=ops.STEP_TAILS)
+        ops.step_fwd_bwd(a, side, phases=ops.STEP_TAILS)
         w2 = dist.all_reduce(g[cut:], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         w1.wait()
         w2.wait()
