@@ -405,7 +405,8 @@ constexpr int TP = 68;
 // gw[o][i] += sum_q dz[q][o] * h[q][i]   (NOUT x NIN <= 64 x 64, NOUT % 8 == 0 or handled by guards, NIN % 4 == 0)
 // thread t owns the 8 x 4 block  o in [8*(t/16), +8), i in [4*(t%16), +4).
 template <int NOUT, int NIN>
-__device__ __forceinline__ void block_outer_accum(const float* s_dz, const float* s_h, int np, float* gw, int tid) {
+__device__ __forceinline__ void block_outer_accum(const float* s_dz, const float* s_h, int np, float* gw, int tid,
+                                                  bool first) {
   const int o0 = (tid >> 4) * 8, i0 = (tid & 15) * 4;
   if (o0 >= NOUT || i0 >= NIN) return;
   float acc[8][4];
@@ -429,16 +430,19 @@ __device__ __forceinline__ void block_outer_accum(const float* s_dz, const float
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
-      if (o0 + a < NOUT && i0 + b < NIN) gw[(o0 + a) * NIN + i0 + b] = acc[a][b];   // this block's partial record
+      if (o0 + a < NOUT && i0 + b < NIN) {   // this block's partial record: the same thread owns an entry for every group
+        float* g = gw + (o0 + a) * NIN + i0 + b;
+        *g = first ? acc[a][b] : *g + acc[a][b];
+      }
 }
 
 // gb[o] += sum_q dz[q][o]
 template <int NOUT>
-__device__ __forceinline__ void block_bias_accum(const float* s_dz, int np, float* gb, int tid) {
+__device__ __forceinline__ void block_bias_accum(const float* s_dz, int np, float* gb, int tid, bool first) {
   if (tid < NOUT) {
     float t = 0.f;
     for (int q = 0; q < np; ++q) t += s_dz[q * TP + tid];
-    gb[tid] = t;
+    gb[tid] = first ? t : gb[tid] + t;
   }
 }
 
@@ -459,12 +463,14 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
   float* s_red = s_h + PB * TP;        // [PB]
   int* s_fr = reinterpret_cast<int*>(s_red + PB);   // [PB]
   const int tid = threadIdx.x;
-  // Persistent: ONE block per SM walks the 128-pixel groups (each with its own partial record), so that this kernel
-  // occupies 71 KB and 4 warps of every SM and the weight-gradient GEMM's CTA (145 KB) fits beside it.
+  // Persistent: ONE block per SM walks the 128-pixel groups, so that this kernel occupies 71 KB and 4 warps of every SM
+  // and the weight-gradient GEMM's CTA (145 KB) fits beside it.  The block adds its groups into ONE partial record
+  // (every entry is owned by one thread, groups in order): the second pass sums gridDim.x records, not B / 128.
   const int ngroups = (B + PB - 1) / PB;
+  float* rec = part + (size_t)blockIdx.x * rec_floats;
 #pragma unroll 1
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-  float* rec = part + (size_t)grp * rec_floats;
+  const bool first = grp == (int)blockIdx.x;
 
   const int p0 = grp * PB;
   const int p = p0 + tid;
@@ -511,8 +517,8 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
 #pragma unroll
   for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_h + i) = make_float4(hcur[i], hcur[i + 1], hcur[i + 2], hcur[i + 3]);
   __syncthreads();
-  block_outer_accum<BO, BH>(s_dz, s_h, np, rec + BR_W4, tid);
-  block_bias_accum<BO>(s_dz, np, rec + BR_B4, tid);
+  block_outer_accum<BO, BH>(s_dz, s_h, np, rec + BR_W4, tid, first);
+  block_bias_accum<BO>(s_dz, np, rec + BR_B4, tid, first);
   float dh[BH];
 #pragma unroll
   for (int i = 0; i < BH; ++i) dh[i] = 0.f;
@@ -542,8 +548,8 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
     float* gw = rec + ((l == 2) ? BR_W3 : BR_W2);
     float* gb = rec + ((l == 2) ? BR_B3 : BR_B2);
     const float* sw = (l == 2) ? s_w3 : s_w2;
-    block_outer_accum<BH, BH>(s_dz, s_h, np, gw, tid);
-    block_bias_accum<BH>(s_dz, np, gb, tid);
+    block_outer_accum<BH, BH>(s_dz, s_h, np, gw, tid, first);
+    block_bias_accum<BH>(s_dz, np, gb, tid, first);
 #pragma unroll
     for (int i = 0; i < BH; ++i) dh[i] = 0.f;
 #pragma unroll 4
@@ -572,8 +578,8 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
   }
   *reinterpret_cast<float4*>(my_h) = make_float4(in0, in1, in2, 0.f);
   __syncthreads();
-  block_outer_accum<BH, 3>(s_dz, s_h, np, rec + BR_W1, tid);
-  block_bias_accum<BH>(s_dz, np, rec + BR_B1, tid);
+  block_outer_accum<BH, 3>(s_dz, s_h, np, rec + BR_W1, tid, first);
+  block_bias_accum<BH>(s_dz, np, rec + BR_B1, tid, first);
   // focus gradient: per-frame gather over the block's pixels in order (training.py:104-108 backward; no atomics)
   s_red[tid] = dfocus;
   s_fr[tid] = valid ? (int)(coord_idx[p] / HW) : -1;
@@ -584,7 +590,7 @@ blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ 
       float t = 0.f;
       for (int q = 0; q < PB; ++q)
         if (s_fr[q] == f) t += s_red[q];
-      rec[BR_FOCUS + f] = t;
+      rec[BR_FOCUS + f] = first ? t : rec[BR_FOCUS + f] + t;
     }
   }
   __syncthreads();   // the next group rewrites the shared tiles
@@ -762,7 +768,7 @@ extern "C" int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, co
   if (rc) return rc;
   rc = nchost::prefer_max_smem_carveout((const void*)blur_bwd_kernel);   // shares SMs with the weight-gradient GEMM
   if (rc) return rc;
-  const int grid = (B + PB - 1) / PB;      // pixel groups = partial records
+  const int grid = (B + PB - 1) / PB;      // pixel groups; one partial record per launched block
   const int rec = nchost::ws_rec_blur_bwd(N);
   const int launch_blocks = grid < nchost::sm_count() ? grid : nchost::sm_count();
   blur_bwd_kernel<<<launch_blocks, PB, smem, (cudaStream_t)stream>>>(
@@ -776,7 +782,7 @@ extern "C" int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, co
   for (int i = 0; i < 8; ++i) segs.seg[i] = {blur_grads[i], offs[i], lens[i]};
   segs.seg[8] = {dfocus, BR_FOCUS, N};
   segs.nseg = 9;
-  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), grid, rec, segs, nullptr,
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), launch_blocks, rec, segs, nullptr,
                                         (cudaStream_t)stream);
 }
 

@@ -9,11 +9,12 @@
 
 namespace {
 
-// A block owns 32 consecutive elements of the record.  Its 8 warps split the nparts records between them (warp g sums
-// records g, g + 8, g + 16, ... in that order, four loads in flight) and the eight partial sums are then added in warp
-// order by warp 0: a FIXED summation tree, so the result is bit-reproducible, with 8 x 32 threads of parallelism per
-// 32 outputs instead of one long serial loop per output (the first version of this kernel took 24 us per call).
-constexpr int RG = 8;   // record groups = warps per block
+// A block owns 32 consecutive elements of the record.  Its 16 warps split the nparts records between them (warp g sums
+// records g, g + 16, g + 32, ... in that order, eight loads in flight) and the sixteen partial sums are then added in
+// warp order by warp 0: a FIXED summation tree, so the result is bit-reproducible.  The kernel is latency-bound (a few
+// MB spread over a few hundred blocks), so what matters is loads in flight: 16 x 8 per 32 outputs (the first version,
+// one serial loop per output, took 24 us per call; 8 warps x 4 loads 10-20 us).
+constexpr int RG = 16;   // record groups = warps per block
 __global__ void __launch_bounds__(32 * RG)
 reduce_partials_kernel(const float* __restrict__ ws, int nparts, long long stride, nchost::ReduceSegs segs, int total,
                        const float* __restrict__ inv_scale_of) {
@@ -23,16 +24,25 @@ reduce_partials_kernel(const float* __restrict__ ws, int nparts, long long strid
   float acc = 0.f;
   if (i < total) {
     const float* p = ws + i;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
     int q = g;
-    for (; q + 3 * RG < nparts; q += 4 * RG) {
-      a0 += p[(long long)q * stride];
-      a1 += p[(long long)(q + RG) * stride];
-      a2 += p[(long long)(q + 2 * RG) * stride];
-      a3 += p[(long long)(q + 3 * RG) * stride];
+    for (; q + 7 * RG < nparts; q += 8 * RG) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcs(p + (long long)(q + k * RG) * stride);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += v[k];
     }
-    for (; q < nparts; q += RG) a0 += p[(long long)q * stride];
-    acc = (a0 + a1) + (a2 + a3);
+    {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (q + k * RG < nparts) ? __ldcs(p + (long long)(q + k * RG) * stride) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += v[k];
+    }
+    acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
   s_part[g][lane] = acc;
   __syncthreads();

@@ -131,6 +131,13 @@ __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst_smem, const C
       : "r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
+// global -> smem, a contiguous run of bytes (multiple of 16, both addresses 16-byte aligned), same completion mechanism
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 // smem tile -> global (bulk async group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t src_smem, int c0,
                                              int c1) {

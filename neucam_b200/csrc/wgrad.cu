@@ -405,18 +405,14 @@ wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int splits,
   }
 }
 
-// part[block][c][k] = sum over the block's rows of s[r][c] * x[r][k]   s: fp32 [Q,nc]; nc <= 4.  HBM-bound (1 KB / row):
-// 512 threads = row lanes x column groups of 8 (one 16-byte load each), 4 rows in flight per thread.
-//   PHASE = false: x = fp16 [Q,WIDTH] row-major activations (the ReLU MLPs' last hidden layer).
-//   PHASE = true (WIDTH 512): x is the scene network's stored 16-bit PHASE of 30 z_3 in the chain's tile-blocked layout
-//   [tile][column group of 8][row][8]; the activation a4 = sin(30 z_3) is regenerated here (one FFMA + one MUFU per
-//   element, on a kernel that is HBM-bound) instead of being written by the forward chain and read back: 0.39 GB less
-//   HBM write traffic per step at Q = 382 725, and a4 from a 16-bit phase is more accurate than its fp16 rounding.
-template <int WIDTH, bool PHASE>
-__global__ void __launch_bounds__(512, PHASE ? 2 : 1)
+// part[block][c][k] = sum over the block's rows of s[r][c] * x[r][k]   s: fp32 [Q,nc]; nc <= 4; x = fp16 [Q,WIDTH]
+// row-major activations (the ReLU MLPs' last hidden layer).  HBM-bound: 512 threads = row lanes x column groups of 8
+// (one 16-byte load each), 4 rows in flight per thread.
+template <int WIDTH>
+__global__ void __launch_bounds__(512, 1)
 skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int nc, int Q,
                     int rows_per_block, float* __restrict__ part) {
-  constexpr int UNR = PHASE ? 2 : 4;          // rows in flight per thread (the phase variant trades them for occupancy)
+  constexpr int UNR = 4;                     // rows in flight per thread
   constexpr int HID = WIDTH;                 // row length of x
   constexpr int CG = WIDTH / 8;              // column groups of 8 (one 16-byte load each)
   constexpr int RL = 512 / CG;               // row lanes
@@ -425,10 +421,9 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
   const int r0 = blockIdx.x * rows_per_block;
   int r1 = r0 + rows_per_block;
   if (r1 > Q) r1 = Q;
-  // row-major x: consecutive threads = consecutive column groups of one row; blocked phases: consecutive threads =
-  // consecutive rows of one column group (128 contiguous bytes per 8 threads)
-  const int cg = PHASE ? threadIdx.x / RL : threadIdx.x % CG;
-  const int rl = PHASE ? threadIdx.x % RL : threadIdx.x / CG;
+  // consecutive threads = consecutive column groups of one row
+  const int cg = threadIdx.x % CG;
+  const int rl = threadIdx.x / CG;
   float acc[4][8];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -441,7 +436,7 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
     for (int u = 0; u < UNR; ++u) {
       const int r = rb + RL * u;
       if (r < r1) {
-        const size_t off = PHASE ? ((((size_t)(r >> 7) * CG + cg) * 128 + (r & 127)) * 8) : ((size_t)r * HID + cg * 8);
+        const size_t off = (size_t)r * HID + cg * 8;
         v[u] = *reinterpret_cast<const uint4*>(x + off);
 #pragma unroll
         for (int c = 0; c < 4; ++c) sv[u][c] = (c < nc) ? __ldg(s + (size_t)r * nc + c) : 0.f;
@@ -456,15 +451,7 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
       const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        float2 f;
-        if (PHASE) {
-          // sin of a 16-bit phase (revolutions * 65536): exact int -> float through the mantissa, one FFMA, one MUFU
-          constexpr float K = 6.283185307179586f / 65536.0f;
-          f.x = __sinf(fmaf(__uint_as_float(0x4B000000u | (w[jj] & 0xFFFFu)), K, -8388608.0f * K));
-          f.y = __sinf(fmaf(__uint_as_float(0x4B000000u | (w[jj] >> 16)), K, -8388608.0f * K));
-        } else {
-          f = __half22float2(*reinterpret_cast<const __half2*>(&w[jj]));
-        }
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[jj]));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           acc[c][2 * jj] = fmaf(sv[u][c], f.x, acc[c][2 * jj]);
@@ -484,6 +471,127 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
 #pragma unroll
     for (int l = 0; l < RL; ++l) t += s_acc[l][c][k];
     part[(size_t)blockIdx.x * nchost::WS_SKINNY_REC + e] = t;   // reduced over blocks, in block order, by reduce.cu
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Scene-network head: dW4[c,k] = sum_r dy[r,c] * sin(phase3[r,k]) as a STREAMING kernel.  The tile-blocked phase layout
+// [tile][column group of 8][row 128][8] makes the 8 column groups (= 64 columns, an "octet") of one 128-row tile a
+// contiguous 16 KB run: a block owns one octet of a range of tiles and pulls those runs (plus the tile's 1.5-2 KB of dy)
+// through a ring of cp.async.bulk stages, so the bytes in flight per SM are the ring (4 x 18 KB x 2 blocks), not what
+// the register file of the math threads can hold -- the per-thread-load version of this kernel sat at 2.8 TB/s because
+// every iteration exposed a full HBM latency.  512 threads: thread = (column group of the octet, row lane of 64), two
+// 16-byte items per stage and a fixed set of nc x 8 accumulators for the whole range.  The block's sums (butterfly over
+// the warp, then the two warps of a column group) go to record `range` of the workspace; reduce.cu adds the records in
+// range order.  HBM-bound: one LOP + FFMA + MUFU + nc FFMA per element.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int HS_STAGES = 4;
+constexpr uint32_t HS_PH_BYTES = 8 * 128 * 16;            // one octet of one tile
+constexpr uint32_t HS_DY_BYTES = 128 * 4 * 4;             // dy of one tile (nc <= 4)
+constexpr uint32_t HS_STAGE_BYTES = HS_PH_BYTES + HS_DY_BYTES;
+constexpr uint32_t HS_SMEM_BYTES = HS_STAGES * HS_STAGE_BYTES + 64 + 128;   // + barriers + alignment slack
+
+template <int NC>
+__global__ void __launch_bounds__(512, 2)
+head_wgrad_stream_kernel(const uint16_t* __restrict__ phase, const float* __restrict__ dy, int Q, int ntiles,
+                         int tiles_per_range, float* __restrict__ part) {
+  extern __shared__ __align__(128) uint8_t hs_raw[];
+  const uint32_t raw = smem_u32(hs_raw);
+  const uint32_t base = (raw + 127u) & ~127u;
+  uint8_t* sm = hs_raw + (base - raw);
+  const uint32_t bar0 = base + HS_STAGES * HS_STAGE_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int octet = blockIdx.x & 7, range = blockIdx.x >> 3;
+  const int t0 = range * tiles_per_range;
+  int t1 = t0 + tiles_per_range;
+  if (t1 > ntiles) t1 = ntiles;
+  const int n = t1 - t0;
+  const int cgl = tid >> 6, rl = tid & 63;
+
+  if (tid == 0) {
+    for (int s = 0; s < HS_STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // a tile whose rows run past Q has no whole dy run to copy: its dy is written by the threads (zeros past Q)
+  auto issue = [&](int i) {
+    const int tile = t0 + i;
+    const uint32_t st = base + (uint32_t)(i % HS_STAGES) * HS_STAGE_BYTES, bar = bar0 + 8u * (uint32_t)(i % HS_STAGES);
+    const bool whole = (long long)(tile + 1) * 128 <= Q;
+    mbar_arrive_expect_tx(bar, HS_PH_BYTES + (whole ? (uint32_t)(128 * NC * 4) : 0u));
+    bulk_load_1d(st, phase + ((size_t)tile * 64 + (size_t)octet * 8) * (128 * 8), HS_PH_BYTES, bar);
+    if (whole) bulk_load_1d(st + HS_PH_BYTES, dy + (size_t)tile * 128 * NC, 128 * NC * 4, bar);
+  };
+  if (tid == 0)
+    for (int i = 0; i < HS_STAGES && i < n; ++i) issue(i);
+
+  float acc[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+
+  for (int i = 0; i < n; ++i) {
+    const int s = i % HS_STAGES;
+    const uint8_t* st = sm + (size_t)s * HS_STAGE_BYTES;
+    float* s_dy = reinterpret_cast<float*>(const_cast<uint8_t*>(st) + HS_PH_BYTES);
+    const int tile = t0 + i;
+    if ((long long)(tile + 1) * 128 > Q) {
+      for (int e = tid; e < 128 * NC; e += 512) {
+        const long long r = (long long)tile * 128 + e / NC;
+        s_dy[e] = (r < Q) ? dy[r * NC + e % NC] : 0.f;
+      }
+      __syncthreads();
+    }
+    mbar_wait(bar0 + 8u * s, (uint32_t)(i / HS_STAGES) & 1u);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = rl + 64 * h;
+      const uint4 v = *reinterpret_cast<const uint4*>(st + ((size_t)cgl * 128 + row) * 16);
+      float d[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) d[c] = s_dy[row * NC + c];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        // sin of a 16-bit phase (revolutions * 65536): exact int -> float through the mantissa, one FFMA, one MUFU
+        constexpr float K = 6.283185307179586f / 65536.0f;
+        const float f0 = __sinf(fmaf(__uint_as_float(0x4B000000u | (w[jj] & 0xFFFFu)), K, -8388608.0f * K));
+        const float f1 = __sinf(fmaf(__uint_as_float(0x4B000000u | (w[jj] >> 16)), K, -8388608.0f * K));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          acc[c][2 * jj] = fmaf(d[c], f0, acc[c][2 * jj]);
+          acc[c][2 * jj + 1] = fmaf(d[c], f1, acc[c][2 * jj + 1]);
+        }
+      }
+    }
+    __syncthreads();   // every thread is done with stage s: refill it
+    if (tid == 0 && i + HS_STAGES < n) issue(i + HS_STAGES);
+  }
+
+  // rows -> one sum per (c, column): butterfly over the warp's 32 row lanes (a fixed tree), then the column group's two
+  // warps through shared memory (the ring is idle now)
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = acc[c][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      acc[c][j] = t;
+    }
+  float* s_red = reinterpret_cast<float*>(sm);   // [16 warps][NC * 8]
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[(tid >> 5) * (NC * 8) + c * 8 + j] = acc[c][j];
+  }
+  __syncthreads();
+  if (tid < 8 * NC * 8) {
+    const int g = tid / (NC * 8), e = tid % (NC * 8), c = e / 8, j = e % 8;
+    const float t = s_red[(2 * g) * (NC * 8) + e] + s_red[(2 * g + 1) * (NC * 8) + e];
+    part[(size_t)range * nchost::WS_SKINNY_REC + c * HID + octet * 64 + g * 8 + j] = t;
   }
 }
 
@@ -626,7 +734,7 @@ extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, cons
   return launch_wgrad_jobs(jobs, n, Q, scale_dev, ws, ws_bytes, stream);
 }
 
-template <int WIDTH, bool PHASE>
+template <int WIDTH>
 static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, float* out, void* ws, int64_t ws_bytes,
                          void* stream) {
   const int blocks = nchost::sm_count() * 2;
@@ -634,9 +742,9 @@ static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, flo
   if (rows < 32) rows = 32;
   const int grid = (int)((Q + rows - 1) / rows);
   NC_CHECK_WS(ws, ws_bytes, (int64_t)grid * nchost::WS_SKINNY_REC * 4);
-  int rc = nchost::ensure_dyn_smem((const void*)skinny_wgrad_kernel<WIDTH, PHASE>, 65536);
+  int rc = nchost::ensure_dyn_smem((const void*)skinny_wgrad_kernel<WIDTH>, 65536);
   if (rc) return rc;
-  skinny_wgrad_kernel<WIDTH, PHASE><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows,
+  skinny_wgrad_kernel<WIDTH><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows,
                                                                          reinterpret_cast<float*>(ws));
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
@@ -650,8 +758,31 @@ static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, flo
 extern "C" int neucam_sine_mlp_head_wgrad(const void* phase3_16, const float* dy, int out_dim, int64_t Q,
                                           float* dw4, void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(phase3_16 && dy && dw4);
-  NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  return launch_skinny<512, true>(phase3_16, dy, out_dim, Q, dw4, ws, ws_bytes, stream);
+  NC_CHECK_ARG((out_dim == 3 || out_dim == 4) && Q > 0);
+  NC_CHECK_ARG(((uintptr_t)phase3_16 & 15) == 0 && ((uintptr_t)dy & 15) == 0);   // cp.async.bulk sources
+  const int ntiles = (int)((Q + 127) / 128);
+  int ranges = nchost::sm_count() * 2 / 8;     // 8 octet blocks per range, two blocks per SM
+  if (ranges < 1) ranges = 1;
+  if (ranges > ntiles) ranges = ntiles;
+  const int tiles_per_range = (ntiles + ranges - 1) / ranges;
+  ranges = (ntiles + tiles_per_range - 1) / tiles_per_range;
+  NC_CHECK_WS(ws, ws_bytes, (int64_t)ranges * nchost::WS_SKINNY_REC * 4);
+  const void* fn = out_dim == 3 ? (const void*)head_wgrad_stream_kernel<3> : (const void*)head_wgrad_stream_kernel<4>;
+  int rc = nchost::ensure_dyn_smem(fn, (int)HS_SMEM_BYTES);
+  if (rc) return rc;
+  if (out_dim == 3)
+    head_wgrad_stream_kernel<3><<<ranges * 8, 512, HS_SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const uint16_t*)phase3_16, dy, (int)Q, ntiles, tiles_per_range, reinterpret_cast<float*>(ws));
+  else
+    head_wgrad_stream_kernel<4><<<ranges * 8, 512, HS_SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const uint16_t*)phase3_16, dy, (int)Q, ntiles, tiles_per_range, reinterpret_cast<float*>(ws));
+  NC_CHECK_CUDA(cudaGetLastError());
+  NC_COUNT_LAUNCH(1);
+  nchost::ReduceSegs segs{};
+  segs.nseg = 1;
+  segs.seg[0] = {dw4, 0, out_dim * HID};
+  return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), ranges, nchost::WS_SKINNY_REC, segs, nullptr,
+                                        (cudaStream_t)stream);
 }
 
 // dw_last[c,k] += sum_r dpre[r,c] * (h[r,k] + h_lo[r,k]) for the last layer of a 256-wide ReLU MLP
@@ -660,7 +791,7 @@ extern "C" int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, c
                                           int64_t Q, float* dw_last, void* ws, int64_t ws_bytes, void* stream) {
   NC_CHECK_ARG(h16 && dpre && dw_last);
   NC_CHECK_ARG(out_dim >= 1 && out_dim <= 4 && Q > 0);
-  int rc = launch_skinny<256, false>(h16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);
+  int rc = launch_skinny<256>(h16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);
   if (rc || h_lo16 == nullptr) return rc;
-  return launch_skinny<256, false>(h_lo16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);   // stream order: ws is free again
+  return launch_skinny<256>(h_lo16, dpre, out_dim, Q, dw_last, ws, ws_bytes, stream);   // stream order: ws is free again
 }
