@@ -273,14 +273,15 @@ int neucam_pack_head_weights(const float* w4, int out_dim, void* w4T16, void* st
  * blur + focal + exp + tm; K = 9 taps with the blur model, K = 1 without): blur taps -> scene MLP forward -> PSF sum +
  * exposure + CRF + image_mse (+ gamma / mask) + ue_loss and their backward -> scene MLP backward -> weight gradients
  * of every network, i.e. exactly the sequence neucam_blur_fwd, neucam_sine_mlp_fwd, neucam_psf_crf_loss,
- * neucam_sine_mlp_bwd, neucam_sine_mlp_wgrad, neucam_sine_mlp_head_wgrad || neucam_blur_bwd.  Every pointer is a
+ * neucam_sine_mlp_bwd, neucam_blur_bwd, neucam_sine_mlp_wgrad, neucam_sine_mlp_head_wgrad.  Every pointer is a
  * device pointer owned by the caller; gradients are ACCUMULATED into the g_* tensors after `zero_ptr[0 .. zero_bytes)`
  * (normally the flat gradient buffer all g_* live in) and `sums` have been cleared.  Outputs: gradients, sums[0] =
  * sum of squared errors, sums[1] = ue_loss, and the scratch tensors (y, dy, uv, ...) as the individual calls leave
- * them.  `side_stream` (optional) runs the blur backward concurrently with the head weight gradient; the call joins
- * it back into `stream` before returning.  Set struct_bytes = sizeof(neucam_step_args). */
-#define NEUCAM_STEP_TO_HIDDEN_WGRAD 1 /* clear, taps, forward, loss, backward chain, hidden-layer weight gradients */
-#define NEUCAM_STEP_TAILS 2           /* head weight gradient || blur-MLP backward */
+ * them.  `side_stream` is reserved and may be NULL: every kernel is enqueued on `stream` (running the blur backward
+ * beside the weight-gradient GEMM on a second stream was measured slower than the sequence).  Set struct_bytes =
+ * sizeof(neucam_step_args). */
+#define NEUCAM_STEP_TO_HIDDEN_WGRAD 1 /* clear, taps, forward, loss, backward chain, blur backward, hidden-layer weight gradients */
+#define NEUCAM_STEP_TAILS 2           /* head weight gradient */
 typedef struct neucam_step_args {
   uint32_t struct_bytes;
   int phases;                   /* 0 or 3 = the whole step; NEUCAM_STEP_* bits select a part, so that a data-parallel
@@ -320,7 +321,7 @@ typedef struct neucam_step_args {
   float* scale;                 /* [1] loss scale (written) */
   void* ws;                     /* reduction workspace for the main stream: >= max over the NEUCAM_WS_* kinds used */
   int64_t ws_bytes;
-  void* ws_side;                /* reduction workspace of the blur backward (side stream): NEUCAM_WS_BLUR_BWD */
+  void* ws_side;                /* reduction workspace of the blur backward: NEUCAM_WS_BLUR_BWD */
   int64_t ws_side_bytes;
 } neucam_step_args;
 int neucam_step_fwd_bwd(const neucam_step_args* args, void* stream, void* side_stream);

@@ -220,7 +220,10 @@ inline int64_t ws_bytes_skinny() { return (int64_t)(2 * sm_count()) * WS_SKINNY_
 inline int ws_rec_psf_crf(int N) { return WS_TM_GRADS + 8 + pad4(N); }   // + gd[3], sum sq, db4[3], pad | dexps[N]
 inline int64_t ws_bytes_psf_crf(int64_t B, int N) { return ((B + 1 + 127) / 128) * (int64_t)ws_rec_psf_crf(N) * 4; }
 inline int ws_rec_blur_bwd(int N) { return pad4(WS_BLUR_PARAMS) + pad4(N); }
-inline int64_t ws_bytes_blur_bwd(int64_t B, int N) { return ((B + 127) / 128) * (int64_t)ws_rec_blur_bwd(N) * 4; }
+inline int64_t ws_bytes_blur_bwd(int64_t B, int N) {   // one record per block: min(64-pixel groups, 3 x SMs)
+  const int64_t groups = (B + 63) / 64;
+  return (groups < 3 * sm_count() ? groups : (int64_t)(3 * sm_count())) * ws_rec_blur_bwd(N) * 4;
+}
 inline int64_t ws_bytes_rigidity(int64_t B) { return ((B + 255) / 256) * 4 * 4; }
 inline int64_t ws_bytes_blend(int64_t KB) { return ((KB + 255) / 256) * 4 * 4; }
 

@@ -36,114 +36,184 @@ struct BlurParams {
   const float *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4;   // layers.{0..3}.{weight,bias}, weight = [out,in]
 };
 
-// dense 64->NOUT layer for one pixel per thread; input column in smem [BH][PB], weights in smem as
-// [in][out] (so that 4 outputs are one broadcast LDS.128); accumulators in registers.
-template <int NOUT>
-__device__ __forceinline__ void dense_from_smem(const float* s_in, const float* s_wt, const float* s_b,
-                                                int tid, float (&acc)[NOUT]) {
+// The blur MLP runs as register-tiled SIMT GEMMs over 64-pixel groups: 256 threads = 16 x 16 tiles of 4 x 4 outputs, so
+// that one 16-byte shared-memory load of each operand feeds 16 FMAs (a thread-per-pixel layout needs a load per 4 FMAs
+// and leaves an SM with 4-9 warps at B = 42 525 pixels).  Activation tiles live in shared memory as [feature 64][pixel
+// 64] floats; the sixteen 16-byte pixel quads of a row are XOR-swizzled with the row's feature quad, which makes every
+// access pattern below conflict-free: a warp reading one row's quads (GEMM over features), sixteen rows' quad g (GEMM
+// over pixels) or 32 consecutive pixels of a row (coalesced copies to / from global memory).
+constexpr int GP = 64;          // pixels per group
+constexpr int BT = 256;         // threads per block
+__device__ __forceinline__ int tile_off(int f, int g) { return f * GP + (((g ^ (f >> 2)) & 15) << 2); }
+__device__ __forceinline__ int tile_at(int f, int px) { return tile_off(f, px >> 2) + (px & 3); }
+
+// out[px][o] = bias[o] + sum_i in[i][px] * w[o][i] for px in [4 tx, +4), o in [4 ty, +4); w = [out][in] as stored (no
+// transposition: the loop walks the inputs four at a time, four 16-byte loads of each operand per 64 FMAs).  The sum
+// runs bias first, then i ascending (the order of a plain per-pixel loop).
+__device__ __forceinline__ void fwd_tile(const float* s_in, const float* s_w, const float* s_bias, int tx, int ty,
+                                         float (&acc)[4][4]) {
+  const float4 bv = *reinterpret_cast<const float4*>(s_bias + 4 * ty);
 #pragma unroll
-  for (int o = 0; o < NOUT; ++o) acc[o] = s_b[o];
+  for (int a = 0; a < 4; ++a) {
+    acc[a][0] = bv.x; acc[a][1] = bv.y; acc[a][2] = bv.z; acc[a][3] = bv.w;
+  }
 #pragma unroll 2
-  for (int i = 0; i < BH; ++i) {
-    const float a = s_in[i * PB + tid];
-    const float* wr = s_wt + i * NOUT;
+  for (int i0 = 0; i0 < BH; i0 += 4) {
+    float4 w[4], h[4];
 #pragma unroll
-    for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(wr[o], a, acc[o]);
+    for (int b = 0; b < 4; ++b) w[b] = *reinterpret_cast<const float4*>(s_w + (4 * ty + b) * BH + i0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = *reinterpret_cast<const float4*>(s_in + tile_off(i0 + j, tx));
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float ww[4] = {w[b].x, w[b].y, w[b].z, w[b].w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float t = acc[a][b];
+        t = fmaf(ww[0], a == 0 ? h[0].x : a == 1 ? h[0].y : a == 2 ? h[0].z : h[0].w, t);
+        t = fmaf(ww[1], a == 0 ? h[1].x : a == 1 ? h[1].y : a == 2 ? h[1].z : h[1].w, t);
+        t = fmaf(ww[2], a == 0 ? h[2].x : a == 1 ? h[2].y : a == 2 ? h[2].z : h[2].w, t);
+        t = fmaf(ww[3], a == 0 ? h[3].x : a == 1 ? h[3].y : a == 2 ? h[3].z : h[3].w, t);
+        acc[a][b] = t;
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(PB)
+template <bool RELU>
+__device__ __forceinline__ void store_tile(float* s_out, int tx, int fq, const float (&acc)[4][4]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    float4 v = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
+    if (RELU) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    *reinterpret_cast<float4*>(s_out + tile_off(4 * fq + b, tx)) = v;
+  }
+}
+
+// rows [0, nrows) of a tile -> dst[f][p0 + px] (row pitch B), coalesced over pixels
+__device__ __forceinline__ void tile_to_global(const float* s_t, float* __restrict__ dst, int nrows, int p0, int B, int tid) {
+  for (int idx = tid; idx < nrows * GP; idx += BT) {
+    const int f = idx >> 6, px = idx & 63;
+    if (p0 + px < B) dst[(size_t)f * B + p0 + px] = s_t[tile_at(f, px)];
+  }
+}
+__device__ __forceinline__ void tile_from_global(float* s_t, const float* __restrict__ src, int nrows, int p0, int B, int tid) {
+  for (int idx = tid; idx < nrows * GP; idx += BT) {
+    const int f = idx >> 6, px = idx & 63;
+    s_t[tile_at(f, px)] = (p0 + px < B) ? src[(size_t)f * B + p0 + px] : 0.f;
+  }
+}
+
+constexpr int BLUR_FWD_SMEM_FLOATS = 2 * BH * BH + BH * 28 + BH * 4 + 160 + 3 * GP + 2 * BH * GP;
+
+__global__ void __launch_bounds__(BT, 3)
 blur_fwd_kernel(const float* __restrict__ coords, const long long* __restrict__ coord_idx,
                 const float* __restrict__ focus, BlurParams bp, int B, int HW, float sy, float sx,
                 float offset_size, float* __restrict__ uv, float* __restrict__ kout,
                 float* __restrict__ hid) {
-  extern __shared__ float sm[];
-  float* s_w2t = sm;                  // [64][64]  (in, out)
-  float* s_w3t = s_w2t + BH * BH;     // [64][64]
-  float* s_w4t = s_w3t + BH * BH;     // [64][28]  (padded to 28 outputs)
-  float* s_w1 = s_w4t + BH * 28;      // [64][4]   (w1[o][0..2], b1[o])
-  float* s_b = s_w1 + BH * 4;         // b2[64], b3[64], b4[28]
-  float* s_h = s_b + 64 + 64 + 28;    // [64][PB]
-  const int tid = threadIdx.x;
-  for (int i = tid; i < BH * BH; i += PB) {
-    const int o = i / BH, k = i % BH;
-    s_w2t[k * BH + o] = bp.w2[i];
-    s_w3t[k * BH + o] = bp.w3[i];
+  extern __shared__ __align__(16) float sm[];
+  float* s_w2 = sm;                   // [64 out][64 in] as stored
+  float* s_w3 = s_w2 + BH * BH;       // [64][64]
+  float* s_w4 = s_w3 + BH * BH;       // [28][64]  (row 27 zero)
+  float* s_w1 = s_w4 + BH * 28;       // [64][4]   (w1[o][0..2], b1[o])
+  float* s_b = s_w1 + BH * 4;         // b2[64], b3[64], b4[28] (+4)
+  float* s_x = s_b + 160;             // [3][64]: focus, y, x of the group's pixels
+  float* s_t0 = s_x + 3 * GP;         // activation tiles (ping-pong)
+  float* s_t1 = s_t0 + BH * GP;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int p0 = blockIdx.x * GP;
+  for (int i = tid; i < BH * BH; i += BT) {
+    s_w2[i] = __ldg(bp.w2 + i);
+    s_w3[i] = __ldg(bp.w3 + i);
   }
-  for (int i = tid; i < BH * 28; i += PB) {
-    const int k = i / 28, o = i % 28;
-    s_w4t[i] = (o < BO) ? bp.w4[o * BH + k] : 0.f;
-  }
-  for (int o = tid; o < BH; o += PB) {
-    s_w1[o * 4 + 0] = bp.w1[o * 3 + 0];
-    s_w1[o * 4 + 1] = bp.w1[o * 3 + 1];
-    s_w1[o * 4 + 2] = bp.w1[o * 3 + 2];
-    s_w1[o * 4 + 3] = bp.b1[o];
+  for (int i = tid; i < BH * 28; i += BT) s_w4[i] = (i < BO * BH) ? __ldg(bp.w4 + i) : 0.f;
+  if (tid < BH) {
+    const int o = tid;
+    *reinterpret_cast<float4*>(s_w1 + o * 4) = make_float4(bp.w1[o * 3], bp.w1[o * 3 + 1], bp.w1[o * 3 + 2], bp.b1[o]);
     s_b[o] = bp.b2[o];
     s_b[64 + o] = bp.b3[o];
+    if (o < 32) s_b[128 + o] = (o < BO) ? bp.b4[o] : 0.f;
+  } else if (tid < BH + GP) {
+    const int px = tid - BH;
+    const int p = p0 + px, pc = p < B ? p : B - 1;
+    s_x[px] = focus[(int)(coord_idx[pc] / HW)];
+    s_x[GP + px] = coords[3 * pc + 1];
+    s_x[2 * GP + px] = coords[3 * pc + 2];
   }
-  for (int o = tid; o < 28; o += PB) s_b[128 + o] = (o < BO) ? bp.b4[o] : 0.f;
   __syncthreads();
 
-  const int p = blockIdx.x * PB + tid;
+  float acc[4][4];
+  {
+    // layer 1 (3 -> 64) + ReLU
+    const float4 f4 = *reinterpret_cast<const float4*>(s_x + 4 * tx), y4 = *reinterpret_cast<const float4*>(s_x + GP + 4 * tx),
+                 x4 = *reinterpret_cast<const float4*>(s_x + 2 * GP + 4 * tx);
+    const float ff[4] = {f4.x, f4.y, f4.z, f4.w}, yy[4] = {y4.x, y4.y, y4.z, y4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float4 w = *reinterpret_cast<const float4*>(s_w1 + (4 * ty + b) * 4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) acc[a][b] = fmaf(w.x, ff[a], fmaf(w.y, yy[a], fmaf(w.z, xx[a], w.w)));
+    }
+    store_tile<true>(s_t0, tx, ty, acc);
+  }
+  __syncthreads();
+  tile_to_global(s_t0, hid, BH, p0, B, tid);
+  fwd_tile(s_t0, s_w2, s_b, tx, ty, acc);
+  store_tile<true>(s_t1, tx, ty, acc);
+  __syncthreads();
+  tile_to_global(s_t1, hid + (size_t)BH * B, BH, p0, B, tid);
+  fwd_tile(s_t1, s_w3, s_b + 64, tx, ty, acc);
+  store_tile<true>(s_t0, tx, ty, acc);
+  __syncthreads();
+  tile_to_global(s_t0, hid + (size_t)2 * BH * B, BH, p0, B, tid);
+  if (ty < 7) {
+    fwd_tile(s_t0, s_w4, s_b + 128, tx, ty, acc);
+    store_tile<false>(s_t1, tx, ty, acc);
+  }
+  __syncthreads();
+
+  // head: softmax over the K kernel weights, tanh over the 2K offsets (modules.py:303-306); warps 0-1 take the softmax of
+  // their pixel, warps 2-7 six offsets each
+  const int px = tid & 63, part = tid >> 6;
+  const int p = p0 + px;
   const bool valid = p < B;
-  const int pc = valid ? p : (B - 1);
-  const float ct = coords[3 * pc], cy = coords[3 * pc + 1], cx = coords[3 * pc + 2];
-  (void)ct;
-  const float f = focus[(int)(coord_idx[pc] / HW)];
-
-  // layer 1 (3 -> 64) + ReLU
-#pragma unroll 8
-  for (int o = 0; o < BH; ++o) {
-    const float4 w = *reinterpret_cast<const float4*>(s_w1 + o * 4);
-    const float h = fmaxf(fmaf(w.x, f, fmaf(w.y, cy, fmaf(w.z, cx, w.w))), 0.f);
-    s_h[o * PB + tid] = h;
-    if (valid) hid[(size_t)(0 * BH + o) * B + p] = h;
+  if (part == 0) {
+    float out[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) out[k] = s_t1[tile_at(k, px)];
+    float mx = out[0];
+#pragma unroll
+    for (int k = 1; k < KT; ++k) mx = fmaxf(mx, out[k]);
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      out[k] = __expf(out[k] - mx);
+      den += out[k];
+    }
+    const float rden = 1.f / den;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      out[k] *= rden;
+      if (valid) kout[(size_t)k * B + p] = out[k];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int o = KT + (part - 1) * 6 + j;
+      const float v = tanhf(s_t1[tile_at(o, px)]);
+      s_t1[tile_at(o, px)] = v;
+      if (valid) kout[(size_t)o * B + p] = v;
+    }
   }
-  float acc[BH];
-  dense_from_smem<BH>(s_h, s_w2t, s_b, tid, acc);
-#pragma unroll
-  for (int o = 0; o < BH; ++o) {
-    const float h = fmaxf(acc[o], 0.f);
-    s_h[o * PB + tid] = h;
-    if (valid) hid[(size_t)(1 * BH + o) * B + p] = h;
-  }
-  dense_from_smem<BH>(s_h, s_w3t, s_b + 64, tid, acc);
-#pragma unroll
-  for (int o = 0; o < BH; ++o) {
-    const float h = fmaxf(acc[o], 0.f);
-    s_h[o * PB + tid] = h;
-    if (valid) hid[(size_t)(2 * BH + o) * B + p] = h;
-  }
-  float out[28];
-  dense_from_smem<28>(s_h, s_w4t, s_b + 128, tid, out);
-
-  // head: softmax over the K kernel weights, tanh over the 2K offsets (modules.py:303-306)
-  float mx = out[0];
-#pragma unroll
-  for (int k = 1; k < KT; ++k) mx = fmaxf(mx, out[k]);
-  float den = 0.f;
-#pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    out[k] = __expf(out[k] - mx);
-    den += out[k];
-  }
-  const float rden = 1.f / den;
-#pragma unroll
-  for (int k = 0; k < KT; ++k) out[k] *= rden;
-#pragma unroll
-  for (int k = KT; k < BO; ++k) out[k] = tanhf(out[k]);
+  __syncthreads();
   if (!valid) return;
-#pragma unroll
-  for (int k = 0; k < BO; ++k) kout[(size_t)k * B + p] = out[k];
-
   // tap coordinates: neighbour grid + learned offsets, centre tap = the pixel itself
-#pragma unroll
-  for (int k = 0; k < KT; ++k) {
+  const float cy = s_x[GP + px], cx = s_x[2 * GP + px];
+  for (int k = part; k < KT; k += 4) {
     const int dy = k / 3 - 1, dx = k % 3 - 1;
     float y = cy + dy * sy, x = cx + dx * sx;
-    y += out[KT + k] * sy * offset_size;
-    x += out[2 * KT + k] * sx * offset_size;
+    y += s_t1[tile_at(KT + k, px)] * sy * offset_size;
+    x += s_t1[tile_at(2 * KT + k, px)] * sx * offset_size;
     if (k == KT / 2) {
       y = cy;
       x = cx;
@@ -397,203 +467,216 @@ constexpr int BR_W1 = 0, BR_B1 = BR_W1 + BH * 3, BR_W2 = BR_B1 + BH, BR_B2 = BR_
 static_assert(BR_END == nchost::WS_BLUR_PARAMS, "workspace layout");
 constexpr int BR_FOCUS = (BR_END + 3) & ~3;
 
-// Tiles of the blur backward live in smem as [pixel][feature] with a 68-float row pitch: a pixel-thread
-// writes/reads its own row with conflict-free 128-bit accesses, and the block-level outer products read
-// 4-feature vectors of a common pixel row.
-constexpr int TP = 68;
-
-// gw[o][i] += sum_q dz[q][o] * h[q][i]   (NOUT x NIN <= 64 x 64, NOUT % 8 == 0 or handled by guards, NIN % 4 == 0)
-// thread t owns the 8 x 4 block  o in [8*(t/16), +8), i in [4*(t%16), +4).
-template <int NOUT, int NIN>
-__device__ __forceinline__ void block_outer_accum(const float* s_dz, const float* s_h, int np, float* gw, int tid,
-                                                  bool first) {
-  const int o0 = (tid >> 4) * 8, i0 = (tid & 15) * 4;
-  if (o0 >= NOUT || i0 >= NIN) return;
-  float acc[8][4];
+// gw[o][i] (+)= sum_px dz[o][px] * h[i][px], gb[o] (+)= sum_px dz[o][px] over the group's 64 pixels, pixels ascending.
+// Thread (oq, iq) owns the 4 x 4 block o in [4 oq, +4), i in [4 iq, +4); NOQ output quads are live (7 for the head).
+template <int NOQ>
+__device__ __forceinline__ void wgrad_tile(const float* s_dz, const float* s_h, float* gw, float* gb, int nout, bool first,
+                                           int tid) {
+  const int oq = tid >> 4, iq = tid & 15;
+  if (oq >= NOQ) return;
+  float acc[4][4], bs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 #pragma unroll 2
-  for (int q = 0; q < np; ++q) {
-    const float4 d0 = *reinterpret_cast<const float4*>(s_dz + q * TP + o0);
-    const float4 d1 = *reinterpret_cast<const float4*>(s_dz + q * TP + o0 + 4);
-    const float4 hv = *reinterpret_cast<const float4*>(s_h + q * TP + i0);
-    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+  for (int g = 0; g < GP / 4; ++g) {
+    float4 d[4], h[4];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a) d[a] = *reinterpret_cast<const float4*>(s_dz + tile_off(4 * oq + a, g));
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dd[a], hh[b], acc[a][b]);
-  }
+    for (int b = 0; b < 4; ++b) h[b] = *reinterpret_cast<const float4*>(s_h + tile_off(4 * iq + b, g));
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (o0 + a < NOUT && i0 + b < NIN) {   // this block's partial record: the same thread owns an entry for every group
-        float* g = gw + (o0 + a) * NIN + i0 + b;
-        *g = first ? acc[a][b] : *g + acc[a][b];
+      for (int b = 0; b < 4; ++b) {
+        float t = acc[a][b];
+        t = fmaf(d[a].x, h[b].x, t);
+        t = fmaf(d[a].y, h[b].y, t);
+        t = fmaf(d[a].z, h[b].z, t);
+        t = fmaf(d[a].w, h[b].w, t);
+        acc[a][b] = t;
       }
-}
-
-// gb[o] += sum_q dz[q][o]
-template <int NOUT>
-__device__ __forceinline__ void block_bias_accum(const float* s_dz, int np, float* gb, int tid, bool first) {
-  if (tid < NOUT) {
-    float t = 0.f;
-    for (int q = 0; q < np; ++q) t += s_dz[q * TP + tid];
-    gb[tid] = first ? t : gb[tid] + t;
+      if (iq == 0) bs[a] = (((bs[a] + d[a].x) + d[a].y) + d[a].z) + d[a].w;
+    }
+  }
+  // this block's partial record: every entry is owned by one thread, for every group
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int o = 4 * oq + a;
+    if (o >= nout) continue;
+    float4* g4 = reinterpret_cast<float4*>(gw + o * BH + 4 * iq);
+    float4 v = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    if (!first) {
+      const float4 old = *g4;
+      v = make_float4(old.x + v.x, old.y + v.y, old.z + v.z, old.w + v.w);
+    }
+    *g4 = v;
+    if (iq == 0) gb[o] = first ? bs[a] : gb[o] + bs[a];
   }
 }
 
-__global__ void __launch_bounds__(PB)
+// dh[px][i] = sum_{o < NO} dz[o][px] * w[o][i] (w = [out][in] as stored, o ascending) for px in [4 tx, +4), i in [4 ti, +4)
+template <int NO>
+__device__ __forceinline__ void dgrad_tile(const float* s_dz, const float* s_w, int tx, int ti, float (&acc)[4][4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+  for (int o = 0; o < NO; ++o) {
+    const float4 d = *reinterpret_cast<const float4*>(s_dz + tile_off(o, tx));
+    const float4 w = *reinterpret_cast<const float4*>(s_w + o * BH + 4 * ti);
+    const float dd[4] = {d.x, d.y, d.z, d.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ww[b], dd[a], acc[a][b]);
+  }
+}
+
+// ReLU backward of a dgrad tile against the layer's input activation (still in s_h): keeps the gradient where h > 0
+__device__ __forceinline__ void relu_mask(const float* s_h, int tx, int ti, float (&acc)[4][4]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const float4 h = *reinterpret_cast<const float4*>(s_h + tile_off(4 * ti + b, tx));
+    acc[0][b] = h.x > 0.f ? acc[0][b] : 0.f;
+    acc[1][b] = h.y > 0.f ? acc[1][b] : 0.f;
+    acc[2][b] = h.z > 0.f ? acc[2][b] : 0.f;
+    acc[3][b] = h.w > 0.f ? acc[3][b] : 0.f;
+  }
+}
+
+constexpr int BLUR_BWD_SMEM_FLOATS = 2 * BH * BH + 28 * BH + 2 * BH * GP + 3 * GP + 2 * GP;
+
+// (three blocks of 8 warps per SM: the kernel is bound by the latency of its dependent phases, not by a pipe)
+__global__ void __launch_bounds__(BT, 3)
 blur_bwd_kernel(const float* __restrict__ coords, const long long* __restrict__ coord_idx,
                 const float* __restrict__ focus, BlurParams bp, float* __restrict__ part, int rec_floats, int B, int HW,
                 int N, float sy, float sx, float offset_size, const float* __restrict__ kout,
                 const float* __restrict__ hid, const float* __restrict__ dkw, const float* __restrict__ duv) {
   extern __shared__ __align__(16) float sm[];
-  // The weight matrices are read straight from global memory: every thread of a warp reads the same row element at
-  // the same time (one broadcast load through L1), and keeping the 39 KB out of shared memory brings a block down to
-  // 71 KB, so that a block fits next to a CTA of the weight-gradient GEMM this kernel runs concurrently with.
-  const float* __restrict__ s_w2 = bp.w2;    // [64][64] (out, in) as stored
-  const float* __restrict__ s_w3 = bp.w3;    // [64][64]
-  const float* __restrict__ s_w4 = bp.w4;    // [27][64]
-  float* s_dz = sm;                    // [PB][TP]  current layer's d(pre-activation)
-  float* s_h = s_dz + PB * TP;         // [PB][TP]  that layer's input activation
-  float* s_red = s_h + PB * TP;        // [PB]
-  int* s_fr = reinterpret_cast<int*>(s_red + PB);   // [PB]
-  const int tid = threadIdx.x;
-  // Persistent: ONE block per SM walks the 128-pixel groups, so that this kernel occupies 71 KB and 4 warps of every SM
-  // and the weight-gradient GEMM's CTA (145 KB) fits beside it.  The block adds its groups into ONE partial record
-  // (every entry is owned by one thread, groups in order): the second pass sums gridDim.x records, not B / 128.
-  const int ngroups = (B + PB - 1) / PB;
+  float* s_w2 = sm;                    // [64 out][64 in] as stored
+  float* s_w3 = s_w2 + BH * BH;        // [64][64]
+  float* s_w4 = s_w3 + BH * BH;        // [28][64] (row 27 zero)
+  float* s_dz = s_w4 + 28 * BH;        // tile: current layer's d(pre-activation) [out][pixel]
+  float* s_h = s_dz + BH * GP;         // tile: that layer's input activation [in][pixel]
+  float* s_x = s_h + BH * GP;          // [3][64]: focus, y, x of the group's pixels
+  float* s_df = s_x + 3 * GP;          // [64] d loss / d focus per pixel
+  int* s_fr = reinterpret_cast<int*>(s_df + GP);   // [64] frame of the pixel (-1 past the end)
+  const int tid = threadIdx.x, tx = tid & 15, ti = tid >> 4;
+  for (int i = tid; i < BH * BH; i += BT) {
+    s_w2[i] = bp.w2[i];
+    s_w3[i] = bp.w3[i];
+  }
+  for (int i = tid; i < 28 * BH; i += BT) s_w4[i] = (i < BO * BH) ? bp.w4[i] : 0.f;
+  // Persistent: at most three blocks per SM (72 KB of shared memory each) walk the 64-pixel groups and each adds its
+  // groups into ONE partial record, every entry owned by one thread, groups in order: the second pass sums gridDim.x
+  // records.
+  const int ngroups = (B + GP - 1) / GP;
   float* rec = part + (size_t)blockIdx.x * rec_floats;
 #pragma unroll 1
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-  const bool first = grp == (int)blockIdx.x;
-
-  const int p0 = grp * PB;
-  const int p = p0 + tid;
-  const bool valid = p < B;
-  int np = B - p0;
-  if (np > PB) np = PB;
-  float* my_dz = s_dz + tid * TP;
-  float* my_h = s_h + tid * TP;
-
-  // ---- d(logits) of the head ----
-  float dlog[28];
-  dlog[27] = 0.f;
-  if (valid) {
-    float w[KT], gsum = 0.f;
+    const bool first = grp == (int)blockIdx.x;
+    const int p0 = grp * GP;
+    // ---- d(logits) of the head: softmax backward (warps 0-1, one pixel per thread), tanh backward of the offsets ----
+    {
+      const int px = tid & 63, prt = tid >> 6;
+      const int p = p0 + px;
+      const bool valid = p < B;
+      if (prt == 0) {
+        float w[KT], d[KT], gsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      w[k] = kout[(size_t)k * B + p];
-      dlog[k] = dkw[(size_t)k * B + p];
-      gsum = fmaf(dlog[k], w[k], gsum);
+        for (int k = 0; k < KT; ++k) {
+          w[k] = valid ? kout[(size_t)k * B + p] : 0.f;
+          d[k] = valid ? dkw[(size_t)k * B + p] : 0.f;
+          gsum = fmaf(d[k], w[k], gsum);
+        }
+#pragma unroll
+        for (int k = 0; k < KT; ++k) s_dz[tile_at(k, px)] = w[k] * (d[k] - gsum);
+        s_dz[tile_at(BO, px)] = 0.f;
+        const int pc = valid ? p : (B - 1);
+        const int fr = (int)(coord_idx[pc] / HW);
+        s_x[px] = focus[fr];
+        s_x[GP + px] = coords[3 * pc + 1];
+        s_x[2 * GP + px] = coords[3 * pc + 2];
+        s_fr[px] = valid ? fr : -1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int o = KT + (prt - 1) * 6 + j;
+          const int k = (o - KT) % KT, isx = o >= 2 * KT;
+          float v = 0.f;
+          if (valid && k != KT / 2) {   // the centre tap is overwritten with the raw coords (training.py:120)
+            const float d = duv[2 * ((size_t)k * B + p) + isx];
+            const float t = kout[(size_t)o * B + p];
+            v = d * (isx ? sx : sy) * offset_size * (1.f - t * t);
+          }
+          s_dz[tile_at(o, px)] = v;
+        }
+      }
     }
-#pragma unroll
-    for (int k = 0; k < KT; ++k) dlog[k] = w[k] * (dlog[k] - gsum);   // softmax backward
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      const float2 d = *reinterpret_cast<const float2*>(duv + 2 * ((size_t)k * B + p));
-      const float ty = kout[(size_t)(KT + k) * B + p], tx = kout[(size_t)(2 * KT + k) * B + p];
-      const bool centre = (k == KT / 2);   // centre tap is overwritten with the raw coords (training.py:120)
-      dlog[KT + k] = centre ? 0.f : d.x * sy * offset_size * (1.f - ty * ty);
-      dlog[2 * KT + k] = centre ? 0.f : d.y * sx * offset_size * (1.f - tx * tx);
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < BO; ++k) dlog[k] = 0.f;
-  }
-
-  // ---- layer 4 (64 -> 27): dW4, db4, dh3 ----
-#pragma unroll
-  for (int o = 0; o < 28; o += 4) *reinterpret_cast<float4*>(my_dz + o) = make_float4(dlog[o], dlog[o + 1], dlog[o + 2], dlog[o + 3]);
-#pragma unroll
-  for (int o = 28; o < 32; o += 4) *reinterpret_cast<float4*>(my_dz + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-  float hcur[BH];   // post-ReLU activation of the layer whose pre-activation gradient is being formed
-#pragma unroll
-  for (int i = 0; i < BH; ++i) hcur[i] = valid ? hid[(size_t)(2 * BH + i) * B + p] : 0.f;
-#pragma unroll
-  for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_h + i) = make_float4(hcur[i], hcur[i + 1], hcur[i + 2], hcur[i + 3]);
-  __syncthreads();
-  block_outer_accum<BO, BH>(s_dz, s_h, np, rec + BR_W4, tid, first);
-  block_bias_accum<BO>(s_dz, np, rec + BR_B4, tid, first);
-  float dh[BH];
-#pragma unroll
-  for (int i = 0; i < BH; ++i) dh[i] = 0.f;
-#pragma unroll
-  for (int o = 0; o < BO; ++o) {
-    const float d = dlog[o];
-    const float* wr = s_w4 + o * BH;
-#pragma unroll
-    for (int i = 0; i < BH; ++i) dh[i] = fmaf(wr[i], d, dh[i]);
-  }
-  __syncthreads();
-
-  // ---- layers 3 and 2 (64 -> 64) ----
-#pragma unroll 1
-  for (int l = 2; l >= 1; --l) {
-    float dz[BH];
-#pragma unroll
-    for (int i = 0; i < BH; ++i) dz[i] = (hcur[i] > 0.f) ? dh[i] : 0.f;   // ReLU backward
-#pragma unroll
-    for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_dz + i) = make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
-    // input activation of layer l+1 (0-based hidden index l-1)
-#pragma unroll
-    for (int i = 0; i < BH; ++i) hcur[i] = valid ? hid[(size_t)((l - 1) * BH + i) * B + p] : 0.f;
-#pragma unroll
-    for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_h + i) = make_float4(hcur[i], hcur[i + 1], hcur[i + 2], hcur[i + 3]);
+    tile_from_global(s_h, hid + (size_t)2 * BH * B, BH, p0, B, tid);
     __syncthreads();
-    float* gw = rec + ((l == 2) ? BR_W3 : BR_W2);
-    float* gb = rec + ((l == 2) ? BR_B3 : BR_B2);
-    const float* sw = (l == 2) ? s_w3 : s_w2;
-    block_outer_accum<BH, BH>(s_dz, s_h, np, gw, tid, first);
-    block_bias_accum<BH>(s_dz, np, gb, tid, first);
-#pragma unroll
-    for (int i = 0; i < BH; ++i) dh[i] = 0.f;
-#pragma unroll 4
-    for (int o = 0; o < BH; ++o) {
-      const float d = my_dz[o];
-      const float* wr = sw + o * BH;
-#pragma unroll
-      for (int i = 0; i < BH; ++i) dh[i] = fmaf(wr[i], d, dh[i]);
-    }
-    __syncthreads();
-  }
 
-  // ---- layer 1 (3 -> 64): dW1, db1, d focus ----
-  const int pc = valid ? p : (B - 1);
-  const float in0 = focus[(int)(coord_idx[pc] / HW)], in1 = coords[3 * pc + 1], in2 = coords[3 * pc + 2];
-  float dfocus = 0.f;
-  {
-    float dz[BH];
-#pragma unroll
-    for (int i = 0; i < BH; ++i) {
-      dz[i] = (valid && hcur[i] > 0.f) ? dh[i] : 0.f;
-      dfocus = fmaf(bp.w1[i * 3], dz[i], dfocus);
-    }
-#pragma unroll
-    for (int i = 0; i < BH; i += 4) *reinterpret_cast<float4*>(my_dz + i) = make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
-  }
-  *reinterpret_cast<float4*>(my_h) = make_float4(in0, in1, in2, 0.f);
-  __syncthreads();
-  block_outer_accum<BH, 3>(s_dz, s_h, np, rec + BR_W1, tid, first);
-  block_bias_accum<BH>(s_dz, np, rec + BR_B1, tid, first);
-  // focus gradient: per-frame gather over the block's pixels in order (training.py:104-108 backward; no atomics)
-  s_red[tid] = dfocus;
-  s_fr[tid] = valid ? (int)(coord_idx[p] / HW) : -1;
-  __syncthreads();
-  for (int f0 = 0; f0 < N; f0 += PB) {
-    const int f = f0 + tid;
-    if (f < N) {
+    float acc[4][4];
+    // ---- layer 4 (64 -> 27): dW4, db4, dh3 ----
+    wgrad_tile<7>(s_dz, s_h, rec + BR_W4, rec + BR_B4, BO, first, tid);
+    dgrad_tile<BO>(s_dz, s_w4, tx, ti, acc);
+    relu_mask(s_h, tx, ti, acc);
+    __syncthreads();
+    store_tile<false>(s_dz, tx, ti, acc);
+    tile_from_global(s_h, hid + (size_t)BH * B, BH, p0, B, tid);
+    __syncthreads();
+    // ---- layers 3 and 2 (64 -> 64) ----
+    wgrad_tile<16>(s_dz, s_h, rec + BR_W3, rec + BR_B3, BH, first, tid);
+    dgrad_tile<BH>(s_dz, s_w3, tx, ti, acc);
+    relu_mask(s_h, tx, ti, acc);
+    __syncthreads();
+    store_tile<false>(s_dz, tx, ti, acc);
+    tile_from_global(s_h, hid, BH, p0, B, tid);
+    __syncthreads();
+    wgrad_tile<16>(s_dz, s_h, rec + BR_W2, rec + BR_B2, BH, first, tid);
+    dgrad_tile<BH>(s_dz, s_w2, tx, ti, acc);
+    relu_mask(s_h, tx, ti, acc);
+    __syncthreads();
+    store_tile<false>(s_dz, tx, ti, acc);
+    __syncthreads();
+    // ---- layer 1 (3 -> 64): dW1, db1, d focus ----
+    {
+      const int o = tid >> 2, c = tid & 3;
       float t = 0.f;
-      for (int q = 0; q < PB; ++q)
-        if (s_fr[q] == f) t += s_red[q];
+#pragma unroll 4
+      for (int g = 0; g < GP / 4; ++g) {
+        const float4 d = *reinterpret_cast<const float4*>(s_dz + tile_off(o, g));
+        if (c < 3) {
+          const float4 xv = *reinterpret_cast<const float4*>(s_x + c * GP + 4 * g);
+          t = fmaf(d.x, xv.x, t);
+          t = fmaf(d.y, xv.y, t);
+          t = fmaf(d.z, xv.z, t);
+          t = fmaf(d.w, xv.w, t);
+        } else {
+          t = (((t + d.x) + d.y) + d.z) + d.w;
+        }
+      }
+      float* dst = (c < 3) ? (rec + BR_W1 + o * 3 + c) : (rec + BR_B1 + o);
+      *dst = first ? t : *dst + t;
+    }
+    if (tid < GP) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int o = 0; o < BH; ++o) t = fmaf(__ldg(bp.w1 + o * 3), s_dz[tile_at(o, tid)], t);
+      s_df[tid] = t;
+    }
+    __syncthreads();
+    // focus gradient: per-frame gather over the group's pixels in order (training.py:104-108 backward; no atomics)
+    for (int f = tid; f < N; f += BT) {
+      float t = 0.f;
+      for (int q = 0; q < GP; ++q)
+        if (s_fr[q] == f) t += s_df[q];
       rec[BR_FOCUS + f] = first ? t : rec[BR_FOCUS + f] + t;
     }
-  }
-  __syncthreads();   // the next group rewrites the shared tiles
+    __syncthreads();   // the next group rewrites the shared tiles
   }
 }
 
@@ -741,11 +824,11 @@ extern "C" int neucam_blur_fwd(const float* coords, const int64_t* coord_idx, co
   NC_CHECK_ARG(K == KT && B > 0 && N > 0 && H > 1 && W > 1);
   BlurParams bp{blur_params[0], blur_params[1], blur_params[2], blur_params[3],
                 blur_params[4], blur_params[5], blur_params[6], blur_params[7]};
-  const size_t smem = sizeof(float) * (2 * BH * BH + BH * 28 + BH * 4 + 64 + 64 + 28 + BH * PB);
+  const size_t smem = sizeof(float) * BLUR_FWD_SMEM_FLOATS;
   int rc = nchost::ensure_dyn_smem((const void*)blur_fwd_kernel, (int)smem);
   if (rc) return rc;
-  const int grid = (B + PB - 1) / PB;
-  blur_fwd_kernel<<<grid, PB, smem, (cudaStream_t)stream>>>(
+  const int grid = (B + GP - 1) / GP;
+  blur_fwd_kernel<<<grid, BT, smem, (cudaStream_t)stream>>>(
       coords, (const long long*)coord_idx, focus, bp, B, H * W, 2.f / (H - 1), 2.f / (W - 1), offset_size, uv,
       kout, hid);
   NC_CHECK_CUDA(cudaGetLastError());
@@ -763,15 +846,13 @@ extern "C" int neucam_blur_bwd(const float* coords, const int64_t* coord_idx, co
   NC_CHECK_WS(ws, ws_bytes, nchost::ws_bytes_blur_bwd(B, N));
   BlurParams bp{blur_params[0], blur_params[1], blur_params[2], blur_params[3],
                 blur_params[4], blur_params[5], blur_params[6], blur_params[7]};
-  const size_t smem = sizeof(float) * (2 * PB * TP + 2 * PB);
+  const size_t smem = sizeof(float) * BLUR_BWD_SMEM_FLOATS;
   int rc = nchost::ensure_dyn_smem((const void*)blur_bwd_kernel, (int)smem);
   if (rc) return rc;
-  rc = nchost::prefer_max_smem_carveout((const void*)blur_bwd_kernel);   // shares SMs with the weight-gradient GEMM
-  if (rc) return rc;
-  const int grid = (B + PB - 1) / PB;      // pixel groups; one partial record per launched block
+  const int grid = (B + GP - 1) / GP;      // pixel groups; one partial record per launched block
   const int rec = nchost::ws_rec_blur_bwd(N);
-  const int launch_blocks = grid < nchost::sm_count() ? grid : nchost::sm_count();
-  blur_bwd_kernel<<<launch_blocks, PB, smem, (cudaStream_t)stream>>>(
+  const int launch_blocks = grid < 3 * nchost::sm_count() ? grid : 3 * nchost::sm_count();
+  blur_bwd_kernel<<<launch_blocks, BT, smem, (cudaStream_t)stream>>>(
       coords, (const long long*)coord_idx, focus, bp, reinterpret_cast<float*>(ws), rec, B, H * W, N, 2.f / (H - 1),
       2.f / (W - 1), offset_size, kout, hid, dkw, duv);
   NC_CHECK_CUDA(cudaGetLastError());

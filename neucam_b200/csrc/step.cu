@@ -1,7 +1,8 @@
 // step.cu -- neucam_step_fwd_bwd: the whole static training step (training.py:95-270 for the multi-focus /
 // multi-exposure model set) enqueued from ONE C call.  It composes the library's own entry points in the order the
-// reference's autograd graph dictates; the only host logic here is stream fork / join for the two independent tails
-// of the backward (head weight gradient || blur-MLP backward).
+// reference's autograd graph dictates, all on the caller's stream.  (Running the blur-MLP backward on a second stream
+// under the weight-gradient GEMM was measured and dropped: the SIMT warps delay the GEMM's single-thread issue paths by
+// more than they hide -- 569 us together vs 455 + ~60 us in sequence, profiles/r2_findings.md.)
 #include "host_util.h"
 #include <cuda_fp16.h>
 
@@ -12,26 +13,6 @@ __global__ void __launch_bounds__(256) coords_to_uv_kernel(const float* __restri
                                                            float* __restrict__ uv) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < B) *reinterpret_cast<float2*>(uv + 2 * p) = make_float2(coords[3 * p + 1], coords[3 * p + 2]);
-}
-
-// fork / join events, one pair per device, created on first use and kept for the life of the process (events that
-// take part in a stream capture must outlive it)
-struct ForkJoin {
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-int fork_join_events(ForkJoin** out) {
-  static ForkJoin ev[nchost::MAX_DEVICES];
-  static std::mutex mu;
-  int dev = 0;
-  NC_CHECK_CUDA(cudaGetDevice(&dev));
-  NC_CHECK_ARG(dev >= 0 && dev < nchost::MAX_DEVICES);
-  std::lock_guard<std::mutex> g(mu);
-  if (ev[dev].fork == nullptr) {
-    NC_CHECK_CUDA(cudaEventCreateWithFlags(&ev[dev].fork, cudaEventDisableTiming));
-    NC_CHECK_CUDA(cudaEventCreateWithFlags(&ev[dev].join, cudaEventDisableTiming));
-  }
-  *out = &ev[dev];
-  return 0;
 }
 
 #define NC_TRY(expr)         \
@@ -56,7 +37,7 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
   const int phases = a->phases == 0 ? 3 : a->phases;
   NC_CHECK_ARG((phases & ~3) == 0);
 
-  ForkJoin* fj = nullptr;
+  (void)side_stream;   // reserved: every kernel of the step runs on `stream` (see the header)
   if (phases & NEUCAM_STEP_TO_HIDDEN_WGRAD) {
   if (a->zero_ptr != nullptr && a->zero_bytes > 0) NC_CHECK_CUDA(cudaMemsetAsync(a->zero_ptr, 0, a->zero_bytes, st));
   NC_CHECK_CUDA(cudaMemsetAsync(a->sums, 0, 4 * sizeof(float), st));
@@ -83,20 +64,11 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
   // S14: scene MLP backward (training.py:270)
   NC_TRY(neucam_sine_mlp_bwd(a->uv, Q, a->w0, a->b0, a->wT_hid16, a->w4T16, a->out_dim, a->dy, a->phase16, a->scale,
                              a->dz16, a->duv, a->g_w0, a->g_b0, a->ws, a->ws_bytes, stream));
-  // The blur-MLP backward (FMA-pipe / latency bound, 71 KB of shared memory per block) forks to the side stream here and
-  // runs UNDER the hidden weight gradients (tensor-pipe bound, 145 KB per CTA): both fit on an SM at the same time.
-  if (has_blur) {
-    void* blur_stream = stream;
-    if (side_stream != nullptr && side_stream != stream) {
-      NC_TRY(fork_join_events(&fj));
-      NC_CHECK_CUDA(cudaEventRecord(fj->fork, st));
-      NC_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, fj->fork, 0));
-      blur_stream = side_stream;
-    }
+  // blur-MLP backward (needs d(uv) of the chain; training.py:99-126 backward)
+  if (has_blur)
     NC_TRY(neucam_blur_bwd(a->coords, a->coord_idx, a->focus, a->blur_params, a->g_blur, a->g_focus, a->B, a->K, a->N,
                            a->H, a->W, a->offset_size, a->kout, a->hid, a->dkw, a->duv, a->ws_side, a->ws_side_bytes,
-                           blur_stream));
-  }
+                           stream));
   NC_TRY(neucam_sine_mlp_wgrad(a->dz16, a->act16, Q, a->scale, a->g_w[0], a->g_b[0], a->g_w[1], a->g_b[1], a->g_w[2],
                                a->g_b[2], a->ws, a->ws_bytes, stream));
   }
@@ -105,11 +77,5 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
   const int64_t ph_stride = ((Q + 127) / 128) * 128 * 512;
   const uint16_t* phase3 = (const uint16_t*)a->phase16 + (size_t)2 * ph_stride;
   NC_TRY(neucam_sine_mlp_head_wgrad(phase3, a->dy, a->out_dim, Q, a->g_w4, a->ws, a->ws_bytes, stream));
-  if (has_blur && side_stream != nullptr && side_stream != stream) {
-    // join the side stream (forked in the first phase, possibly by an earlier call with the same streams)
-    NC_TRY(fork_join_events(&fj));
-    NC_CHECK_CUDA(cudaEventRecord(fj->join, (cudaStream_t)side_stream));
-    NC_CHECK_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
-  }
   return 0;
 }

@@ -204,10 +204,7 @@ hidden_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const WgradParams p)
 //   barriers: full[s] (leader: both CTAs' TMA bytes), mma_done[s] (tcgen05.commit, both CTAs), empty[s] (the CTA's four
 //   bias warps have read the A tile): the producer refills a stage only after the MMAs AND the bias pass are done with it.
 // ------------------------------------------------------------------------------------------------------------------
-#ifndef WIDE_WGRAD_STAGES
-#define WIDE_WGRAD_STAGES 3
-#endif
-constexpr int WNSTAGE = WIDE_WGRAD_STAGES;   // 3 x 48 KB = 144 KB: leaves room for a 71 KB blur_bwd block on the same SM
+constexpr int WNSTAGE = 4;
 constexpr uint32_t WA_STAGE = 2 * ATOM_BYTES;             // 64 k x 128 dz columns
 constexpr uint32_t WB_STAGE = 4 * ATOM_BYTES;             // 64 k x 256 activation columns (this CTA's halves of both N = 256 MMAs)
 constexpr uint32_t WSTAGE_BYTES = WA_STAGE + WB_STAGE;

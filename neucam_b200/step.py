@@ -5,7 +5,8 @@
     S7      neucam_sine_mlp_fwd    scene sine-MLP on all K*B taps (tcgen05)
     S9-S12  neucam_psf_crf_loss    PSF sum, exposure, CRF, image_mse (+gamma/mask), ue_loss; and their backward
     S14     neucam_sine_mlp_bwd    dgrad chain + layer-0 wgrad (tcgen05)
-            neucam_sine_mlp_wgrad  hidden-layer weight gradients (tcgen05 split-K)  ||  neucam_blur_bwd (side stream)
+            neucam_blur_bwd        blur MLP / focus backward
+            neucam_sine_mlp_wgrad  hidden-layer weight gradients (tcgen05 split-K)
             neucam_sine_mlp_head_wgrad
             [all-reduce]           one NCCL sum over the flat gradient buffer when world_size > 1
             neucam_adam_*          fused Adam over the flat buffers + fp16 operand re-pack
@@ -230,9 +231,8 @@ class FusedTrainStep:
         self.sums = self.scalars[0:4]
         self.absmax_bits = self.scalars[4:5]
         self.scale = torch.ones(1, device=dev)
-        self._side = torch.cuda.Stream(device=self.device)
-        # reduction workspaces (fixed-order second pass instead of float atomics): the main stream's calls run back to
-        # back and share one; the blur backward runs concurrently on the side stream and has its own
+        # reduction workspaces (fixed-order second pass instead of float atomics): the calls run back to back and share
+        # one; the blur backward keeps its own (one record per block of a grid sized to the machine)
         N = self.shape[0]
         main_bytes = max(ops.reduce_ws_bytes(ops.WS_SINE_BWD), ops.reduce_ws_bytes(ops.WS_WGRAD),
                          ops.reduce_ws_bytes(ops.WS_HEAD_WGRAD), ops.reduce_ws_bytes(ops.WS_PSF_CRF, B, N))
@@ -381,7 +381,7 @@ class FusedTrainStep:
         self._sync_operands()
         if events is None:
             # the product path: the whole forward + backward from ONE C call (neucam_step_fwd_bwd)
-            ops.step_fwd_bwd(self._step_args(use_mask), self._side if self.has_blur else None)
+            ops.step_fwd_bwd(self._step_args(use_mask), None)
             return
 
         # per-kernel path (bench.py's in-step kernel timing; tests pin it to the one-call path): the same entry points
@@ -419,21 +419,14 @@ class FusedTrainStep:
         timed("sine_chain_bwd", lambda: ops.sine_mlp_bwd(
             uv, self.aw[0].data, self.ab[0].data, self.wT16, self.w4T16, dyf, self.phase16, self.scale,
             self.dz16, self.aw[0].grad, self.ab[0].grad, duv=self.duv.view(-1, 2), ws=self.ws_main))
-        # the FMA-pipe-bound blur backward forks to the side stream and runs UNDER the tensor-bound weight-gradient GEMM
-        # (71 KB + 145 KB of shared memory: both fit on an SM); the head wgrad follows on the main stream; then join
-        main = torch.cuda.current_stream(self.device)
         if self.has_blur:
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
-                             self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw,
-                             self.duv, ws=self.ws_side)
+            ops.blur_bwd(self.coords, self.coord_idx, self.focus.data, [p.data for p in self.blur_p], self.blur_g,
+                         self.focus.grad, self.shape, K, float(o.offset_size), self.kout, self.hid, self.dkw,
+                         self.duv, ws=self.ws_side)
         timed("hidden_wgrad", lambda: ops.sine_mlp_wgrad(
             self.dz16, self.act16, self.scale, [self.aw[i].grad for i in (1, 2, 3)],
             [self.ab[i].grad for i in (1, 2, 3)], ws=self.ws_main))
         ops.sine_mlp_head_wgrad(self.phase16, dyf, self.aw[4].grad, ws=self.ws_main)
-        if self.has_blur:
-            main.wait_stream(self._side)
 
     def reduce_gradients(self):
         """The step's only collective: SUM of the flat gradient buffer across the data-parallel ranks."""
@@ -463,10 +456,9 @@ class FusedTrainStep:
         a = self._step_args(use_mask)
         g = self.params.grad
         cut = self._bucket_split()
-        side = self._side if self.has_blur else None     # the blur backward forks in phase 1, joins in phase 2
-        ops.step_fwd_bwd(a, side, phases=ops.STEP_TO_HIDDEN_WGRAD)
+        ops.step_fwd_bwd(a, None, phases=ops.STEP_TO_HIDDEN_WGRAD)
         w1 = dist.all_reduce(g[:cut], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        ops.step_fwd_bwd(a, side, phases=ops.STEP_TAILS)
+        ops.step_fwd_bwd(a, None, phases=ops.STEP_TAILS)
         w2 = dist.all_reduce(g[cut:], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         w1.wait()
         w2.wait()
