@@ -153,6 +153,14 @@ int neucam_relu_mlp_head_wgrad(const void* h16, const void* h_lo16, const float*
  *   (per stage: st_layer, st_kb 0..3 | 4 = encoded-input block, st_lo 0 hi / 1 lo) and wT_stages in
  *   neucam_relu_mlp_bwd's fixed order (NULL to skip). */
 int neucam_relu_mlp_encode(const float* x, int64_t Q, int num_freq, void* feat16, void* stream);
+/* neucam_relu_mlp_head_prep: the pointwise front of a ReLU MLP's backward in one pass over [Q,out_dim]: dpre = dy *
+ *   d(out)/d(pre) from the forward output y (out_kind 1 tanh: 1 - y^2, 2 sigmoid: y (1 - y); 0: dpre = dy, in which
+ *   case y and dpre are not touched and may be NULL -- the scene network's linear head uses it that way); ACCUMULATES
+ *   db_last [out_dim] += sum_r dpre[r,:]; writes *scale_out = the power-of-two loss scale of max|dpre| (as
+ *   neucam_loss_scale with `target`).  scratch_bits: 4 bytes.  Workspace: NEUCAM_WS_HEAD_PREP. */
+int neucam_relu_mlp_head_prep(const float* dy, const float* y, int out_dim, int out_kind, int64_t Q, float target,
+                              float* dpre, float* db_last, uint32_t* scratch_bits, float* scale_out, void* ws,
+                              int64_t ws_bytes, void* stream);
 int neucam_relu_mlp_encode_bwd(const float* x, const float* dfeat, int64_t Q, int num_freq, float* dx, void* stream);
 int neucam_relu_mlp_pack(const float* const* w, const int* ld, int L, int E, int S, const uint8_t* st_layer,
                          const uint8_t* st_kb, const uint8_t* st_lo, int with_input_grad, void* w_stages,
@@ -230,6 +238,7 @@ int neucam_layer_blend_bwd(const float* dout, const float* back, const float* fr
  *   tanh(CRF(x + ln2 * expo)).  The backward takes dldr [M,3], writes dx [M,3] and (optionally) dexpo [M], and
  *   ACCUMULATES the 12 parameter gradients (workspace: M/128 records of 1156 floats = NEUCAM_WS_TM with n = M). */
 #define NEUCAM_WS_TM 7
+#define NEUCAM_WS_HEAD_PREP 8 /* neucam_relu_mlp_head_prep (n, aux unused) */
 int neucam_tm_fwd(const float* const* tm_params, int tm_width, const float* x, const float* expo, int64_t M,
                   float* ldr, void* stream);
 int neucam_tm_bwd(const float* const* tm_params, int tm_width, const float* x, const float* expo, const float* dldr,

@@ -226,6 +226,7 @@ inline int64_t ws_bytes_blur_bwd(int64_t B, int N) {   // one record per block: 
 }
 inline int64_t ws_bytes_rigidity(int64_t B) { return ((B + 255) / 256) * 4 * 4; }
 inline int64_t ws_bytes_blend(int64_t KB) { return ((KB + 255) / 256) * 4 * 4; }
+inline int64_t ws_bytes_head_prep() { return (int64_t)(2 * sm_count()) * 4 * 4; }   // one float4 record per block
 
 #define NC_CHECK_WS(ws, ws_bytes, need)                                                                      \
   do {                                                                                                       \

@@ -91,6 +91,7 @@ extern "C" int neucam_reduce_ws_bytes(int kind, int64_t n, int aux, int64_t* byt
     case NEUCAM_WS_BLUR_BWD: b = nchost::ws_bytes_blur_bwd(n, aux); break;
     case NEUCAM_WS_RIGIDITY: b = nchost::ws_bytes_rigidity(n); break;
     case NEUCAM_WS_BLEND: b = nchost::ws_bytes_blend(n); break;
+    case NEUCAM_WS_HEAD_PREP: b = nchost::ws_bytes_head_prep(); break;
     case NEUCAM_WS_TM: b = ((n + 127) / 128) * (int64_t)(nchost::WS_TM_GRADS + 4) * 4; break;
     default: NC_CHECK_ARG(!"unknown workspace kind");
   }

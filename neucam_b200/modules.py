@@ -150,8 +150,10 @@ class _SineMLPFunction(torch.autograd.Function):
         dz = ctx.dz
         dev = uv.device
         dy = dy.contiguous().float()
-        scale = ops.loss_scale_from(dy)
         tg = ctx.grad_targets
+        # head bias gradient db4 += dy.sum(0) and the loss scale of max|dy| from one pass over dy
+        db4 = tg[9] if tg is not None else torch.zeros(dy.shape[1], dtype=torch.float32, device=dev)
+        _, scale = ops.relu_head_prep(dy, None, 0, db4)
         if tg is not None:
             # the step owns preallocated gradient buffers: every kernel below ACCUMULATES, so let them add straight
             # into param.grad and hand autograd nothing for the parameters
@@ -166,9 +168,7 @@ class _SineMLPFunction(torch.autograd.Function):
         ops.sine_mlp_wgrad(dz, act, scale, dws, dbs)
         ops.sine_mlp_head_wgrad(cos, dy, dw4)
         if tg is not None:
-            tg[9].add_(dy.sum(0))
             return (None, duv) + (None,) * 10
-        db4 = dy.sum(0)
         return None, duv, dw0, db0, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2], dw4, db4
 
 

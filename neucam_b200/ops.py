@@ -22,7 +22,7 @@ def num_tiles(Q):
 
 # reduction workspaces (include/neucam_b200.h: NEUCAM_WS_*): every cross-block reduction writes per-block partial
 # records there and sums them in block order -- no float atomics, bit-reproducible results
-WS_SINE_BWD, WS_WGRAD, WS_HEAD_WGRAD, WS_PSF_CRF, WS_BLUR_BWD, WS_RIGIDITY, WS_BLEND, WS_TM = range(8)
+WS_SINE_BWD, WS_WGRAD, WS_HEAD_WGRAD, WS_PSF_CRF, WS_BLUR_BWD, WS_RIGIDITY, WS_BLEND, WS_TM, WS_HEAD_PREP = range(9)
 
 
 def reduce_ws_bytes(kind, n=0, aux=0):
@@ -149,6 +149,23 @@ def loss_scale_from(dy):
                                       _lib.ptr(out[1:]), _lib.ptr(out), _lib.cur_stream())
     _lib.check(rc, "neucam_loss_scale")
     return out[:1]
+
+
+def relu_head_prep(dy, y, out_kind, db_last, ws=None):
+    """dpre = dy * d(out)/d(pre) (out_kind 0 none / 1 tanh / 2 sigmoid, from the forward output y), db_last += dpre.sum(0)
+    and the power-of-two loss scale of max|dpre| in one pass; returns (dpre, scale).  out_kind 0: dpre is dy itself."""
+    _chk_cuda(dy, db_last)
+    Q, out_dim = dy.shape
+    dpre = torch.empty_like(dy) if out_kind != 0 else dy
+    out = torch.empty(2, dtype=torch.float32, device=dy.device)       # [scale, scratch bits]
+    if ws is None:
+        ws = new_ws(WS_HEAD_PREP, device=dy.device)
+    rc = _lib.lib().neucam_relu_mlp_head_prep(_lib.ptr(dy), _lib.ptr(y if out_kind != 0 else None), out_dim,
+                                              int(out_kind), ctypes.c_int64(Q), ctypes.c_float(SCALE_TARGET),
+                                              _lib.ptr(dpre if out_kind != 0 else None), _lib.ptr(db_last),
+                                              _lib.ptr(out[1:]), _lib.ptr(out), *_ws_args(ws), _lib.cur_stream())
+    _lib.check(rc, "neucam_relu_mlp_head_prep")
+    return dpre, out[:1]
 
 
 def _ptr_array(tensors):

@@ -10,7 +10,7 @@ import ctypes
 
 import torch
 
-from . import _lib, ops
+from . import _gradmode, _lib, ops
 
 
 class _BlurTaps(torch.autograd.Function):
@@ -28,6 +28,7 @@ class _BlurTaps(torch.autograd.Function):
         ctx.save_for_backward(coords, coord_idx, focus_flat, kout, hid, *params)
         ctx.cfg = cfg
         ctx.focus_shape = focus.shape
+        ctx.grad_targets = _gradmode.targets_of([focus, *blur_params])
         kw = kout[:K].clone()
         return uv, kw
 
@@ -35,6 +36,12 @@ class _BlurTaps(torch.autograd.Function):
     def backward(ctx, duv, dkw):
         coords, coord_idx, focus_flat, kout, hid, *params = ctx.saved_tensors
         shape, K, offset_size = ctx.cfg
+        tg = ctx.grad_targets
+        if tg is not None:
+            # the step owns preallocated gradient buffers and the kernel ACCUMULATES: add straight into param.grad
+            ops.blur_bwd(coords, coord_idx, focus_flat, params, list(tg[1:]), tg[0].view(-1), shape, K,
+                         float(offset_size), kout, hid, dkw.contiguous(), duv.contiguous())
+            return (None,) * (4 + len(params))
         sizes = [p.numel() for p in params] + [focus_flat.numel()]
         buf = torch.zeros(sum(sizes), device=coords.device)
         parts = torch.split(buf, sizes)
@@ -60,11 +67,20 @@ class _PsfCrfLoss(torch.autograd.Function):
         has_blur = kw is not None
         tm = [p.contiguous() for p in tm_params]
         n_exp = exps.numel() if exps is not None else 0
+        # direct mode (the step owns preallocated gradient buffers, _gradmode): the kernel, which produces every gradient
+        # in its one pass and ACCUMULATES, adds the CRF / exposure gradients straight into param.grad.  That bakes in
+        # d(total)/d(this loss) = 1, which is how the steps that switch the mode on use it (layered.py: the term enters
+        # `total` unweighted); backward then hands dy / dkw on unscaled as well.
+        tg = _gradmode.targets_of(list(tm_params) + ([exps] if exps is not None else []))
         sizes = [p.numel() for p in tm] + [max(n_exp, 1), 4, 4, 1]     # tm grads | dexps | db4 | sums | absmax bits
         buf = torch.zeros(sum(sizes), device=dev)
         parts = torch.split(buf, sizes)
         tm_g = [g.view_as(p) for g, p in zip(parts[:len(tm)], tm)]
         dexps, db4, sums, absmax = parts[len(tm):]
+        if tg is not None:
+            tm_g = list(tg[:len(tm)])
+            if exps is not None:
+                dexps = tg[len(tm)].view(-1)
         dy = torch.empty_like(y)
         dkw = torch.empty_like(kw) if has_blur else None
         scale = torch.empty(1, device=dev)
@@ -76,6 +92,7 @@ class _PsfCrfLoss(torch.autograd.Function):
         ue = sums[1] * float(ue_weight)
         ctx.save_for_backward(dy, dkw, buf)
         ctx.layout = (sizes, [p.shape for p in tm], exps.shape if exps is not None else None)
+        ctx.direct = tg is not None
         ctx.mark_non_differentiable(img, ue)
         return img + ue, img, ue
 
@@ -83,6 +100,8 @@ class _PsfCrfLoss(torch.autograd.Function):
     def backward(ctx, g_total, _g_img, _g_ue):
         dy, dkw, buf = ctx.saved_tensors
         sizes, tm_shapes, exps_shape = ctx.layout
+        if ctx.direct:
+            return (dy, dkw) + (None,) * (8 + len(tm_shapes))
         parts = torch.split(buf * g_total, sizes)          # one launch scales every small gradient
         tm_g = [g.view(shape) for g, shape in zip(parts, tm_shapes)]
         d_exps = parts[len(tm_shapes)][:exps_shape.numel()].view(exps_shape) if exps_shape is not None else None

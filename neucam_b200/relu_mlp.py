@@ -133,14 +133,13 @@ class _ReluMLPFunction(torch.autograd.Function):
         lib = _lib.lib()
         stream = _lib.cur_stream()
         dy = dy.contiguous().float()
-        if out_kind == 1:
-            dpre = dy * (1.0 - y * y)
-        elif out_kind == 2:
-            dpre = dy * y * (1.0 - y)
-        else:
-            dpre = dy
-        dpre = dpre.contiguous()
-        scale = ops.loss_scale_from(dpre)
+        # per-block partial records + fixed-order second pass (no float atomics); one workspace serves every call below,
+        # which run back to back on this stream
+        red_ws = ops.new_ws(ops.WS_WGRAD, device=dev)
+        tg = ctx.grad_targets
+        db_last = tg[2 * H + 1] if tg is not None else torch.zeros(ws[H].shape[0], dtype=torch.float32, device=dev)
+        # dpre = dy * d(out)/d(pre), db_last += dpre.sum(0), loss scale of max|dpre|: one kernel
+        dpre, scale = ops.relu_head_prep(dy, y, out_kind, db_last, red_ws)
         want_dx = ctx.needs_input_grad[0]
         w_last = ws[H].contiguous()
         out_dim = w_last.shape[0]
@@ -161,7 +160,6 @@ class _ReluMLPFunction(torch.autograd.Function):
         # buffers (nothing is then returned for the parameters), else into one zero-filled temporary.
         skip_slot = {l: 1 + i for i, l in enumerate(sorted(skips))}
         enc_numel = (1 + len(skips)) * WID * FEAT
-        tg = ctx.grad_targets
         if tg is not None:
             dw, db = list(tg[0::2]), list(tg[1::2])
             enc = torch.zeros(enc_numel, dtype=torch.float32, device=dev).view(1 + len(skips), WID, FEAT)
@@ -174,9 +172,6 @@ class _ReluMLPFunction(torch.autograd.Function):
             enc = parts[-1].view(1 + len(skips), WID, FEAT)                    # dw_first, dw_skip...
         arr = lambda items: (ctypes.c_void_p * len(items))(*[0 if t is None else t.data_ptr() for t in items])
         ldw = (ctypes.c_int * H)(*[int(w.shape[1]) for w in ws[:H]])
-        # per-block partial records + fixed-order second pass (no float atomics); one workspace serves both calls,
-        # which run back to back on this stream
-        red_ws = ops.new_ws(ops.WS_WGRAD, device=dev)
         rc = lib.neucam_relu_mlp_wgrad(_lib.ptr(dz16[0]), _lib.ptr(lo(dz16)), _lib.ptr(act16[0]), _lib.ptr(lo(act16)),
                                        _lib.ptr(feat16), ctypes.c_int64(Q), H, _lib.ptr(scale), _lib.ptr(enc[0]),
                                        arr([None] + dw[1:H]), ldw, arr(db[:H]),
@@ -189,12 +184,11 @@ class _ReluMLPFunction(torch.autograd.Function):
         _lib.check(rc, "neucam_relu_mlp_head_wgrad")
         fold = lambda e: e[:, :E] + e[:, E:2 * E]      # hi + lo halves of the features
         if tg is not None:
-            db[H].add_(dpre.sum(0))
             dw[0].add_(fold(enc[0]))
             for l, slot in skip_slot.items():
                 dw[l][:, WID:].add_(fold(enc[slot]))
             return (dx, None) + (None,) * (2 * (H + 1))
-        db[H] = dpre.sum(0)
+        db[H] = db_last
         dw[0] = fold(enc[0])
         for l, slot in skip_slot.items():
             dw[l][:, WID:] = fold(enc[slot])
