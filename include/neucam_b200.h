@@ -289,8 +289,9 @@ int neucam_pack_head_weights(const float* w4, int out_dim, void* w4T16, void* st
  * them.  `side_stream` is reserved and may be NULL: every kernel is enqueued on `stream` (running the blur backward
  * beside the weight-gradient GEMM on a second stream was measured slower than the sequence).  Set struct_bytes =
  * sizeof(neucam_step_args). */
-#define NEUCAM_STEP_TO_HIDDEN_WGRAD 1 /* clear, taps, forward, loss, backward chain, blur backward, hidden-layer weight gradients */
-#define NEUCAM_STEP_TAILS 2           /* head weight gradient */
+#define NEUCAM_STEP_TO_HIDDEN_WGRAD 1 /* clear, taps, forward, loss, backward chain, hidden-layer weight gradients */
+#define NEUCAM_STEP_TAILS 2           /* blur-MLP backward, head weight gradient (a whole-step call runs the blur
+                                         backward ahead of the weight-gradient GEMM instead: same results) */
 typedef struct neucam_step_args {
   uint32_t struct_bytes;
   int phases;                   /* 0 or 3 = the whole step; NEUCAM_STEP_* bits select a part, so that a data-parallel

@@ -36,6 +36,7 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
   const int64_t Q = (int64_t)a->K * a->B;
   const int phases = a->phases == 0 ? 3 : a->phases;
   NC_CHECK_ARG((phases & ~3) == 0);
+  const bool whole = phases == 3;
 
   (void)side_stream;   // reserved: every kernel of the step runs on `stream` (see the header)
   if (phases & NEUCAM_STEP_TO_HIDDEN_WGRAD) {
@@ -64,8 +65,9 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
   // S14: scene MLP backward (training.py:270)
   NC_TRY(neucam_sine_mlp_bwd(a->uv, Q, a->w0, a->b0, a->wT_hid16, a->w4T16, a->out_dim, a->dy, a->phase16, a->scale,
                              a->dz16, a->duv, a->g_w0, a->g_b0, a->ws, a->ws_bytes, stream));
-  // blur-MLP backward (needs d(uv) of the chain; training.py:99-126 backward)
-  if (has_blur)
+  // blur-MLP backward (needs d(uv) of the chain; training.py:99-126 backward).  A call that covers the whole step runs
+  // it here; a data-parallel caller that splits the step gets it in the tails, under its all-reduce of the atlas bucket
+  if (has_blur && whole)
     NC_TRY(neucam_blur_bwd(a->coords, a->coord_idx, a->focus, a->blur_params, a->g_blur, a->g_focus, a->B, a->K, a->N,
                            a->H, a->W, a->offset_size, a->kout, a->hid, a->dkw, a->duv, a->ws_side, a->ws_side_bytes,
                            stream));
@@ -73,6 +75,10 @@ extern "C" int neucam_step_fwd_bwd(const neucam_step_args* a, void* stream, void
                                a->g_b[2], a->ws, a->ws_bytes, stream));
   }
   if (!(phases & NEUCAM_STEP_TAILS)) return 0;
+  if (has_blur && !whole)
+    NC_TRY(neucam_blur_bwd(a->coords, a->coord_idx, a->focus, a->blur_params, a->g_blur, a->g_focus, a->B, a->K, a->N,
+                           a->H, a->W, a->offset_size, a->kout, a->hid, a->dkw, a->duv, a->ws_side, a->ws_side_bytes,
+                           stream));
   // a4 = sin(30 z_3) is regenerated from the stored phase of z_3 (third slice of phase16)
   const int64_t ph_stride = ((Q + 127) / 128) * 128 * 512;
   const uint16_t* phase3 = (const uint16_t*)a->phase16 + (size_t)2 * ph_stride;

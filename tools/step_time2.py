@@ -1,0 +1,37 @@
+"""Like tools/step_time.py, but cycling through 8 device-resident batches with the five small copies bench.py does per step."""
+import os, sys, time
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neucam_b200 import harness
+from neucam_b200.step import FusedTrainStep, StepOptions
+import bench
+
+name = sys.argv[1] if len(sys.argv) > 1 else "mfme_blender"
+mode = sys.argv[2] if len(sys.argv) > 2 else "cycle"
+cfg = harness.CONFIGS[name]
+B = harness.pixels_per_step(cfg)
+models = harness.build_static_models(cfg["shape"], cfg["focal_list"], hidden=512, seed=0)
+step = FusedTrainStep(models, cfg["shape"], StepOptions(use_random_gamma=cfg["use_random_gamma"]), B, device="cuda")
+host = bench.make_host_batches(cfg, B, 8, seed=100, pin=True)
+resident = [{k: v.cuda() for k, v in b.items()} for b in host]
+def load(i):
+    b = resident[i % 8]
+    step.coords.copy_(b["coords"].view(-1, 3)); step.coord_idx.copy_(b["coord_idx"].view(-1)); step.img.copy_(b["img"].view(-1, 3))
+    step.gamma_w.copy_(b["gamma_weights"].view(-1)); step.gamma.copy_(b["gamma"])
+load(0)
+step.capture()
+for i in range(5):
+    load(i); step.run_resident()
+torch.cuda.synchronize()
+out = []
+for rep in range(3):
+    time.sleep(0.5)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        if mode == "cycle":
+            load(i)
+        step.run_resident()
+    e1.record(); torch.cuda.synchronize()
+    out.append(e0.elapsed_time(e1) / 20)
+print(name, mode, "ms/step", " ".join(f"{b:.4f}" for b in out))
