@@ -8,8 +8,9 @@ metric : scene-MLP fwd+bwd samples/s (1 sample = one scene-MLP query = one of th
 workload: BASELINE.json configs[1] -- config_mfme_blender.txt in its 9-image 3-focus x 3-exposure form:
           N,H,W = 9,300,450, sample_frac 3.5e-2 -> B = 42 525 px/step, K = 9 taps, Q = 382 725 samples/step,
           blur + focal + exposure + CRF + random-gamma loss + Adam.  Synthetic seeded scene, random-init nets.
-value  : whole-job samples/s, step inputs already resident in HBM (device-timed with CUDA events, max over ranks).
-          A step = forward + backward + (all-reduce) + Adam, replayed from ONE CUDA graph.
+value  : whole-job samples/s, step inputs already resident in HBM (device-timed with CUDA events, max over ranks): the
+          video is attached to the step (attach_dataset) and every step's batch is drawn by the on-device sampler.
+          A step = sampler + forward + backward + (all-reduce) + Adam, the latter four replayed from ONE CUDA graph.
 e2e    : same metric through the public API (FusedTrainStep.step) with pinned HOST batches: the H2D copy of every
           step's inputs and a D2H read of the loss are inside the timed region.
 roofline: the slowest tensor-core kernel, algorithmic FLOPs / CUDA-event time (events around the kernel inside real
@@ -321,8 +322,14 @@ def measure_static(D, cfg, B, global_pixels, steps, warmup, with_kernels=True, k
     step.capture()          # forward + backward + all-reduce + Adam + re-pack as ONE CUDA graph (2 warm-up steps + capture)
     launches_per_step = (ops.launch_count() - n0) // 3
 
+    # device-resident loop = the product's resident-data path: the video lives in HBM (attach_dataset) and every step's
+    # batch is drawn there by the on-device sampler (neucam_sample_batch, one launch; dataio.py:356-393 semantics),
+    # plus the step's random gamma (4 bytes, device to device)
+    scene = harness.SyntheticScene(cfg["shape"], cfg["focal_list"], seed=0)
+    step.attach_dataset(scene.data, gamma_weights=scene.gamma_weights if cfg["use_random_gamma"] else None)
+
     def one_step(i):
-        load_resident(i)
+        step.sample_resident(seed=100 + D.rank, step=i, gamma=resident[i % n_batches]["gamma"])
         step.run_resident()
 
     for i in range(warmup):
@@ -433,7 +440,8 @@ def static_line(D, args, name, cfg, peaks, peak_src, B, global_pixels, scaling, 
                             "NOT larger than L2 -- this small config is partly L2-resident by nature"),
                    "parallelism": f"dp{world}: pixel batch sharded, NCCL all-reduce of the flat gradient captured in the "
                                   "step graph, atlas bucket overlapped with the backward's tails",
-                   "cuda_graph": True},
+                   "cuda_graph": True,
+                   "resident_input": "video in HBM, batch drawn per step by neucam_sample_batch (on-device sampler)"},
         "px_per_s": value / K,
         "tflops_algorithmic": value * FLOP_PER_SAMPLE_FWD_BWD / 1e12,
         "frac_of_tensor_peak_whole_step": value / world * FLOP_PER_SAMPLE_FWD_BWD / 1e12 / step_peak,

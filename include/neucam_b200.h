@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NEUCAM_ABI_VERSION 7
+#define NEUCAM_ABI_VERSION 8
 
 #define NEUCAM_ERR_BAD_ARG (-1)
 #define NEUCAM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point unavailable */

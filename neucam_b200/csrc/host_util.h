@@ -163,24 +163,6 @@ inline int ensure_dyn_smem(const void* func, int bytes) {
   return 0;
 }
 
-// Kernels that are meant to share an SM with another kernel must agree on the SM's L1 / shared-memory split: the
-// carve-out is per-SM state that can only change while the SM is empty, so a kernel that runs with a small carve-out
-// keeps a larger-footprint kernel's CTAs out until its own blocks have drained.  Ask for the maximum.
-inline int prefer_max_smem_carveout(const void* func) {
-  static std::mutex mu;
-  static std::vector<std::pair<const void*, int>> done;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> g(mu);
-  for (auto& e : done)
-    if (e.first == func && e.second == dev) return 0;
-  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return (int)e;
-  done.emplace_back(func, dev);
-  return 0;
-}
-
 // Number of kernels this library has launched (all devices, all streams): bench.py reports it as `gpu_launches`.
 inline std::atomic<long long>& launch_counter() {
   static std::atomic<long long> c{0};

@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "neucam_b200", "libneucam_b200.so")
 KEEP = re.compile(r"^(UTCHMMA|UTCQMMA|UTCBAR|UTMALDG|UTMASTG|UTMAPF|UTMACCTL|LDTM|STTM|UTCATOM|MUFU|HMMA|FFMA|FMUL|F2FP|"
-                  r"LDS|STS|LDG|STG|LDL|STL|ATOM|RED|SYNCS|ELECT|R2UR|BAR|USETMAXREG|UBLKPF|CCTL|MEMBAR|ERRBAR)")
+                  r"LDS|STS|LDG|STG|LDL|STL|ATOM|RED|SYNCS|ELECT|R2UR|BAR|USETMAXREG|UBLKPF|UBLKCP|CCTL|MEMBAR|ERRBAR)")
 
 
 def main():
@@ -36,7 +36,7 @@ def main():
         fam = collections.Counter()
         for op, n in c.items():
             if KEEP.match(op):
-                key = op if op.startswith(("UTC", "UTMA", "LDTM", "STTM", "MUFU")) else op.split(".")[0]
+                key = op if op.startswith(("UTC", "UTMA", "UBLK", "LDTM", "STTM", "MUFU")) else op.split(".")[0]
                 fam[key] += n
         print(f"\n{short}   total {total}")
         for key, n in sorted(fam.items(), key=lambda kv: (-kv[1], kv[0])):
