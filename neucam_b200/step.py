@@ -392,7 +392,8 @@ class FusedTrainStep:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             # ~50 us of GPU idle-spin ahead of the start event: the host enqueues the event pair and the kernel while
             # it runs, so the bracket holds the kernel and not the host's launch latency behind a short predecessor
-            torch.cuda._sleep(100000)
+            if hasattr(torch.cuda, "_sleep"):
+                torch.cuda._sleep(100000)
             e0.record()
             out = fn()
             e1.record()
