@@ -97,7 +97,9 @@ int neucam_sine_mlp_wgrad(const void* dz16, const void* act16, int64_t Q, const 
                           void* stream);
 
 /* neucam_sine_mlp_head_wgrad: ACCUMULATES dW4 [out_dim,512] += dy^T a4 with a4 = sin(30 z3) regenerated from
- *   phase3_16 = the third layer's slice of phase16 (phase16 + 2 * ceil(Q/128)*128*512 elements). */
+ *   phase3_16 = the third layer's slice of phase16 (phase16 + 2 * ceil(Q/128)*128*512 elements; whole 128-row tiles are
+ *   read, as the forward wrote them).  out_dim 3 or 4; phase3_16 and dy 16-byte aligned (cp.async.bulk sources).
+ *   Workspace: NEUCAM_WS_HEAD_WGRAD. */
 int neucam_sine_mlp_head_wgrad(const void* phase3_16, const float* dy, int out_dim, int64_t Q, float* dw4, void* ws,
                                int64_t ws_bytes, void* stream);
 
