@@ -129,6 +129,12 @@ inline int make_tmap_16b_sw64(CUtensorMap* out, const void* base, uint64_t rows,
   return make_tmap_16b_any(out, base, rows, cols, pitch_elems, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// ... and of 16 elements = 32 B, SWIZZLE_32B (piece index XOR-ed with (row >> 2) & 1; tile base 256-byte aligned).
+inline int make_tmap_16b_sw32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                               uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_16b_any(out, base, rows, cols, pitch_elems, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 constexpr int MAX_DEVICES = 64;
 
 inline int sm_count() {

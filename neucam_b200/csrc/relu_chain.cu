@@ -64,7 +64,10 @@ constexpr int NTHREADS = (NEPI_WARPS + 2) * 32;
 constexpr int WARP_PRODUCER = NEPI_WARPS, WARP_MMA = NEPI_WARPS + 1;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_AREADY = 9, BAR_FFULL = 10, BAR_FEMPTY = 11 };
+// ACC: a GEMM's accumulator is complete (MMA -> epilogue).  ACCFREE: all 512 epilogue threads hold their accumulator
+// columns in registers (epilogue -> MMA: the next GEMM may overwrite the accumulator).  AREADY[kb]: k-block kb (64 hidden
+// units) of the next operand tile is written (every epilogue thread owns 16 columns of every k-block).
+enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_ACCFREE = 9, BAR_FFULL = 10, BAR_FEMPTY = 11, BAR_AREADY = 12 };
 
 struct ReluMaps {
   CUtensorMap feat;            // [Q,64] fp16, box 64 x 128 (forward)
@@ -111,25 +114,24 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;"
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// One warp's 32 rows x 32 columns (hi and lo) -> its staging tile -> two TMA stores.  The previous pair of stores
-// must have finished READING the tile before it is rewritten.
-__device__ __forceinline__ void store_chunk_tma(const CUtensorMap* m_hi, const CUtensorMap* m_lo, uint32_t stage,
-                                                uint32_t lane, int col0, int row0, const uint32_t (&w)[16],
-                                                const uint32_t (&wl)[16], bool with_lo) {
-  if (elect_one()) tma_store_wait_read0();
-  __syncwarp();
-  const uint32_t hi = stage + lane * 64u, lo = hi + 2048u;
-  const uint32_t sw = (lane >> 1) & 3u;   // SWIZZLE_64B: piece index ^ ((row >> 1) & 3): bank-conflict free
-#pragma unroll
-  for (uint32_t q = 0; q < 4; ++q) {
-    st_shared_v4(hi + ((q ^ sw) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-    if (with_lo) st_shared_v4(lo + ((q ^ sw) << 4), wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+// One warp's 32 rows x 16 columns of one k-block (hi and lo) -> a 1 KB staging slot each -> TMA stores.  The caller
+// has made sure that earlier stores from the slot have finished READING it.
+__device__ __forceinline__ void store_kb_tma(const CUtensorMap* m_hi, const CUtensorMap* m_lo, uint32_t slot,
+                                             uint32_t lane, int col0, int row0, const uint32_t (&w)[8],
+                                             const uint32_t (&wl)[8], bool with_lo) {
+  const uint32_t hi = slot + lane * 32u, lo = hi + 1024u;
+  const uint32_t sw = (lane >> 2) & 1u;   // SWIZZLE_32B: 16-byte piece index ^ address bit 7 = (row >> 2) & 1
+  st_shared_v4(hi + (sw << 4), w[0], w[1], w[2], w[3]);
+  st_shared_v4(hi + ((sw ^ 1u) << 4), w[4], w[5], w[6], w[7]);
+  if (with_lo) {
+    st_shared_v4(lo + (sw << 4), wl[0], wl[1], wl[2], wl[3]);
+    st_shared_v4(lo + ((sw ^ 1u) << 4), wl[4], wl[5], wl[6], wl[7]);
   }
   fence_proxy_async_smem();
   __syncwarp();
   if (elect_one()) {
-    tma_store_2d(m_hi, stage, col0, row0);
-    if (with_lo) tma_store_2d(m_lo, stage + 2048u, col0, row0);
+    tma_store_2d(m_hi, slot, col0, row0);
+    if (with_lo) tma_store_2d(m_lo, slot + 1024u, col0, row0);
     tma_store_commit();
   }
 }
@@ -176,7 +178,8 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
       mbar_init(bar(BAR_WEMPTY + s), 1);
     }
     mbar_init(bar(BAR_ACC), 1);
-    mbar_init(bar(BAR_AREADY), NEPI_WARPS * 32);
+    mbar_init(bar(BAR_ACCFREE), NEPI_WARPS * 32);
+    for (int k = 0; k < 4; ++k) mbar_init(bar(BAR_AREADY + k), NEPI_WARPS * 32);
     mbar_init(bar(BAR_FFULL), 1);
     mbar_init(bar(BAR_FEMPTY), 1);
     mbar_fence_init();
@@ -222,24 +225,34 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
   } else if (warp == WARP_MMA) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = make_idesc_f16(TILE_M, WID, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
-    uint32_t slot = 0, ph = 0, aph = 0, fph = 0;
+    uint32_t slot = 0, ph = 0, aph = 0, fph = 0, free_ph = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int g = 0; g < p.n_gemm; ++g) {
         stamp(p.trace, 1, 10 * g + 0);
-        mbar_wait_backoff(bar(BAR_AREADY), aph, 32);   // operand tile written (and the accumulator drained)
-        aph ^= 1;
+        // the previous GEMM's accumulator is in the epilogue threads' registers: it may be overwritten.  The operand
+        // k-blocks are waited for one by one below, so this GEMM's first MMAs run under the epilogue that is still
+        // producing the later k-blocks.
+        mbar_wait_backoff(bar(BAR_ACCFREE), free_ph, 32);
+        free_ph ^= 1;
         stamp(p.trace, 1, 10 * g + 1);
+        const bool reads_tile = BWD || g > 0;      // the forward's first GEMM reads the encoded-input tile only
+        uint32_t have = reads_tile ? 0u : 0xFu;    // operand k-blocks already waited for
         if (!BWD && g == 0) {
           mbar_wait(bar(BAR_FFULL), fph);
           fph ^= 1;
         }
         tc_fence_after_sync();
         for (int s = p.stage_begin[g]; s < p.stage_begin[g + 1]; ++s) {
+          const uint32_t srcs[2] = {p.a_src[s], p.a_src2[s]};
+          if (srcs[0] < 4u && !(have & (1u << srcs[0]))) {
+            mbar_wait(bar(BAR_AREADY + srcs[0]), aph);
+            have |= 1u << srcs[0];
+            tc_fence_after_sync();
+          }
           mbar_wait(bar(BAR_WFULL + slot), ph);
           tc_fence_after_sync();
           if (elect_one()) {
             const uint32_t b_addr = base + OFF_W + slot * STAGE_BYTES;
-            const uint32_t srcs[2] = {p.a_src[s], p.a_src2[s]};
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               const uint32_t src = srcs[t];
@@ -260,6 +273,12 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
           __syncwarp();
           if (++slot == NSTAGE) { slot = 0; ph ^= 1; }
         }
+        if (reads_tile) {
+          // a plan that skips a k-block still consumes its phase: the four barriers advance together
+          for (uint32_t k = 0; k < 4; ++k)
+            if (!(have & (1u << k))) mbar_wait(bar(BAR_AREADY + k), aph);
+          aph ^= 1;
+        }
         if (elect_one()) {
           if (!BWD && g == p.feat_last_gemm) umma_commit(bar(BAR_FEMPTY));
           umma_commit(bar(BAR_ACC));
@@ -269,20 +288,59 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
       }
     }
   } else {
-    // ---------------- epilogue warps: thread = (sample row = TMEM lane, column quarter) ----------------
+    // ---------------- epilogue warps: thread = (sample row = TMEM lane, 16 columns of EVERY k-block) ----------------
+    // Thread (quad, sub) owns row quad * 32 + lane and, of each 64-column k-block kb, the 16 columns [64 kb + 16 sub,
+    // +16).  An epilogue first pulls its 64 accumulator values into registers (-> ACCFREE), then turns them into the
+    // next operand tile k-block by k-block (-> AREADY[kb]): the next GEMM's MMAs for k-block 0 run while k-blocks 1..3
+    // are still being produced, instead of a whole epilogue and a whole GEMM taking turns.
     const uint32_t quad = warp & 3u, sub = warp >> 2;
     const uint32_t row = quad * 32u + lane;
     const uint32_t t_row = tmem_base + ((quad * 32u) << 16);
-    const uint32_t c_lo = 2u * sub, c_hi = 2u * sub + 2u;   // this thread's two 32-column chunks
     float4* s_xch = reinterpret_cast<float4*>(sm + OFF_XCH);
     const uint32_t stage = base + OFF_STAGE + warp * 4096u;
+    const bool with_lo = p.store_lo != 0;
     uint32_t acc_ph = 0;
-    if (!BWD) mbar_arrive(bar(BAR_AREADY));   // the first GEMM of the first tile has nothing to wait for
+    mbar_arrive(bar(BAR_ACCFREE));   // the first GEMM of the first tile finds the accumulator free
     float scale = 1.f, inv_scale = 1.f;
     if (BWD) {
       scale = *p.scale;
       inv_scale = 1.f / scale;
     }
+    // one k-block share of this thread: 16 values -> hi / lo fp16 pairs -> operand tile (tensor memory).  The copies for
+    // HBM (the weight-gradient GEMMs' operands) are kept in registers and stored AFTER all four k-blocks have been handed
+    // to the MMA warp: staging, proxy fence and TMA issue stay off the path the next GEMM waits on.
+    auto pack_kb = [&](uint32_t kb, const float (&v)[16], bool to_tmem, bool sat, uint32_t (&w)[8], uint32_t (&wl)[8]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        w[j] = sat ? pack_h2_sat(v[2 * j], v[2 * j + 1]) : pack_h2(v[2 * j], v[2 * j + 1]);
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        wl[j] = sat ? pack_h2_sat(v[2 * j] - hi.x, v[2 * j + 1] - hi.y) : pack_h2(v[2 * j] - hi.x, v[2 * j + 1] - hi.y);
+      }
+      if (to_tmem && !RELU_DBG(1)) {
+        tmem_st_32x32b_x8(t_row + TM_AHI + kb * 32 + sub * 8, w);
+        if (!BWD || p.lo_operand) tmem_st_32x32b_x8(t_row + TM_ALO + kb * 32 + sub * 8, wl);
+      }
+    };
+    // the warp's 32 rows x 4 x 16 columns (hi[, lo]) -> staging -> TMA stores; hi only: four 1 KB slots, one round;
+    // hi + lo: 2 KB per k-block, two rounds of two k-blocks
+    auto store_tile = [&](const uint32_t (&W)[4][8], const uint32_t (&WL)[4][8], int layer, int tile) {
+      if (!p.store) return;
+      const int row0 = tile * TILE_M + (int)quad * 32;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half == 0 || with_lo) {
+          if (elect_one()) tma_store_wait_read0();   // the slots' previous stores have been read out
+          __syncwarp();
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int kb = 2 * half + k2;
+          const uint32_t slot = stage + (with_lo ? (uint32_t)k2 * 2048u : (uint32_t)kb * 1024u);
+          store_kb_tma(&maps.out_hi[layer], &maps.out_lo[layer], slot, lane, kb * 64 + (int)sub * 16, row0, W[kb], WL[kb],
+                       with_lo);
+        }
+      }
+    };
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const long long grow = (long long)tile * TILE_M + row;
       const bool valid = grow < p.Q;
@@ -291,44 +349,38 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         float dp[4] = {0.f, 0.f, 0.f, 0.f};
         if (valid)
           for (int o = 0; o < p.out_dim; ++o) dp[o] = p.dpre[grow * p.out_dim + o] * scale;
-        uint2 gq = make_uint2(0, 0);
-        if (valid) gq = *reinterpret_cast<const uint2*>(p.gates + ((size_t)(p.H - 1) * p.Q + grow) * 8 + c_lo);
-#pragma unroll 1
-        for (uint32_t c = c_lo; c < c_hi; ++c) {
-          const uint32_t gw = (c & 1u) ? gq.y : gq.x;
-          uint32_t w[16], wl[16];
+        const uint16_t* grow_gates = reinterpret_cast<const uint16_t*>(p.gates + ((size_t)(p.H - 1) * p.Q + grow) * 8);
+        uint32_t W[4][8], WL[4][8];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t gw = valid ? grow_gates[4 * kb + sub] : 0u;
+          float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int col = c * 32 + 2 * j;
-            float d0 = 0.f, d1 = 0.f;
+            const int col = kb * 64 + sub * 16 + j;
+            float d = 0.f;
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              d0 = fmaf(dp[o], s_head[o * WID + col], d0);
-              d1 = fmaf(dp[o], s_head[o * WID + col + 1], d1);
-            }
-            if (((gw >> (2 * j)) & 1u) == 0u) d0 = 0.f;       // ReLU closed
-            if (((gw >> (2 * j + 1)) & 1u) == 0u) d1 = 0.f;
-            w[j] = pack_h2_sat(d0, d1);
-            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-            wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
+            for (int o = 0; o < 4; ++o) d = fmaf(dp[o], s_head[o * WID + col], d);
+            v[j] = ((gw >> j) & 1u) ? d : 0.f;       // ReLU closed -> 0
           }
-          tmem_st_32x32b_x16(t_row + TM_AHI + c * 16, w);
-          if (p.lo_operand) tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
-          if (p.store)
-            store_chunk_tma(&maps.out_hi[p.H - 1], &maps.out_lo[p.H - 1], stage, lane, (int)c * 32,
-                            tile * TILE_M + (int)quad * 32, w, wl, p.store_lo != 0);
+          pack_kb((uint32_t)kb, v, true, true, W[kb], WL[kb]);
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive(bar(BAR_AREADY + kb));
         }
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive(bar(BAR_AREADY));
+        store_tile(W, WL, p.H - 1, tile);
       }
       for (int g = 0; g < p.n_gemm; ++g) {
         const bool last = (g == p.n_gemm - 1);
         const bool dfeat_gemm = BWD && last && p.dfeat != nullptr;
         const int layer = BWD ? (p.H - 2 - g) : g;        // layer whose operand tile this epilogue produces
-        uint2 gq = make_uint2(0, 0);
-        if (BWD && !dfeat_gemm && valid)   // fetched before the accumulator wait: the latency hides under the MMAs
-          gq = *reinterpret_cast<const uint2*>(p.gates + ((size_t)layer * p.Q + grow) * 8 + c_lo);
+        const bool produces = BWD ? !last : !last;        // a later GEMM of this tile reads the tile written here
+        uint32_t gw[4] = {0u, 0u, 0u, 0u};
+        if (BWD && !dfeat_gemm && valid) {   // fetched before the accumulator wait: the latency hides under the MMAs
+          const uint16_t* gg = reinterpret_cast<const uint16_t*>(p.gates + ((size_t)layer * p.Q + grow) * 8);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) gw[kb] = gg[4 * kb + sub];
+        }
         if (warp == 0) stamp(p.trace, 2, 10 * g + 0);
         mbar_wait_backoff(bar(BAR_ACC), acc_ph, 64);
         acc_ph ^= 1;
@@ -349,70 +401,64 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             }
           }
           tc_fence_before_sync();
-          continue;   // last GEMM of the tile: the next tile's prologue re-arms BAR_AREADY
+          mbar_arrive(bar(BAR_ACCFREE));
+          continue;   // last GEMM of the tile
         }
+        // the thread's 4 x 16 accumulator columns -> registers; from here on the accumulator is free
+        uint32_t r[4][16];
+        if (!RELU_DBG(8)) {
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) tmem_ld_32x32b_x16(t_row + TM_ACC + kb * 64 + sub * 16, r[kb]);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[kb][j] = 0x3f000000u + kb + j;
+        }
+        tc_fence_before_sync();
+        mbar_arrive(bar(BAR_ACCFREE));
         float yacc[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t* gate_dst = (!BWD && p.gates_out != nullptr && valid) ? p.gates_out + ((size_t)g * p.Q + grow) * 8 : nullptr;
-        // rolled: the unrolled body thrashes the instruction cache (forward measured 225 -> 291 us)
-#pragma unroll 1
-        for (uint32_t c = c_lo; c < c_hi; ++c) {
-          uint32_t r[32];
-          if (!RELU_DBG(8)) {
-            tmem_ld_32x32b_x32(t_row + TM_ACC + c * 32, r);
-            tmem_ld_wait();
+        uint16_t* gate_dst = (!BWD && p.gates_out != nullptr && valid)
+                                 ? reinterpret_cast<uint16_t*>(p.gates_out + ((size_t)g * p.Q + grow) * 8) : nullptr;
+        uint32_t W[4][8], WL[4][8];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          float v[16];
+          if (!BWD) {
+            const float* bz = s_bias + g * WID + kb * 64 + sub * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[kb][j]) + bz[j], 0.f);
+            if (last) {
+              const float* hw = s_head + kb * 64 + sub * 16;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) yacc[o] = fmaf(v[j], hw[o * WID + j], yacc[o]);
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = 0x3f000000u + c + j;
+            for (int j = 0; j < 16; ++j) v[j] = ((gw[kb] >> j) & 1u) ? __uint_as_float(r[kb][j]) : 0.f;
           }
-          uint32_t w[16], wl[16];
-          if (!BWD) {
-            const float* bz = s_bias + g * WID + c * 32;
+          pack_kb((uint32_t)kb, v, produces, BWD, W[kb], WL[kb]);
+          if (produces) {
+            tmem_st_wait();
+            tc_fence_before_sync();
+            mbar_arrive(bar(BAR_AREADY + kb));
+          }
+          if (!BWD && gate_dst != nullptr) {
+            // gate bit = "the STORED fp16 activation is positive"
             uint32_t gbits = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float h0 = fmaxf(__uint_as_float(r[2 * j]) + bz[2 * j], 0.f);
-              const float h1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bz[2 * j + 1], 0.f);
-              if (last) {
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                  yacc[o] = fmaf(h0, s_head[o * WID + c * 32 + 2 * j], yacc[o]);
-                  yacc[o] = fmaf(h1, s_head[o * WID + c * 32 + 2 * j + 1], yacc[o]);
-                }
-              }
-              w[j] = pack_h2(h0, h1);
-              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-              wl[j] = pack_h2(h0 - hi.x, h1 - hi.y);
-              // gate bit = "the STORED activation is positive"
-              gbits |= ((w[j] & 0x7FFFu) != 0u ? 1u : 0u) << (2 * j);
-              gbits |= ((w[j] & 0x7FFF0000u) != 0u ? 1u : 0u) << (2 * j + 1);
+            for (int j = 0; j < 8; ++j) {
+              gbits |= ((W[kb][j] & 0x7FFFu) != 0u ? 1u : 0u) << (2 * j);
+              gbits |= ((W[kb][j] & 0x7FFF0000u) != 0u ? 1u : 0u) << (2 * j + 1);
             }
-            if (gate_dst != nullptr) gate_dst[c] = gbits;
-          } else {
-            const uint32_t gw = (c & 1u) ? gq.y : gq.x;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float d0 = __uint_as_float(r[2 * j]), d1 = __uint_as_float(r[2 * j + 1]);
-              if (((gw >> (2 * j)) & 1u) == 0u) d0 = 0.f;
-              if (((gw >> (2 * j + 1)) & 1u) == 0u) d1 = 0.f;
-              w[j] = pack_h2_sat(d0, d1);
-              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-              wl[j] = pack_h2_sat(d0 - hi.x, d1 - hi.y);
-            }
+            gate_dst[4 * kb + sub] = (uint16_t)gbits;
           }
-          if (!RELU_DBG(1)) {
-            tmem_st_32x32b_x16(t_row + TM_AHI + c * 16, w);
-            if (!BWD || p.lo_operand) tmem_st_32x32b_x16(t_row + TM_ALO + c * 16, wl);
-          } else if (w[3] == 0x12345678u && wl[5] == 0x9abcdef0u) {
-            p.y[0] = 1.f;   // keeps the math alive
-          }
-          if (p.store)
-            store_chunk_tma(&maps.out_hi[layer], &maps.out_lo[layer], stage, lane, (int)c * 32,
-                            tile * TILE_M + (int)quad * 32, w, wl, p.store_lo != 0);
         }
-        tmem_st_wait();
-        tc_fence_before_sync();
+        store_tile(W, WL, layer, tile);
         if (warp == 0) stamp(p.trace, 2, 10 * g + 2);
-        if (!BWD || !last) mbar_arrive(bar(BAR_AREADY));
 
         if (!BWD && last) {
           // output layer: combine the four column quarters of every row in a fixed order (bit-reproducible)
@@ -503,10 +549,10 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   p.feat_last_gemm = 0;
   for (int g = 0; g < n_gemm; ++g) {
     if (act16) {
-      rc = nchost::make_tmap_16b_sw64(&maps.out_hi[g], (const __half*)act16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+      rc = nchost::make_tmap_16b_sw32(&maps.out_hi[g], (const __half*)act16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 16);
       if (rc) return rc;
       if (act_lo16) {
-        rc = nchost::make_tmap_16b_sw64(&maps.out_lo[g], (const __half*)act_lo16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+        rc = nchost::make_tmap_16b_sw32(&maps.out_lo[g], (const __half*)act_lo16 + (size_t)g * Q * WID, (uint64_t)Q, WID, WID, 32, 16);
         if (rc) return rc;
       } else {
         maps.out_lo[g] = maps.out_hi[g];
@@ -590,10 +636,10 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
   p.out_dim = out_dim;
   for (int l = 0; l < MAX_GEMM; ++l) {
     if (l < H) {
-      rc = nchost::make_tmap_16b_sw64(&maps.out_hi[l], (const __half*)dz16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+      rc = nchost::make_tmap_16b_sw32(&maps.out_hi[l], (const __half*)dz16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 16);
       if (rc) return rc;
       if (dz_lo16) {
-        rc = nchost::make_tmap_16b_sw64(&maps.out_lo[l], (const __half*)dz_lo16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 32);
+        rc = nchost::make_tmap_16b_sw32(&maps.out_lo[l], (const __half*)dz_lo16 + (size_t)l * Q * WID, (uint64_t)Q, WID, WID, 32, 16);
         if (rc) return rc;
       } else {
         maps.out_lo[l] = maps.out_hi[l];

@@ -4,6 +4,8 @@ follows modules.py:282-312 and is pinned to the unmodified reference by tests/te
 autograd, for every uv-mapping / alpha network shape the shipped configs build
 (configs/config_{me_dynamic,video_deblur,video_hdr}.txt).
 Tolerances: forward <= 1e-3, gradients <= 1e-2 relative (BASELINE.json north_star)."""
+import zlib
+
 import pytest
 import torch
 
@@ -46,7 +48,7 @@ def run(net, x, upstream, fused, monkeypatch):
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("Q", [1000, 128 * 300 + 5])
 def test_forward_and_gradients_match_oracle(case, Q, monkeypatch):
-    torch.manual_seed(hash(case) % 1000)
+    torch.manual_seed(zlib.crc32(case.encode()) % 1000)   # (str hash() is salted per process: the draw must not be)
     c = CASES[case]
     net = modules.SimpleMLP(hidden_dim=256, num_layer=c["num_layer"], in_dim=3, out_dim=c["out_dim"],
                             use_encoding=c["use_encoding"], num_frequencies=c["num_frequencies"], skip_layer=[4],
