@@ -42,12 +42,13 @@ namespace {
 
 constexpr int WID = 256;
 constexpr int TILE_M = 128;
-constexpr int NSTAGE = 4;                        // weight stages in flight (128 KB)
+constexpr int NSTAGE = 8;                        // weight stages in flight (8 x 16 KB per CTA of the pair)
 constexpr int MAX_GEMM = 7;
 constexpr int MAX_STAGES = 64;
 constexpr int FEAT = 64;
 constexpr uint32_t KB_BYTES = TILE_M * 128;      // one k-block of the operand tile: 128 rows x 64 fp16
-constexpr uint32_t STAGE_BYTES = WID * 128;      // one weight stage: 256 rows x 64 fp16
+constexpr uint32_t STAGE_BYTES = (WID / 2) * 128;   // this CTA's half of a weight stage: 128 of its 256 rows x 64 fp16
+constexpr uint16_t PAIR_MASK = 0x3;
 constexpr uint32_t OFF_F = 0;                                    // encoded-input operand tile (forward)
 constexpr uint32_t OFF_W = OFF_F + KB_BYTES;
 constexpr uint32_t OFF_STAGE = OFF_W + NSTAGE * STAGE_BYTES;     // per epilogue warp: 32 rows x 64 B hi | lo
@@ -57,7 +58,7 @@ constexpr uint32_t TM_ACC = 0, TM_AHI = 256, TM_ALO = 384;
 constexpr uint32_t OFF_HEAD = OFF_BIAS + MAX_GEMM * WID * 4;     // float [4][256] last-layer weights
 constexpr uint32_t OFF_XCH = OFF_HEAD + 4 * WID * 4;              // float4 [3][128]: output-layer partial sums
 constexpr uint32_t OFF_BAR = OFF_XCH + 3 * TILE_M * 16;
-constexpr uint32_t OFF_TMEM = OFF_BAR + 128;
+constexpr uint32_t OFF_TMEM = OFF_BAR + 256;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
 constexpr int NEPI_WARPS = 16;                    // 4 per scheduler: the epilogue is SIMT-latency bound with fewer
 constexpr int NTHREADS = (NEPI_WARPS + 2) * 32;
@@ -67,7 +68,11 @@ static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 // ACC: a GEMM's accumulator is complete (MMA -> epilogue).  ACCFREE: all 512 epilogue threads hold their accumulator
 // columns in registers (epilogue -> MMA: the next GEMM may overwrite the accumulator).  AREADY[kb]: k-block kb (64 hidden
 // units) of the next operand tile is written (every epilogue thread owns 16 columns of every k-block).
-enum { BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_ACC = 8, BAR_ACCFREE = 9, BAR_FFULL = 10, BAR_FEMPTY = 11, BAR_AREADY = 12 };
+// Two CTAs form a pair (cluster of 2, tcgen05 cta_group::2): the leader's MMA thread issues M256 x N256 x K16 MMAs over
+// both CTAs' 128-row tiles (each operand tile in its own CTA's tensor memory) against a weight stage of which each CTA
+// stages half; the peer CTA's MMA warp relays its epilogue's ACCFREE / AREADY / FFULL events to the leader (PEER_*).
+enum { BAR_WFULL = 0, BAR_WEMPTY = 8, BAR_ACC = 16, BAR_ACCFREE = 17, BAR_FFULL = 18, BAR_FEMPTY = 19, BAR_AREADY = 20,
+       BAR_PEER_ACCFREE = 24, BAR_PEER_FFULL = 25, BAR_PEER_AREADY = 26 };
 
 struct ReluMaps {
   CUtensorMap feat;            // [Q,64] fp16, box 64 x 128 (forward)
@@ -155,7 +160,7 @@ __device__ __forceinline__ void stamp(long long* trace, int role, int id) {
 #endif
 
 template <bool BWD>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__ ReluParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -182,22 +187,33 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
     for (int k = 0; k < 4; ++k) mbar_init(bar(BAR_AREADY + k), NEPI_WARPS * 32);
     mbar_init(bar(BAR_FFULL), 1);
     mbar_init(bar(BAR_FEMPTY), 1);
+    mbar_init(bar(BAR_PEER_ACCFREE), 1);
+    mbar_init(bar(BAR_PEER_FFULL), 1);
+    for (int k = 0; k < 4; ++k) mbar_init(bar(BAR_PEER_AREADY + k), 1);
     mbar_fence_init();
   }
   if (warp == WARP_MMA) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
+    tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish_2cta();
   }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before any remote arrive / commit / TMA signal
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const int S = p.stage_begin[p.n_gemm];
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  // a pair walks tiles (2j, 2j+1) + it * gridDim.x together; it runs while its leader's tile exists.  When only the
+  // peer's tile is past the end it runs a phantom tile (all rows invalid: TMA loads zero-fill, stores are clipped).
+  const int lead0 = (int)(blockIdx.x & ~1u);
 
   if (warp == WARP_PRODUCER) {
     // ---------------- TMA producer: encoded-input tile (forward) + the weight stages of every GEMM ----------------
     uint32_t slot = 0, ph = 0, fph = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const uint32_t full0 = mapa_shared(bar(BAR_WFULL), 0);   // the leader's w_full barriers (shared::cluster addresses)
+    for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
+      const int tile = lt + (int)crank;
       if (!BWD) {
         mbar_wait(bar(BAR_FEMPTY), fph ^ 1);
         fph ^= 1;
@@ -212,10 +228,12 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         stamp(p.trace, 0, 100 + s);
         if (elect_one()) {
           if (RELU_DBG(4)) {
-            mbar_arrive(bar(BAR_WFULL + slot));
+            if (leader) mbar_arrive(bar(BAR_WFULL + slot));
           } else {
-            mbar_arrive_expect_tx(bar(BAR_WFULL + slot), STAGE_BYTES);
-            tma_load_2d(base + OFF_W + slot * STAGE_BYTES, &maps.w, bar(BAR_WFULL + slot), 0, s * WID);
+            // the leader's barrier collects both halves of the 256-row weight stage
+            if (leader) mbar_arrive_expect_tx(bar(BAR_WFULL + slot), 2 * STAGE_BYTES);
+            tma_load_2d_2cta(base + OFF_W + slot * STAGE_BYTES, &maps.w, full0 + 8u * slot, 0,
+                             s * WID + (int)crank * (WID / 2));
           }
         }
         __syncwarp();
@@ -223,68 +241,110 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
       }
     }
   } else if (warp == WARP_MMA) {
-    // ---------------- MMA issuer ----------------
-    const uint32_t idesc = make_idesc_f16(TILE_M, WID, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
-    uint32_t slot = 0, ph = 0, aph = 0, fph = 0, free_ph = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      for (int g = 0; g < p.n_gemm; ++g) {
-        stamp(p.trace, 1, 10 * g + 0);
-        // the previous GEMM's accumulator is in the epilogue threads' registers: it may be overwritten.  The operand
-        // k-blocks are waited for one by one below, so this GEMM's first MMAs run under the epilogue that is still
-        // producing the later k-blocks.
-        mbar_wait_backoff(bar(BAR_ACCFREE), free_ph, 32);
-        free_ph ^= 1;
-        stamp(p.trace, 1, 10 * g + 1);
-        const bool reads_tile = BWD || g > 0;      // the forward's first GEMM reads the encoded-input tile only
-        uint32_t have = reads_tile ? 0u : 0xFu;    // operand k-blocks already waited for
-        if (!BWD && g == 0) {
-          mbar_wait(bar(BAR_FFULL), fph);
-          fph ^= 1;
-        }
-        tc_fence_after_sync();
-        for (int s = p.stage_begin[g]; s < p.stage_begin[g + 1]; ++s) {
-          const uint32_t srcs[2] = {p.a_src[s], p.a_src2[s]};
-          if (srcs[0] < 4u && !(have & (1u << srcs[0]))) {
-            mbar_wait(bar(BAR_AREADY + srcs[0]), aph);
-            have |= 1u << srcs[0];
-            tc_fence_after_sync();
+    // ---------------- MMA issuer (leader CTA) / event relay (peer CTA) ----------------
+    if (leader) {
+      const uint32_t idesc = make_idesc_f16(2 * TILE_M, WID, FMT_F16, FMT_F16, MAJOR_K, MAJOR_K);
+      uint32_t slot = 0, ph = 0, aph = 0, fph = 0, free_ph = 0;
+      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
+        for (int g = 0; g < p.n_gemm; ++g) {
+          stamp(p.trace, 1, 10 * g + 0);
+          // the previous GEMM's accumulator is in the epilogue threads' registers (both CTAs): it may be overwritten.
+          // The operand k-blocks are waited for one by one below, so this GEMM's first MMAs run under the epilogue
+          // that is still producing the later k-blocks.
+          mbar_wait_backoff(bar(BAR_ACCFREE), free_ph, 32);
+          mbar_wait(bar(BAR_PEER_ACCFREE), free_ph);
+          free_ph ^= 1;
+          stamp(p.trace, 1, 10 * g + 1);
+          const bool reads_tile = BWD || g > 0;      // the forward's first GEMM reads the encoded-input tile only
+          uint32_t have = reads_tile ? 0u : 0xFu;    // operand k-blocks already waited for
+          if (!BWD && g == 0) {
+            mbar_wait(bar(BAR_FFULL), fph);
+            mbar_wait(bar(BAR_PEER_FFULL), fph);
+            fph ^= 1;
           }
-          mbar_wait(bar(BAR_WFULL + slot), ph);
           tc_fence_after_sync();
-          if (elect_one()) {
-            const uint32_t b_addr = base + OFF_W + slot * STAGE_BYTES;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint32_t src = srcs[t];
-              if (src == 255u) continue;
-              // operand k-block: 64 K-elements = 32 tensor-memory columns; one K16 step = 8 columns
-              const uint32_t a_tm = tmem_base + (src < 4 ? TM_AHI + src * 32 : TM_ALO + (src - 5) * 32);
-#pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16) {
-                if (RELU_DBG(2)) continue;
-                const uint32_t acc = (s > p.stage_begin[g] || t > 0 || k16 > 0) ? 1u : 0u;
-                const uint64_t bd = make_sdesc_sw128(b_addr + k16 * 32, 0, 1024);
-                if (src == 4) umma_f16_ss(tmem_base + TM_ACC, make_sdesc_sw128(base + OFF_F + k16 * 32, 0, 1024), bd, idesc, acc);
-                else          umma_f16_ts(tmem_base + TM_ACC, a_tm + k16 * 8, bd, idesc, acc);
-              }
+          for (int s = p.stage_begin[g]; s < p.stage_begin[g + 1]; ++s) {
+            const uint32_t srcs[2] = {p.a_src[s], p.a_src2[s]};
+            if (srcs[0] < 4u && !(have & (1u << srcs[0]))) {
+              mbar_wait(bar(BAR_AREADY + srcs[0]), aph);
+              mbar_wait(bar(BAR_PEER_AREADY + srcs[0]), aph);
+              have |= 1u << srcs[0];
+              tc_fence_after_sync();
             }
-            umma_commit(bar(BAR_WEMPTY + slot));
+            mbar_wait(bar(BAR_WFULL + slot), ph);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t b_addr = base + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const uint32_t src = srcs[t];
+                if (src == 255u) continue;
+                // operand k-block: 64 K-elements = 32 tensor-memory columns; one K16 step = 8 columns
+                const uint32_t a_tm = tmem_base + (src < 4 ? TM_AHI + src * 32 : TM_ALO + (src - 5) * 32);
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  if (RELU_DBG(2)) continue;
+                  const uint32_t acc = (s > p.stage_begin[g] || t > 0 || k16 > 0) ? 1u : 0u;
+                  const uint64_t bd = make_sdesc_sw128(b_addr + k16 * 32, 0, 1024);
+                  if (src == 4)
+                    umma_f16_ss_2cta(tmem_base + TM_ACC, make_sdesc_sw128(base + OFF_F + k16 * 32, 0, 1024), bd, idesc, acc);
+                  else
+                    umma_f16_ts_2cta(tmem_base + TM_ACC, a_tm + k16 * 8, bd, idesc, acc);
+                }
+              }
+              umma_commit_2cta(bar(BAR_WEMPTY + slot), PAIR_MASK);
+            }
+            __syncwarp();
+            if (++slot == NSTAGE) { slot = 0; ph ^= 1; }
+          }
+          if (reads_tile) {
+            // a plan that skips a k-block still consumes its phase: the four barriers advance together
+            for (uint32_t k = 0; k < 4; ++k)
+              if (!(have & (1u << k))) {
+                mbar_wait(bar(BAR_AREADY + k), aph);
+                mbar_wait(bar(BAR_PEER_AREADY + k), aph);
+              }
+            aph ^= 1;
+          }
+          if (elect_one()) {
+            if (!BWD && g == p.feat_last_gemm) umma_commit_2cta(bar(BAR_FEMPTY), PAIR_MASK);
+            umma_commit_2cta(bar(BAR_ACC), PAIR_MASK);
           }
           __syncwarp();
-          if (++slot == NSTAGE) { slot = 0; ph ^= 1; }
+          stamp(p.trace, 1, 10 * g + 2);
         }
-        if (reads_tile) {
-          // a plan that skips a k-block still consumes its phase: the four barriers advance together
-          for (uint32_t k = 0; k < 4; ++k)
-            if (!(have & (1u << k))) mbar_wait(bar(BAR_AREADY + k), aph);
-          aph ^= 1;
+      }
+    } else {
+      // peer CTA: no MMAs to issue; this warp hands its CTA's epilogue / TMA events to the leader's MMA thread, in
+      // the order the leader waits for them
+      const uint32_t r_free = mapa_shared(bar(BAR_PEER_ACCFREE), 0), r_ffull = mapa_shared(bar(BAR_PEER_FFULL), 0),
+                     r_ready0 = mapa_shared(bar(BAR_PEER_AREADY), 0);
+      uint32_t aph = 0, fph = 0, free_ph = 0;
+      for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
+        for (int g = 0; g < p.n_gemm; ++g) {
+          mbar_wait_backoff(bar(BAR_ACCFREE), free_ph, 32);
+          free_ph ^= 1;
+          tc_fence_after_sync();
+          tc_fence_before_sync();
+          if (elect_one()) mbar_arrive_cluster(r_free);
+          __syncwarp();
+          if (!BWD && g == 0) {
+            mbar_wait(bar(BAR_FFULL), fph);
+            fph ^= 1;
+            if (elect_one()) mbar_arrive_cluster(r_ffull);
+            __syncwarp();
+          }
+          if (BWD || g > 0) {
+            for (uint32_t k = 0; k < 4; ++k) {
+              mbar_wait(bar(BAR_AREADY + k), aph);
+              tc_fence_after_sync();
+              tc_fence_before_sync();
+              if (elect_one()) mbar_arrive_cluster(r_ready0 + 8u * k);
+              __syncwarp();
+            }
+            aph ^= 1;
+          }
         }
-        if (elect_one()) {
-          if (!BWD && g == p.feat_last_gemm) umma_commit(bar(BAR_FEMPTY));
-          umma_commit(bar(BAR_ACC));
-        }
-        __syncwarp();
-        stamp(p.trace, 1, 10 * g + 2);
       }
     }
   } else {
@@ -309,6 +369,8 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
     // one k-block share of this thread: 16 values -> hi / lo fp16 pairs -> operand tile (tensor memory).  The copies for
     // HBM (the weight-gradient GEMMs' operands) are kept in registers and stored AFTER all four k-blocks have been handed
     // to the MMA warp: staging, proxy fence and TMA issue stay off the path the next GEMM waits on.
+    // (Deferring the wait for k-block kb's tensor-memory stores until after the math of kb + 1 was measured: it hides
+    //  the store latency but delays the first hand-off, which is what the next GEMM waits for: forward 152 -> 160 us.)
     auto pack_kb = [&](uint32_t kb, const float (&v)[16], bool to_tmem, bool sat, uint32_t (&w)[8], uint32_t (&wl)[8]) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -316,9 +378,14 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
         wl[j] = sat ? pack_h2_sat(v[2 * j] - hi.x, v[2 * j + 1] - hi.y) : pack_h2(v[2 * j] - hi.x, v[2 * j + 1] - hi.y);
       }
-      if (to_tmem && !RELU_DBG(1)) {
-        tmem_st_32x32b_x8(t_row + TM_AHI + kb * 32 + sub * 8, w);
-        if (!BWD || p.lo_operand) tmem_st_32x32b_x8(t_row + TM_ALO + kb * 32 + sub * 8, wl);
+      if (to_tmem) {
+        if (!RELU_DBG(1)) {
+          tmem_st_32x32b_x8(t_row + TM_AHI + kb * 32 + sub * 8, w);
+          if (!BWD || p.lo_operand) tmem_st_32x32b_x8(t_row + TM_ALO + kb * 32 + sub * 8, wl);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(bar(BAR_AREADY + kb));   // k-block kb is in tensor memory: the MMA warp may use it
       }
     };
     // the warp's 32 rows x 4 x 16 columns (hi[, lo]) -> staging -> TMA stores; hi only: four 1 KB slots, one round;
@@ -341,9 +408,10 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
         }
       }
     };
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int lt = lead0; lt < p.ntiles; lt += gridDim.x) {
+      const int tile = lt + (int)crank;
       const long long grow = (long long)tile * TILE_M + row;
-      const bool valid = grow < p.Q;
+      const bool valid = tile < p.ntiles && grow < p.Q;
       if (BWD) {
         // prologue: dz_{H-1} = mask(h_{H-1}) * (dpre . w_last), scaled, as the first operand tile
         float dp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -364,9 +432,6 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             v[j] = ((gw >> j) & 1u) ? d : 0.f;       // ReLU closed -> 0
           }
           pack_kb((uint32_t)kb, v, true, true, W[kb], WL[kb]);
-          tmem_st_wait();
-          tc_fence_before_sync();
-          mbar_arrive(bar(BAR_AREADY + kb));
         }
         store_tile(W, WL, p.H - 1, tile);
       }
@@ -441,11 +506,6 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
             for (int j = 0; j < 16; ++j) v[j] = ((gw[kb] >> j) & 1u) ? __uint_as_float(r[kb][j]) : 0.f;
           }
           pack_kb((uint32_t)kb, v, produces, BWD, W[kb], WL[kb]);
-          if (produces) {
-            tmem_st_wait();
-            tc_fence_before_sync();
-            mbar_arrive(bar(BAR_AREADY + kb));
-          }
           if (!BWD && gate_dst != nullptr) {
             // gate bit = "the STORED fp16 activation is positive"
             uint32_t gbits = 0;
@@ -491,13 +551,21 @@ relu_chain_kernel(const __grid_constant__ ReluMaps maps, const __grid_constant__
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
+  cluster_sync_all();   // neither CTA exits (or frees tensor memory) while the pair's MMAs / remote arrives are in flight
+  if (warp == WARP_MMA) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 #ifdef NEUCAM_DEBUG
 int g_relu_dbg = 0;
 long long* g_relu_trace = nullptr;
 #endif
+
+// whole CTA pairs; an odd tile count gives one pair a phantom tile
+int pair_grid(int ntiles) {
+  int grid = nchost::sm_count();
+  if (grid > ntiles) grid = ntiles;
+  return (grid + 1) / 2 * 2;
+}
 
 int check_stage_plan(int n_gemm, const int* stage_begin) {
   if (n_gemm < 1 || n_gemm > MAX_GEMM) return 1;
@@ -544,7 +612,7 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
   const int S = stage_begin[n_gemm];
   int rc = nchost::make_tmap_16b(&maps.feat, feat16, (uint64_t)Q, FEAT, FEAT, TILE_M, 64);
   if (rc) return rc;
-  rc = nchost::make_tmap_16b(&maps.w, w_stages, (uint64_t)S * WID, 64, 64, WID, 64);
+  rc = nchost::make_tmap_16b(&maps.w, w_stages, (uint64_t)S * WID, 64, 64, WID / 2, 64);   // a CTA's half of a stage
   if (rc) return rc;
   p.feat_last_gemm = 0;
   for (int g = 0; g < n_gemm; ++g) {
@@ -591,8 +659,7 @@ extern "C" int neucam_relu_mlp_fwd(const void* feat16, int64_t Q, const void* w_
 #endif
   rc = nchost::ensure_dyn_smem((const void*)relu_chain_kernel<false>, (int)SMEM_BYTES);
   if (rc) return rc;
-  const int sms = nchost::sm_count();
-  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  const int grid = pair_grid(p.ntiles);
   relu_chain_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
@@ -617,7 +684,7 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
   ReluParams p{};
   int rc = nchost::make_tmap_16b(&maps.feat, wT_stages, 8 * WID, 64, 64, TILE_M, 64);   // unused in this direction
   if (rc) return rc;
-  rc = nchost::make_tmap_16b(&maps.w, wT_stages, (uint64_t)(n_gemm > 0 ? n_gemm : 1) * 8 * WID, 64, 64, WID, 64);
+  rc = nchost::make_tmap_16b(&maps.w, wT_stages, (uint64_t)(n_gemm > 0 ? n_gemm : 1) * 8 * WID, 64, 64, WID / 2, 64);
   if (rc) return rc;
   // per K-block: a hi stage (x dz_hi and dz_lo) and a lo stage (x dz_hi)
   for (int g = 0; g <= n_gemm; ++g) p.stage_begin[g] = 8 * g;
@@ -658,8 +725,7 @@ extern "C" int neucam_relu_mlp_bwd(const float* dpre, int64_t Q, const void* wT_
   p.dfeat = dfeat;
   rc = nchost::ensure_dyn_smem((const void*)relu_chain_kernel<true>, (int)SMEM_BYTES);
   if (rc) return rc;
-  const int sms = nchost::sm_count();
-  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  const int grid = pair_grid(p.ntiles);
   relu_chain_kernel<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(maps, p);
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
