@@ -5,18 +5,28 @@
 //   forward   feat[Q,64] --W0--> relu --W1--> relu ... --W_{H-1}--> relu --w_last (SIMT)--> tanh|sigmoid
 //   backward  dpre[Q,out] --w_last (SIMT)--> mask --W_{H-1}^T--> mask ... --W_1^T--> mask [--W_0^T--> dfeat]
 //
-// A CTA owns a 128-sample tile for the whole chain.  The activation tile never touches shared memory: it lives in
-// TENSOR MEMORY as the A operand of tcgen05.mma (lane = sample row, two fp16 per 32-bit column: 128 columns for the
-// hi parts, 128 for the lo parts, next to the 256 accumulator columns = all 512 columns of the SM).  Every layer is
-// a sequence of weight "stages" of 256 x 64 fp16 streamed through a 4-deep TMA ring (128 KB of shared memory),
-// accumulated by M128 x N256 x K16 MMAs, drained by 16 epilogue warps (32 sample rows x 64 hidden units each) that
-// apply bias + ReLU (forward) or the forward's gate bits (backward), write the next operand tile back into tensor
-// memory with
-// tcgen05.st and TMA-store it to HBM for the weight-gradient GEMMs through a 4 KB staging tile per warp (32 rows x
-// 32 columns, hi and lo; direct st.global from the row-per-thread layout cost 32 L1 tag requests per instruction and
-// 8 k cycles per GEMM).  The encoded input (raw coordinates + NeRF positional
-// encoding, zero-padded to 64 features) is a 16 KB shared-memory operand tile loaded by TMA, so the first layer and
-// the skip connection are tensor-core GEMMs too.
+// A CTA owns a 128-sample tile for the whole chain; two CTAs form a pair (cluster of 2, tcgen05 cta_group::2).  The
+// activation tile never touches shared memory: it lives in TENSOR MEMORY as the A operand of tcgen05.mma (lane = sample
+// row, two fp16 per 32-bit column: 128 columns for the hi parts, 128 for the lo parts, next to the 256 accumulator
+// columns = all 512 columns of the SM).  Every layer is a sequence of weight "stages" of 256 x 64 fp16 of which each CTA
+// of the pair stages HALF (128 rows, 16 KB) through its 8-deep TMA ring; the leader's MMA thread issues M256 x N256 x K16
+// MMAs over both CTAs' operand tiles (a single-CTA M128 version spent 183 cycles per MMA against 131 at the tensor rate:
+// the full 8 KB B tile per MMA plus the ring refill saturate one SM's shared memory).  16 epilogue warps drain the
+// accumulator, apply bias + ReLU (forward) or the forward's gate bits (backward), write the next operand tile back into
+// tensor memory with tcgen05.st and TMA-store it to HBM for the weight-gradient GEMMs through 1 KB staging slots per
+// warp (32 rows x 16 columns, SWIZZLE_32B; direct st.global from the row-per-thread layout cost 32 L1 tag requests per
+// instruction and 8 k cycles per GEMM).  The encoded input (raw coordinates + NeRF positional encoding, zero-padded to
+// 64 features) is a 16 KB shared-memory operand tile loaded by TMA, so the first layer and the skip connection are
+// tensor-core GEMMs too.
+//
+// Epilogue / MMA overlap.  All 512 TMEM columns hold ONE tile, so a second tile cannot be in flight; instead the NEXT
+// GEMM of the same tile chases the epilogue k-block by k-block.  Thread (lane quadrant, sub) owns 16 columns of EVERY
+// 64-column k-block; an epilogue first pulls its 64 accumulator values into registers (ACCFREE: the accumulator may be
+// overwritten), then produces k-block 0, hands it over (AREADY[0]), k-block 1, ... -- the next GEMM's MMAs for k-block kb
+// run while k-blocks kb+1.. are still being produced, and the copies for HBM are staged and stored after the last
+// hand-off.  The peer CTA's MMA warp has no MMAs to issue; it relays its CTA's ACCFREE / AREADY / feat-tile events to the
+// leader.  Measured (Q = 165 888, 4-layer network): forward 178 -> 152 us, backward 166 -> 133 us against the version
+// whose whole epilogue and whole GEMM took turns (one CTA per tile: 178 -> 156 / 166 -> 140; pairs: the rest).
 //
 // Precision.  A ReLU network's gradient is discontinuous in its pre-activations: with plain fp16 operands the
 // forward's ~4e-4 relative error in z flips ~3e-4 of the ReLU gates against the fp32 reference, which alone puts
@@ -28,11 +38,11 @@
 // and the saved activations are carried as hi + lo pairs as well (three MMAs per product), with a power-of-two
 // loss scale on dz.
 //
-// Warp roles: 0..15 epilogue (warp e: TMEM lane quadrant e & 3 = 32 sample rows, column quarter e >> 2 = 64 of the
-// 256 hidden units), 16 TMA producer, 17 MMA issuer + TMEM owner (control warps have the highest ids).
-// Measured (Q = 165 888, 3 GEMM layers; ReluParams::dbg ablations and neucam_debug_set_relu_trace): forward 214 us with
-// the stores, 174 us without; of those 174 us, 70 us are MMAs (8.8 k cycles per hidden GEMM = 183 cycles per MMA) and
-// 104 us everything else: a tile's epilogue and its MMAs are serial because all 512 TMEM columns hold ONE tile.
+// Warp roles: 0..15 epilogue (warp e: TMEM lane quadrant e & 3 = 32 sample rows, sub = e >> 2 = which 16 columns of every
+// k-block), 16 TMA producer, 17 MMA issuer (leader) / event relay (peer) + TMEM owner (control warps have the highest
+// ids).  What bounds it now: the hand-off latency at the start of every GEMM (accumulator complete -> 64 columns per
+// thread to registers -> first k-block written and published, through the peer relay -> first MMA), ~1.5 us of a
+// ~5.8 us layer; the MMAs themselves are ~2.6 us of it.
 #include "host_util.h"
 #include "tc05.cuh"
 
