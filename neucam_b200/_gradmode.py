@@ -6,6 +6,7 @@ ordinary way."""
 import contextlib
 
 _direct = False
+_step_cache = None     # dict that lives for ONE forward + backward of a step (parameters are constant inside it), or None
 
 
 def direct():
@@ -34,3 +35,21 @@ def targets_of(params):
             return None
         out.append(g)
     return tuple(out)
+
+
+@contextlib.contextmanager
+def one_step():
+    """Scope of one forward + backward of a training step.  Parameters do not change inside it, so operand copies derived
+    from them (the hi / lo fp16 weight stages of a ReLU MLP that the step evaluates twice: on the taps and on the
+    rigidity loss's shifted pixels) are packed once and shared through `step_cache()`.  The step's optimizer kernel writes
+    the parameters without bumping torch's version counters, which is why the cache must not outlive the scope."""
+    global _step_cache
+    prev, _step_cache = _step_cache, {}
+    try:
+        yield
+    finally:
+        _step_cache = prev
+
+
+def step_cache():
+    return _step_cache

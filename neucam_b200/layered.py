@@ -259,7 +259,7 @@ class LayeredTrainStep:
             raise _lib.NeucamNativeError("LayeredTrainStep was built for host-logic tests only; no optimizer state")
         self.params.zero_grad()
         # the flat gradient buffer is preallocated and zeroed: the fused networks' weight-gradient kernels add into it
-        with _gradmode.accumulate_into_param_grad():
+        with _gradmode.accumulate_into_param_grad(), _gradmode.one_step():
             losses = self.forward(model_input, gt, gamma, use_mask)
             losses["total"].backward()
         self._losses = OrderedDict((k, v.detach()) for k, v in losses.items())

@@ -95,15 +95,25 @@ class _ReluMLPFunction(torch.autograd.Function):
         st, a_src, a_src2, begin = forward_plan(H, skips)
         S = len(st)
         n_bwd = 8 * ((H - 1) + (1 if want_dx else 0)) if need_grad else 0
-        w_stages = torch.empty((S * WID, 64), dtype=torch.float16, device=dev)
-        wT_stages = torch.empty((max(n_bwd, 1) * WID, 64), dtype=torch.float16, device=dev) if need_grad else None
-        w_ptrs = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
-        ld = (ctypes.c_int * L)(*[int(w.stride(0)) for w in ws])
-        rc = lib.neucam_relu_mlp_pack(w_ptrs, ld, L, E, S, _u8([s[0] for s in st]), _u8([s[1] for s in st]),
-                                      _u8([s[2] for s in st]), int(want_dx), _lib.ptr(w_stages), _lib.ptr(wT_stages),
-                                      stream)
-        _lib.check(rc, "neucam_relu_mlp_pack")
-        bias = torch.stack(bs[:H]).contiguous()
+        # the packed operand stages depend on the parameters only: inside one step (parameters constant) a network that is
+        # evaluated again -- the rigidity loss's shifted pixels -- re-uses the first call's
+        cache = _gradmode.step_cache()
+        key = ("relu_pack", tuple(w.data_ptr() for w in ws), tuple(b.data_ptr() for b in bs), S, n_bwd, str(dev))
+        packed = cache.get(key) if cache is not None else None
+        if packed is None:
+            w_stages = torch.empty((S * WID, 64), dtype=torch.float16, device=dev)
+            wT_stages = torch.empty((max(n_bwd, 1) * WID, 64), dtype=torch.float16, device=dev) if need_grad else None
+            w_ptrs = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+            ld = (ctypes.c_int * L)(*[int(w.stride(0)) for w in ws])
+            rc = lib.neucam_relu_mlp_pack(w_ptrs, ld, L, E, S, _u8([s[0] for s in st]), _u8([s[1] for s in st]),
+                                          _u8([s[2] for s in st]), int(want_dx), _lib.ptr(w_stages),
+                                          _lib.ptr(wT_stages), stream)
+            _lib.check(rc, "neucam_relu_mlp_pack")
+            bias = torch.stack(bs[:H]).contiguous()
+            if cache is not None:
+                cache[key] = (w_stages, wT_stages, bias)
+        else:
+            w_stages, wT_stages, bias = packed
         w_last, b_last = ws[H].contiguous(), bs[H].contiguous()
         out_dim = w_last.shape[0]
         n_parts = 2 if SPLIT_BACKWARD_OPERANDS else 1
