@@ -265,16 +265,17 @@ static_assert(REC_GD == nchost::WS_TM_GRADS, "workspace layout");
 
 __global__ void __launch_bounds__(PB)
 psf_crf_loss_kernel(MidParams mp, TmParams tm) {
-  __shared__ float s_u[3][TMW], s_a[3][TMW], s_v[3][TMW];
+  // per channel and hidden unit: (u, a, v, v * u) as ONE 16-byte shared-memory word: the CRF and its slope are evaluated
+  // in a single pass over the 128 units (one broadcast LDS.128, FFMA, FMNMX, FFMA, FSETP, predicated FADD per unit)
+  __shared__ float4 s_tm[3][TMW];
   __shared__ float s_x[3][PB + 1], s_g[3][PB + 1];
   __shared__ float s_de[PB];
   __shared__ int s_fr[PB];
   __shared__ float s_red[PB / 32][8];
   const int tid = threadIdx.x;
   for (int c = 0; c < 3; ++c) {
-    s_u[c][tid] = tm.u[c][tid];
-    s_a[c][tid] = tm.a[c][tid];
-    s_v[c][tid] = tm.v[c][tid];
+    const float u = tm.u[c][tid], v = tm.v[c][tid];
+    s_tm[c][tid] = make_float4(u, tm.a[c][tid], v, v * u);
   }
   s_fr[tid] = -1;
   s_de[tid] = 0.f;
@@ -321,9 +322,14 @@ psf_crf_loss_kernel(MidParams mp, TmParams tm) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     lnx[c] = x[c] + LN2 * dt;
-    float o = tm.d[c][0];
+    float o = tm.d[c][0], acc = 0.f;   // CRF output and d(CRF)/d(lnx) = sum over the open units of v * u
 #pragma unroll 8
-    for (int i = 0; i < TMW; ++i) o = fmaf(s_v[c][i], fmaxf(fmaf(s_u[c][i], lnx[c], s_a[c][i]), 0.f), o);
+    for (int i = 0; i < TMW; ++i) {
+      const float4 t = s_tm[c][i];
+      const float pre = fmaf(t.x, lnx[c], t.y);
+      o = fmaf(t.z, fmaxf(pre, 0.f), o);
+      acc += (pre > 0.f) ? t.w : 0.f;
+    }
     ldr[c] = tanhf(o);
     float dl = 0.f;   // d loss / d ldr
     if (is_pixel) {
@@ -348,12 +354,6 @@ psf_crf_loss_kernel(MidParams mp, TmParams tm) {
       dl = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * (1.f / 3.f) * mp.ue_weight;
     }
     g[c] = dl * (1.f - ldr[c] * ldr[c]);
-    float acc = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < TMW; ++i) {
-      const float pre = fmaf(s_u[c][i], lnx[c], s_a[c][i]);
-      acc += (pre > 0.f) ? s_v[c][i] * s_u[c][i] : 0.f;
-    }
     dlnx[c] = g[c] * acc;
     s_x[c][tid] = lnx[c];
     s_g[c][tid] = g[c];
@@ -397,7 +397,7 @@ psf_crf_loss_kernel(MidParams mp, TmParams tm) {
     if (np > PB) np = PB;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float ui = s_u[c][i], ai = s_a[c][i], vi = s_v[c][i];
+      const float ui = s_tm[c][i].x, ai = s_tm[c][i].y, vi = s_tm[c][i].z;
       float gu = 0.f, ga = 0.f, gv = 0.f;
       for (int q = 0; q < np; ++q) {
         const float xx = s_x[c][q], gg = s_g[c][q];
