@@ -404,31 +404,34 @@ wgrad_reduce_kernel(const float* __restrict__ part, ReduceJobs jobs, int splits,
 
 // part[block][c][k] = sum over the block's rows of s[r][c] * x[r][k]   s: fp32 [Q,nc]; nc <= 4; x = fp16 [Q,WIDTH]
 // row-major activations (the ReLU MLPs' last hidden layer).  HBM-bound: 512 threads = row lanes x column groups of 8
-// (one 16-byte load each), 4 rows in flight per thread.
-template <int WIDTH>
-__global__ void __launch_bounds__(512, 1)
-skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int nc, int Q,
+// (one 16-byte load each), 4 rows in flight per thread.  NC = number of output rows (1 alpha, 2 uv): with the
+// accumulators sized for it (instead of always 4) a thread fits 64 registers and TWO blocks share an SM: 64 KB of loads
+// in flight per SM instead of 32.
+template <int WIDTH, int NC>
+__global__ void __launch_bounds__(512, NC <= 2 ? 2 : 1)
+skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, int Q,
                     int rows_per_block, float* __restrict__ part) {
+  constexpr int nc = NC;
   constexpr int UNR = 4;                     // rows in flight per thread
   constexpr int HID = WIDTH;                 // row length of x
   constexpr int CG = WIDTH / 8;              // column groups of 8 (one 16-byte load each)
   constexpr int RL = 512 / CG;               // row lanes
-  extern __shared__ float s_acc_raw[];   // [RL][4][WIDTH] floats = 64 KB (dynamic: above the 48 KB static limit)
-  float (*s_acc)[4][HID] = reinterpret_cast<float (*)[4][HID]>(s_acc_raw);
+  extern __shared__ float s_acc_raw[];   // [RL][NC][WIDTH] floats (dynamic: above the 48 KB static limit for NC > 2)
+  float (*s_acc)[NC][HID] = reinterpret_cast<float (*)[NC][HID]>(s_acc_raw);
   const int r0 = blockIdx.x * rows_per_block;
   int r1 = r0 + rows_per_block;
   if (r1 > Q) r1 = Q;
   // consecutive threads = consecutive column groups of one row
   const int cg = threadIdx.x % CG;
   const int rl = threadIdx.x / CG;
-  float acc[4][8];
+  float acc[NC][8];
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
   for (int rb = r0 + rl; rb < r1; rb += UNR * RL) {
     uint4 v[UNR];
-    float sv[UNR][4];
+    float sv[UNR][NC];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int r = rb + RL * u;
@@ -436,11 +439,11 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
         const size_t off = (size_t)r * HID + cg * 8;
         v[u] = *reinterpret_cast<const uint4*>(x + off);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sv[u][c] = (c < nc) ? __ldg(s + (size_t)r * nc + c) : 0.f;
+        for (int c = 0; c < NC; ++c) sv[u][c] = __ldg(s + (size_t)r * nc + c);
       } else {
         v[u] = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sv[u][c] = 0.f;
+        for (int c = 0; c < NC; ++c) sv[u][c] = 0.f;
       }
     }
 #pragma unroll
@@ -450,7 +453,7 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
       for (int jj = 0; jj < 4; ++jj) {
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[jj]));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
           acc[c][2 * jj] = fmaf(sv[u][c], f.x, acc[c][2 * jj]);
           acc[c][2 * jj + 1] = fmaf(sv[u][c], f.y, acc[c][2 * jj + 1]);
         }
@@ -458,7 +461,7 @@ skinny_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ s, i
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) s_acc[rl][c][cg * 8 + j] = acc[c][j];
   __syncthreads();
@@ -731,25 +734,36 @@ extern "C" int neucam_relu_mlp_wgrad(const void* dz16, const void* dz_lo16, cons
   return launch_wgrad_jobs(jobs, n, Q, scale_dev, ws, ws_bytes, stream);
 }
 
-template <int WIDTH>
-static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, float* out, void* ws, int64_t ws_bytes,
-                         void* stream) {
+template <int WIDTH, int NC>
+static int launch_skinny_nc(const void* x16, const float* s, int64_t Q, float* out, void* ws, int64_t ws_bytes,
+                            void* stream) {
   const int blocks = nchost::sm_count() * 2;
   int rows = (int)((Q + blocks - 1) / blocks);
   if (rows < 32) rows = 32;
   const int grid = (int)((Q + rows - 1) / rows);
   NC_CHECK_WS(ws, ws_bytes, (int64_t)grid * nchost::WS_SKINNY_REC * 4);
-  int rc = nchost::ensure_dyn_smem((const void*)skinny_wgrad_kernel<WIDTH>, 65536);
+  constexpr int SMEM = (512 / (WIDTH / 8)) * NC * WIDTH * 4;
+  int rc = nchost::ensure_dyn_smem((const void*)skinny_wgrad_kernel<WIDTH, NC>, SMEM);
   if (rc) return rc;
-  skinny_wgrad_kernel<WIDTH><<<grid, 512, 65536, (cudaStream_t)stream>>>((const __half*)x16, s, nc, (int)Q, rows,
-                                                                         reinterpret_cast<float*>(ws));
+  skinny_wgrad_kernel<WIDTH, NC><<<grid, 512, SMEM, (cudaStream_t)stream>>>((const __half*)x16, s, (int)Q, rows,
+                                                                           reinterpret_cast<float*>(ws));
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
   nchost::ReduceSegs segs{};
   segs.nseg = 1;
-  segs.seg[0] = {out, 0, nc * WIDTH};
+  segs.seg[0] = {out, 0, NC * WIDTH};
   return nchost::launch_reduce_partials(reinterpret_cast<const float*>(ws), grid, nchost::WS_SKINNY_REC, segs, nullptr,
                                         (cudaStream_t)stream);
+}
+template <int WIDTH>
+static int launch_skinny(const void* x16, const float* s, int nc, int64_t Q, float* out, void* ws, int64_t ws_bytes,
+                         void* stream) {
+  switch (nc) {
+    case 1: return launch_skinny_nc<WIDTH, 1>(x16, s, Q, out, ws, ws_bytes, stream);
+    case 2: return launch_skinny_nc<WIDTH, 2>(x16, s, Q, out, ws, ws_bytes, stream);
+    case 3: return launch_skinny_nc<WIDTH, 3>(x16, s, Q, out, ws, ws_bytes, stream);
+    default: return launch_skinny_nc<WIDTH, 4>(x16, s, Q, out, ws, ws_bytes, stream);
+  }
 }
 
 extern "C" int neucam_sine_mlp_head_wgrad(const void* phase3_16, const float* dy, int out_dim, int64_t Q,
