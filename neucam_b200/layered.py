@@ -319,14 +319,24 @@ class LayeredTrainStep:
         return model_input, {"img": d["img"][None]}
 
     # -- CUDA graph ---------------------------------------------------------------------------------------------
-    def capture(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None):
+    def capture(self, model_input, gt, gamma=None, use_mask=False, lr_groups=None, adopt=False):
         """Captures forward + autograd backward + gradient all-reduce (NCCL collectives are captured like any other
         stream work) + Adam over STATIC device copies of one batch into ONE CUDA graph; `run_resident()` replays it
-        after `load_resident()` refreshed the static buffers.  The rigidity window is decided at capture time."""
+        after `load_resident()` refreshed the static buffers.  The rigidity window is decided at capture time.
+        adopt=True: the given DEVICE tensors become the static buffers themselves (no copies) -- pass what
+        `sample_resident()` returned and every later `sample_resident()` + `run_resident()` is a step on a fresh batch
+        with no host involvement and no staging copy (gamma: a device tensor [1] the caller updates in place)."""
         dev = self.device
-        self._static_in = {k: v.to(dev).clone() for k, v in model_input.items() if torch.is_tensor(v)}
-        self._static_gt = {"img": gt["img"].to(dev).clone()}
-        self._static_gamma = None if gamma is None else torch.as_tensor(gamma, dtype=torch.float32).to(dev).view(1).clone()
+        if adopt:
+            self._static_in = {k: v for k, v in model_input.items() if torch.is_tensor(v)}
+            self._static_gt = {"img": gt["img"]}
+            self._static_gamma = gamma
+            if any(t.device != dev for t in list(self._static_in.values()) + [gt["img"]] + ([gamma] if gamma is not None else [])):
+                raise ValueError("capture(adopt=True) needs tensors that already live on the step's device")
+        else:
+            self._static_in = {k: v.to(dev).clone() for k, v in model_input.items() if torch.is_tensor(v)}
+            self._static_gt = {"img": gt["img"].to(dev).clone()}
+            self._static_gamma = None if gamma is None else torch.as_tensor(gamma, dtype=torch.float32).to(dev).view(1).clone()
         P = self.params
         saved = [t.clone() for t in (P.flat, P.exp_avg, P.exp_avg_sq, P.adam_state)]
         side = torch.cuda.Stream(dev)
