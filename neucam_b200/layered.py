@@ -331,7 +331,8 @@ class LayeredTrainStep:
             self._static_in = {k: v for k, v in model_input.items() if torch.is_tensor(v)}
             self._static_gt = {"img": gt["img"]}
             self._static_gamma = gamma
-            if any(t.device != dev for t in list(self._static_in.values()) + [gt["img"]] + ([gamma] if gamma is not None else [])):
+            given = list(self._static_in.values()) + [gt["img"]] + ([gamma] if gamma is not None else [])
+            if any(t.device.type != dev.type or (dev.index is not None and t.device.index != dev.index) for t in given):
                 raise ValueError("capture(adopt=True) needs tensors that already live on the step's device")
         else:
             self._static_in = {k: v.to(dev).clone() for k, v in model_input.items() if torch.is_tensor(v)}

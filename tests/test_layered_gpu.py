@@ -322,6 +322,38 @@ def test_device_resident_sampler_feeds_the_layered_step():
     assert torch.equal(a, b["coord_idx"]) and 0 <= int(a.min()) and int(a.max()) < n * h * w
 
 
+def test_capture_adopts_the_sampler_buffers():
+    """capture(adopt=True): the on-device sampler writes straight into the graph's static buffers, so sample_resident()
+    + run_resident() is a step on a fresh batch with no staging copy -- same losses and parameters as eager steps on the
+    same sampled batches."""
+    kind = "me_dynamic"
+    shape = SHAPES[kind]
+    B = 640
+    n, h, w = shape
+    g = torch.Generator().manual_seed(5)
+    data = torch.rand(n * h * w, 3, generator=g) * 2 - 1
+    gw = torch.rand(n * h * w, generator=g)
+    results = []
+    for use_graph in (False, True):
+        models, _, opts, _, _ = _setup(kind, B, seed=8)
+        step = LayeredTrainStep(models, shape, opts, device="cuda")
+        step.attach_dataset(data, B, gamma_weights=gw)
+        gamma = torch.tensor([25.0], device="cuda")
+        inp, gt = step.sample_resident(seed=11, step=0)
+        if use_graph:
+            step.capture(inp, gt, gamma, adopt=True)
+        seen = []
+        for i in range(3):
+            step.sample_resident(seed=11, step=i)
+            out = step.run_resident() if use_graph else step.step(inp, gt, gamma)
+            seen.append(out["total"].item())
+        torch.cuda.synchronize()
+        results.append((seen, step.params.flat.clone()))
+    assert results[0][0] == pytest.approx(results[1][0], rel=1e-6)
+    assert len(set(results[1][0])) == 3                      # three different batches went through the graph
+    assert torch.equal(results[0][1], results[1][1])
+
+
 def test_render_layers_matches_a_plain_torch_evaluation(monkeypatch):
     """Full-frame render of a two-layer model set (fused networks under no_grad) against the same modules evaluated
     with plain fp32 torch ops (ReLU chain switched off, sine networks through a torch stand-in)."""
