@@ -14,38 +14,45 @@ constexpr int FEAT = 64;
 constexpr int WID = 256;
 constexpr float PI_F = 3.14159265358979323846f;
 
-// thread = sample
+// thread = sample.  NF (number of frequencies) is a template parameter: with the encoded width E known at compile time
+// the 64 output halves are assembled in registers (a run-time E indexes the arrays dynamically and sends them to local
+// memory: 18 us per call at Q = 165 888 for a 21 MB write).
+template <int NF>
 __global__ void __launch_bounds__(256)
-encode_kernel(const float* __restrict__ x, long long Q, int nf, __half* __restrict__ feat) {
+encode_kernel(const float* __restrict__ x, long long Q, __half* __restrict__ feat) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
-  const int E = 3 + 6 * nf;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  constexpr int E = 3 + 6 * NF;
+  float v[E];
   const float c[3] = {x[3 * q], x[3 * q + 1], x[3 * q + 2]};
   v[0] = c[0]; v[1] = c[1]; v[2] = c[2];
-  for (int i = 0; i < nf; ++i) {
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
     const float w = (float)((double)(1 << i) * 3.14159265358979323846);   // fp32(2^i pi), as torch multiplies
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float a = w * c[j];
-      v[3 + 6 * i + 2 * j] = sinf(a);
-      v[3 + 6 * i + 2 * j + 1] = cosf(a);
+      sincosf(a, &v[3 + 6 * i + 2 * j], &v[3 + 6 * i + 2 * j + 1]);
     }
   }
-  __align__(16) __half out[FEAT];
+  __half out[FEAT];
 #pragma unroll
   for (int j = 0; j < FEAT; ++j) out[j] = __float2half_rn(0.f);
+#pragma unroll
   for (int j = 0; j < E; ++j) {
     const __half hi = __float2half_rn(v[j]);
     out[j] = hi;
     out[E + j] = __float2half_rn(v[j] - __half2float(hi));
   }
   uint4* dst = reinterpret_cast<uint4*>(feat + q * FEAT);
-  const uint4* src = reinterpret_cast<const uint4*>(out);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) dst[j] = src[j];
+  for (int j = 0; j < 8; ++j) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      w4[k] = (uint32_t)__half_as_ushort(out[8 * j + 2 * k]) | ((uint32_t)__half_as_ushort(out[8 * j + 2 * k + 1]) << 16);
+    dst[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
 }
 
 // dx_j = dfeat[j] + sum_i 2^i pi (cos(a) dfeat[sin col] - sin(a) dfeat[cos col]);  only the hi columns carry gradient
@@ -61,7 +68,9 @@ encode_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dfeat, 
     for (int i = 0; i < nf; ++i) {
       const float w = (float)((double)(1 << i) * 3.14159265358979323846);
       const float a = w * c;
-      acc = fmaf(w, cosf(a) * g[3 + 6 * i + 2 * j] - sinf(a) * g[3 + 6 * i + 2 * j + 1], acc);
+      float sn, cs;
+      sincosf(a, &sn, &cs);
+      acc = fmaf(w, cs * g[3 + 6 * i + 2 * j] - sn * g[3 + 6 * i + 2 * j + 1], acc);
     }
     dx[3 * q + j] = acc;
   }
@@ -119,7 +128,15 @@ pack_kernel(const __grid_constant__ PackPlan plan, int n_fwd, __half* __restrict
 // feat16 [Q,64] fp16 from coordinates x [Q,3] fp32; num_freq = 0: no positional encoding (E = 3), else E = 3 + 6 nf.
 extern "C" int neucam_relu_mlp_encode(const float* x, int64_t Q, int num_freq, void* feat16, void* stream) {
   NC_CHECK_ARG(x && feat16 && Q > 0 && num_freq >= 0 && 2 * (3 + 6 * num_freq) <= FEAT);
-  encode_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, Q, num_freq, (__half*)feat16);
+  const unsigned grid = (unsigned)((Q + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (num_freq) {
+    case 0: encode_kernel<0><<<grid, 256, 0, st>>>(x, Q, (__half*)feat16); break;
+    case 1: encode_kernel<1><<<grid, 256, 0, st>>>(x, Q, (__half*)feat16); break;
+    case 2: encode_kernel<2><<<grid, 256, 0, st>>>(x, Q, (__half*)feat16); break;
+    case 3: encode_kernel<3><<<grid, 256, 0, st>>>(x, Q, (__half*)feat16); break;
+    default: encode_kernel<4><<<grid, 256, 0, st>>>(x, Q, (__half*)feat16); break;   // 2 * (3 + 6 nf) <= 64: nf <= 4
+  }
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
   return 0;
