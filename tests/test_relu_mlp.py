@@ -77,6 +77,22 @@ def test_patch_shaped_input_and_no_grad_path():
     assert torch.equal(y, y2.detach())
 
 
+@pytest.mark.parametrize("Q", [1, 127, 129, 128 * 3])
+def test_tiny_and_odd_tile_counts(Q, monkeypatch):
+    """The chain runs on CTA pairs: one tile (the peer CTA walks a phantom tile), an odd tile count, partial tiles."""
+    torch.manual_seed(3)
+    net = modules.SimpleMLP(hidden_dim=256, num_layer=4, in_dim=3, out_dim=2, use_encoding=True, num_frequencies=3,
+                            skip_layer=[4], nonlinear="tanh").cuda()
+    x = (torch.rand(Q, 3, device="cuda") * 2 - 1)
+    upstream = torch.randn(Q, 2, device="cuda") * 1e-4
+    y1, dx1, g1 = run(net, x, upstream, True, monkeypatch)
+    y0, dx0, g0 = run(net, x, upstream, False, monkeypatch)
+    assert rel(y1, y0) < 1e-3
+    assert rel(dx1, dx0) < 1e-2
+    for k in g0:
+        assert rel(g1[k], g0[k]) < 1e-2, (k, rel(g1[k], g0[k]))
+
+
 def test_blur_network_keeps_the_generic_path():
     net = modules.SimpleMLP(hidden_dim=64, num_layer=4, in_dim=3, out_dim=27, use_encoding=False,
                             num_frequencies=7, skip_layer=[4], nonlinear="both")
