@@ -55,17 +55,29 @@ encode_kernel(const float* __restrict__ x, long long Q, __half* __restrict__ fea
   }
 }
 
-// dx_j = dfeat[j] + sum_i 2^i pi (cos(a) dfeat[sin col] - sin(a) dfeat[cos col]);  only the hi columns carry gradient
+// dx_j = dfeat[j] + sum_i 2^i pi (cos(a) dfeat[sin col] - sin(a) dfeat[cos col]);  only the hi columns carry gradient.
+// NF is a template parameter so that the E = 3 + 6 NF gradient values of a row are requested up front (as 16-byte loads
+// where the row allows) instead of one by one between the sincosf calls.
+template <int NF>
 __global__ void __launch_bounds__(256)
-encode_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dfeat, long long Q, int nf,
-                  float* __restrict__ dx) {
+encode_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dfeat, long long Q, float* __restrict__ dx) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
-  const float* g = dfeat + q * FEAT;
+  constexpr int E = 3 + 6 * NF;
+  constexpr int E4 = (E + 3) / 4;
+  float g[4 * E4];
+  const float4* g4 = reinterpret_cast<const float4*>(dfeat + q * FEAT);   // rows are 256-byte aligned
+#pragma unroll
+  for (int k = 0; k < E4; ++k) {
+    const float4 t = g4[k];
+    g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w;
+  }
+#pragma unroll
   for (int j = 0; j < 3; ++j) {
     const float c = x[3 * q + j];
     float acc = g[j];
-    for (int i = 0; i < nf; ++i) {
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
       const float w = (float)((double)(1 << i) * 3.14159265358979323846);
       const float a = w * c;
       float sn, cs;
@@ -146,7 +158,16 @@ extern "C" int neucam_relu_mlp_encode(const float* x, int64_t Q, int num_freq, v
 extern "C" int neucam_relu_mlp_encode_bwd(const float* x, const float* dfeat, int64_t Q, int num_freq, float* dx,
                                           void* stream) {
   NC_CHECK_ARG(x && dfeat && dx && Q > 0 && num_freq >= 0 && 2 * (3 + 6 * num_freq) <= FEAT);
-  encode_bwd_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, dfeat, Q, num_freq, dx);
+  NC_CHECK_ARG(((uintptr_t)dfeat & 15) == 0);
+  const unsigned grid = (unsigned)((Q + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (num_freq) {
+    case 0: encode_bwd_kernel<0><<<grid, 256, 0, st>>>(x, dfeat, Q, dx); break;
+    case 1: encode_bwd_kernel<1><<<grid, 256, 0, st>>>(x, dfeat, Q, dx); break;
+    case 2: encode_bwd_kernel<2><<<grid, 256, 0, st>>>(x, dfeat, Q, dx); break;
+    case 3: encode_bwd_kernel<3><<<grid, 256, 0, st>>>(x, dfeat, Q, dx); break;
+    default: encode_bwd_kernel<4><<<grid, 256, 0, st>>>(x, dfeat, Q, dx); break;
+  }
   NC_CHECK_CUDA(cudaGetLastError());
   NC_COUNT_LAUNCH(1);
   return 0;
