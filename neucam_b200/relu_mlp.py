@@ -98,8 +98,12 @@ class _ReluMLPFunction(torch.autograd.Function):
         # the packed operand stages depend on the parameters only: inside one step (parameters constant) a network that is
         # evaluated again -- the rigidity loss's shifted pixels -- re-uses the first call's
         cache = _gradmode.step_cache()
-        key = ("relu_pack", tuple(w.data_ptr() for w in ws), tuple(b.data_ptr() for b in bs), S, n_bwd, str(dev))
+        # (the backward stages of a call that also needs the input gradient are a superset, in the same order, of those
+        #  of a call that does not: whichever was packed with more serves both)
+        key = ("relu_pack", tuple(w.data_ptr() for w in ws), tuple(b.data_ptr() for b in bs), S, str(dev))
         packed = cache.get(key) if cache is not None else None
+        if packed is not None and packed[3] < n_bwd:
+            packed = None
         if packed is None:
             w_stages = torch.empty((S * WID, 64), dtype=torch.float16, device=dev)
             wT_stages = torch.empty((max(n_bwd, 1) * WID, 64), dtype=torch.float16, device=dev) if need_grad else None
@@ -111,9 +115,9 @@ class _ReluMLPFunction(torch.autograd.Function):
             _lib.check(rc, "neucam_relu_mlp_pack")
             bias = torch.stack(bs[:H]).contiguous()
             if cache is not None:
-                cache[key] = (w_stages, wT_stages, bias)
+                cache[key] = (w_stages, wT_stages, bias, n_bwd)
         else:
-            w_stages, wT_stages, bias = packed
+            w_stages, wT_stages, bias = packed[:3]
         w_last, b_last = ws[H].contiguous(), bs[H].contiguous()
         out_dim = w_last.shape[0]
         n_parts = 2 if SPLIT_BACKWARD_OPERANDS else 1
